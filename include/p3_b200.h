@@ -1,0 +1,207 @@
+/*
+ * p3_b200.h — C ABI of libp3b200.so, the B200-native (sm_100a) batched leaf
+ * evaluator that sits behind p3achygo's `nn::Engine` boundary.
+ *
+ * Every entry point below replaces (or is what a reference-side binding would
+ * call from) one member of the reference interface; the reference location is
+ * cited on each declaration as `cc/...:line`.  Signatures are plain C: opaque
+ * handle, POD structs, pointers and sizes.  No torch / C++ types cross this
+ * boundary.  All functions return 0 on success and a non-zero code on failure;
+ * `p3_last_error()` returns a thread-local description.  The reference treats
+ * engine errors as fatal (CHECK / LOG(FATAL), cc/nn/engine/trt_engine.cc:27-35),
+ * so the C++ adapter in INTEGRATION.md CHECKs every return code.
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * P3_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef P3_B200_H_
+#define P3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants: cc/constants/constants.h:36-72 ------------------------------------------ */
+#define P3_BOARD_LEN 19
+#define P3_NUM_BOARD_LOCS 361          /* kNumBoardLocs */
+#define P3_MAX_MOVES 362               /* kMaxMovesPerPosition (361 + pass) */
+#define P3_NUM_VALUE_LOGITS 2          /* kNumValueLogits */
+#define P3_NUM_SCORE_LOGITS 800        /* kNumScoreLogits */
+#define P3_NUM_LAST_MOVES 5            /* kNumLastMoves */
+#define P3_NUM_PLANES_V1 15            /* kNumInputFeaturePlanesV1 */
+#define P3_NUM_SCALARS_V1 8            /* kNumInputFeatureScalarsV1 */
+#define P3_NUM_PLANES_V0 13            /* kNumInputFeaturePlanesV0 */
+#define P3_NUM_SCALARS_V0 7            /* kNumInputFeatureScalarsV0 */
+#define P3_BLACK 1
+#define P3_WHITE (-1)
+#define P3_EMPTY 0
+#define P3_PASS_ENCODING 361           /* kPassMoveEncoding */
+
+/* ---- error codes ------------------------------------------------------------------------ */
+enum {
+  P3_OK = 0,
+  P3_ERR_INVALID_ARG = 1,
+  P3_ERR_NO_DEVICE = 2,     /* no CUDA device / driver: there is no CPU fallback */
+  P3_ERR_CUDA = 3,          /* a CUDA runtime / driver call failed */
+  P3_ERR_IO = 4,            /* weight file missing / malformed */
+  P3_ERR_UNSUPPORTED = 5    /* model shape / version not supported by the kernels */
+};
+
+/* Arithmetic the tower runs in.  Both accumulate in fp32. */
+enum {
+  P3_PRECISION_FP32 = 0,  /* fp32 operands, CUDA-core FFMA: parity mode (max-abs 1e-3 vs fp32 oracle) */
+  P3_PRECISION_BF16 = 1   /* bf16 operands, tcgen05.mma with fp32 TMEM accumulators: throughput mode   */
+};
+
+/* ---- POD mirrors of the reference structs ------------------------------------------------ */
+
+/* game::Loc, cc/game/loc.h:15-21.  kNoopLoc = {-1,-1}, kPassLoc = {19,0} (loc.h:46-47). */
+typedef struct p3_loc {
+  int32_t i;
+  int32_t j;
+} p3_loc;
+
+/* nn::GoFeatures, cc/nn/engine/go_features.h:12-22 (1860 bytes; game::Color = int8_t). */
+typedef struct p3_go_features {
+  int32_t bsize;
+  int8_t color;
+  float komi;
+  int8_t board[P3_NUM_BOARD_LOCS];
+  p3_loc last_moves[P3_NUM_LAST_MOVES];
+  int8_t stones_atari[P3_NUM_BOARD_LOCS];
+  int8_t stones_two_liberties[P3_NUM_BOARD_LOCS];
+  int8_t stones_three_liberties[P3_NUM_BOARD_LOCS];
+  int8_t stones_laddered[P3_NUM_BOARD_LOCS];
+} p3_go_features;
+
+/* nn::NNInferResult, cc/nn/engine/engine.h:12-20 (7568 bytes, 16-byte aligned). */
+typedef struct p3_infer_result {
+  float move_logits[P3_MAX_MOVES];
+  float move_probs[P3_MAX_MOVES];
+  float value_probs[P3_NUM_VALUE_LOGITS];   /* [0] = P(loss), [1] = P(win), side to move */
+  float score_probs[P3_NUM_SCORE_LOGITS];
+#if defined(__cplusplus)
+  alignas(16)
+#else
+  _Alignas(16)
+#endif
+  float opt_move_probs[P3_MAX_MOVES];
+  float err2_outcome;
+} p3_infer_result;
+
+/* Outputs of python/model.py:1267-1293 that the reference C++ does not read
+ * (cc/nn/engine/trt_names.h:9-21) but that parity tests compare. */
+typedef struct p3_aux_result {
+  float pi_logits_aux[P3_MAX_MOVES];      /* 08 */
+  float pi_logits_soft[P3_MAX_MOVES];     /* 21 */
+  float pi_logits_optimistic[P3_MAX_MOVES]; /* 22 */
+  float outcome_logits[2];                /* 02 */
+  float score_logits[P3_NUM_SCORE_LOGITS]; /* 05 */
+  float gamma;                            /* 07 */
+  float q[3];                             /* 09-11: q6, q16, q50 */
+  float q_err[3];                         /* 12-14 */
+  float q_score[3];                       /* 15-17 */
+  float q_score_err[3];                   /* 18-20 */
+  float mcts_dist_logits[51];             /* 23 */
+  float mcts_dist_probs[51];              /* 24 */
+  float ownership[P3_NUM_BOARD_LOCS];     /* 04 */
+  /* leaf statistics of mcts::LeafEvaluator::InitFields, cc/mcts/leaf_evaluator.cc:83-112 */
+  float value;                            /* p[1] - p[0] */
+  float score_mean;                       /* sum p_i (i - 400 + .5) */
+  float score_var;                        /* E[s^2] - E[s]^2 */
+} p3_aux_result;
+
+typedef struct p3_engine p3_engine;
+
+/* ---- engine lifecycle: nn::CreateEngine, cc/nn/engine/engine_factory.cc:56-73 ------------ */
+
+/* Construct an evaluator.  Replaces `TrtEngine::Create(path, batch_size, version)`
+ * (cc/nn/engine/trt_engine.cc:85-166, :358-362).  `weights_path` is a flat P3W1 weight
+ * file (p3achygo_b200/weights.py; tag tree of python/export_weights.py:16-90).
+ * `feat_version`: 1 = 15 planes / 8 scalars (cc/nn/engine/trt_engine.cc:89-97). */
+int p3_engine_create(const char* weights_path, int device, int batch_size, int feat_version,
+                     int precision, p3_engine** out);
+void p3_engine_destroy(p3_engine* e);
+
+/* nn::Engine::LoadBatch, cc/nn/engine/engine.h:35 (TRT impl cc/nn/engine/trt_engine.cc:222-236).
+ * Thread-safe for distinct `batch_id`; takes no lock; may overlap p3_engine_run_inference
+ * (cc/nn/nn_interface.cc:276). Copies the 1860-byte game state into pinned staging. */
+int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* features);
+
+/* nn::Engine::RunInference, cc/nn/engine/engine.h:36 (cc/nn/engine/trt_engine.cc:238-304).
+ * H2D(game state) -> encode -> tower -> heads -> D2H(results) -> stream sync. Always the full batch. */
+int p3_engine_run_inference(p3_engine* e);
+
+/* nn::Engine::GetBatch, cc/nn/engine/engine.h:37 (cc/nn/engine/trt_engine.cc:306-351).
+ * Fills every field (opt_move_probs is the softmax of 22:pi_logits_optimistic, computed on device
+ * instead of the host core::Softmax of trt_engine.cc:347). Thread-safe for distinct `batch_id`. */
+int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result);
+
+/* nn::Engine::GetOwnership, cc/nn/engine/engine.h:38-39 (TF impl cc/nn/engine/tf_engine.cc:292-299). */
+int p3_engine_get_ownership(p3_engine* e, int batch_id, float own[P3_NUM_BOARD_LOCS]);
+
+/* nn::Engine::kind()/path(), cc/nn/engine/engine.h:33-34. */
+const char* p3_engine_path(const p3_engine* e);
+int p3_engine_batch_size(const p3_engine* e);
+
+/* ---- parity / measurement hooks (no reference counterpart; used by tests and bench) ------ */
+
+/* The feature planes the encode kernel produced for `batch_id` in the last run, in the reference's
+ * host layout: planes NHWC float[19*19*C] and scalars float[S] (cc/nn/engine/go_features.cc:10-68). */
+int p3_engine_get_planes(p3_engine* e, int batch_id, float* planes, float* scalars);
+/* The non-consumed model outputs + leaf statistics for `batch_id` of the last run. */
+int p3_engine_get_aux(p3_engine* e, int batch_id, p3_aux_result* aux);
+/* Run encode -> tower -> heads on the game state already resident in HBM (last H2D), without any
+ * host<->device copy; returns device time in ms measured with CUDA events on the engine's stream. */
+int p3_engine_run_device(p3_engine* e, float* ms_total);
+/* Per-stage device times of the most recent p3_engine_run_device (ms): [0] encode, [1] tower, [2] heads. */
+int p3_engine_stage_ms(p3_engine* e, float ms[3]);
+/* Number of kernel launches one p3_engine_run_inference issues (for bench.py's gpu_launches). */
+int p3_engine_launches_per_run(const p3_engine* e);
+/* Algorithmic FLOPs per position of the loaded net (2*MAC of all convs / denses). */
+double p3_engine_flops_per_position(const p3_engine* e);
+/* Enable (1) / disable (0) CUDA-graph replay of the device-side sequence (default on; env P3_CUDA_GRAPH=0). */
+int p3_engine_set_cuda_graph(p3_engine* e, int enabled);
+
+/* ---- stand-alone kernels ---------------------------------------------------------------- */
+
+/* nn::LoadGoFeatures after the zero fill, cc/nn/engine/go_features.cc:62-68 + trt_engine.cc:230-233,
+ * for `n` positions held in HOST memory: planes float[n,19,19,P], scalars float[n,S] in HOST memory. */
+int p3_encode_features(int device, const p3_go_features* features, int n, int feat_version,
+                       float* planes, float* scalars);
+
+/* Board::GetStonesWithLiberties(1|2|3), cc/game/board.cc:670-690, from raw boards (int8 [n,361], HOST):
+ * out[n,3,361] = colour of every stone whose group has exactly 1 / 2 / 3 liberties. */
+int p3_board_liberties(int device, const int8_t* boards, int n, int8_t* out);
+
+/* Legal-move mask of Game::IsValidMove without history (cc/game/board.cc:595-644 minus superko and
+ * pass-alive): out[n,362] = 1 for pass, and for empty points that are not suicide for `colors[b]`.
+ * `forbidden` (optional, int8 [n,361], non-zero = host-known superko / pass-alive prohibited point). */
+int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const int8_t* forbidden,
+                  int n, uint8_t* out);
+
+/* Gumbel root sampling, cc/mcts/gumbel.cc:283-321 with core::Probability::GumbelSample
+ * (cc/core/probability.cc:12-30) over PCG32 (cc/core/rand.cc:32-71), for `n` independent roots.
+ *   logits [n,362], legal [n,362] (0 = masked: logit -10000, no noise, no PRNG draw),
+ *   prng_state[n]: PRng state_[0] before the call; updated to the state after k_valid draws,
+ *   noise_scaling, k (<= 64).
+ *   out_moves [n,k] (move encodings, -1 padded), out_scores [n,k] (logit + noise), out_kvalid [n]. */
+int p3_gumbel_topk(int device, const float* logits, const uint8_t* legal, uint64_t* prng_state, int n,
+                   float noise_scaling, int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid);
+
+/* One conv layer on the tcgen05 path against the fp32 CUDA-core path, for kernel unit tests:
+ * x [n,361,cin] fp32 NHWC (HOST), w OIHW [cout,cin,ks,ks] fp32 (HOST), y [n,361,cout] fp32 (HOST).
+ * precision selects the kernel. Applies no BN / activation. */
+int p3_conv_test(int device, int precision, const float* x, const float* w, int n, int cin, int cout,
+                 int ksize, float* y);
+
+const char* p3_last_error(void);
+const char* p3_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3_B200_H_ */

@@ -1,0 +1,127 @@
+// Shared declarations of libp3b200: error plumbing, the padded board-row layout every trunk
+// activation uses in HBM, and the launch signatures of the kernels in this directory.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "p3_b200.h"
+
+namespace p3 {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define P3_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      return ::p3::fail(P3_ERR_CUDA, std::string(#call) + " -> " + cudaGetErrorString(_e) +    \
+                                         " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                         \
+  } while (0)
+
+// ---- padded board-row layout ---------------------------------------------------------------
+// A trunk activation of a batch is a 2-D matrix [B * kRowsPerPos, C] (row-major, C contiguous).
+// Point (r, c) of position b lives in row  b*400 + 20 + r*20 + c.  Rows 0..19 of each position
+// and column 19 of every board row hold ZEROS, so a 3x3 tap (dy, dx) of a "same"-padded
+// convolution is the pure row shift  dy*20 + dx : the zero rows/columns are the padding
+// (applied after BN + mish, as the reference's conv(mish(BN(x))) with padding="same" requires,
+// python/model.py:276-281).  361 of 400 rows are live.
+constexpr int kRowsPerPos = 400;
+constexpr int kRowPitch = 20;
+constexpr int kRowBase = 20;
+
+__host__ __device__ inline int board_row(int point) {  // point = r*19 + c  ->  padded row
+  return kRowBase + (point / 19) * kRowPitch + (point % 19);
+}
+__host__ __device__ inline bool row_is_live(int q) {  // q in [0, 400)
+  return q >= kRowBase && ((q - kRowBase) % kRowPitch) != 19;
+}
+__host__ __device__ inline int row_point(int q) {  // live padded row -> point index
+  return ((q - kRowBase) / kRowPitch) * 19 + ((q - kRowBase) % kRowPitch);
+}
+
+// What a conv epilogue writes besides the raw sum.
+enum ActMode : int {
+  kActNone = 0,      // no activated copy
+  kActMishBN = 1,    // act = mish(raw * scale[c] + shift[c])   (the NEXT layer's BN folded in)
+  kActIdentity = 2,  // act = raw (cast to the operand type); input of the head convs
+  kActMish = 3       // act = mish(raw); input of the broadcast mix (python/model.py:574)
+};
+
+struct ConvEpilogue {
+  const float* residual = nullptr;  // [rows, cout] fp32, added to the accumulator (may alias raw_out)
+  float* raw_out = nullptr;         // [rows, cout] fp32 raw sum (residual stream), or null
+  void* act_out = nullptr;          // [rows, cout] activated copy in the operand type, or null
+  const float* scale = nullptr;     // [cout] next layer's folded BN (kActMishBN)
+  const float* shift = nullptr;
+  int act_mode = kActNone;
+};
+
+// ---- fp32 CUDA-core path (conv_fp32.cu) ------------------------------------------------------
+// in [rows, cin] fp32; w [taps][cin][cout] fp32; tap_off[taps] row shifts.
+int conv_fp32_launch(const float* in, const float* w, int rows, int cin, int cout, int taps,
+                     const int* tap_off_host, const ConvEpilogue& ep, cudaStream_t stream);
+
+// ---- tcgen05 path (conv_tc.cu) -----------------------------------------------------------------
+struct TcConvPlan;  // TMA maps + tile config for one layer (opaque; built once per layer)
+int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int cin, int cout,
+                        int taps, const int* tap_off_host, TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* plan);
+int tc_conv_launch(const TcConvPlan* plan, const ConvEpilogue& ep, cudaStream_t stream);
+bool tc_conv_supported(int cin, int cout);
+
+// ---- encode (encode.cu) --------------------------------------------------------------------------
+// feats: device copy of p3_go_features[n]. planes [n,361,P] fp32, scalars [n,S] fp32,
+// masks [n,361] uint16 (bit ch set <=> planes[...,ch] == 1).
+int encode_launch(const p3_go_features* feats, int n, int version, float* planes, float* scalars,
+                  uint16_t* masks, cudaStream_t stream);
+int liberties_launch(const int8_t* boards, int n, int8_t* out, cudaStream_t stream);
+int legal_mask_launch(const int8_t* boards, const int8_t* colors, const int8_t* forbidden, int n,
+                      uint8_t* out, cudaStream_t stream);
+
+// ---- init conv (init_conv.cu) ------------------------------------------------------------------------
+// 5x5 conv over the binary planes as a sparse gather-add of weight rows + game-state dense.
+// wt [25][P][C] fp32, gs_w [S][C], gs_b [C]; writes raw fp32 [n*400, C] and the activated copy.
+int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
+                     const float* wt, const float* gs_w, const float* gs_b, float* raw_out, void* act_out,
+                     bool act_bf16, const float* scale, const float* shift, cudaStream_t stream);
+
+// ---- broadcast mix (broadcast.cu) -------------------------------------------------------------------
+// y[b,q,c] = sum_p W[p,q] * x[b,p,c] + bias[q], then act = mish(BN(y)); x, act in the operand type.
+int broadcast_launch(const void* x, const float* w, const float* bias, int n, int C, void* act_out,
+                     bool bf16, const float* scale, const float* shift, cudaStream_t stream);
+
+// ---- heads (heads.cu) ------------------------------------------------------------------------------------
+struct HeadWeights {
+  int Ch, Cv;
+  // policy
+  const float *gp_scale, *gp_shift;        // BN of g (folded)
+  const float *gp_dense_w, *gp_dense_b;    // [2Ch, Ch], [Ch]
+  const float* moves_w;                    // [4][Ch]: main, aux, soft, optimistic
+  const float *pass_w, *pass_b;            // [2Ch][4], [4]  (bias includes the -3)
+  // value
+  const float *outcome_pre_w, *outcome_pre_b;  // [2Ch, Cv]
+  const float *outcome_w, *outcome_b;          // [Cv, 14]
+  const float *mcts_w, *mcts_b;                // [Cv, 51]
+  const float* own_w;                          // [Ch]
+  const float *gamma_pre_w, *gamma_pre_b;      // [2Ch, Cv]
+  const float *gamma_w, *gamma_b;              // [Cv], [1]
+  const float *score_pre_w, *score_pre_b;      // [2Ch + 1, Cv]
+  const float *score_w, *score_b;              // [Cv], [1]
+  const float* scores;                         // [800]
+};
+// pgv [n*400, 3*Ch] fp32 (p | g | v); results/aux device arrays of n.
+int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
+                 cudaStream_t stream);
+
+// ---- gumbel (gumbel.cu) --------------------------------------------------------------------------------------
+int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
+                  int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid, cudaStream_t stream);
+
+}  // namespace p3

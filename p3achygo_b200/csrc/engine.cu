@@ -1,0 +1,836 @@
+// libp3b200 engine: the C ABI of include/p3_b200.h over the kernels in this directory.
+//
+// One p3_engine = one evaluator on one GPU (the reference runs one engine per process per GPU,
+// python/rl_loop/selfplay.py:51-64): weights resident in HBM, a pinned host staging area the
+// LoadBatch threads write (1860 B of game state per slot instead of the reference's 21 692 B of fp32
+// planes, cc/nn/engine/trt_engine.cc:222-236), and one stream that runs
+//     H2D(game state) -> encode -> init conv -> residual tower -> head conv -> heads -> D2H(results)
+// The device-side sequence is captured once into a CUDA graph and replayed (as the reference does with
+// its TensorRT graph, trt_engine.cc:168-220).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "weights_file.h"
+
+namespace p3 {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+namespace {
+
+int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(P3_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                      "); libp3b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(P3_ERR_INVALID_ARG, "device index out of range");
+  P3_CUDA(cudaSetDevice(device));
+  return P3_OK;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    bytes = n;
+    P3_CUDA(cudaMalloc(&p, n ? n : 1));
+    return P3_OK;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int upload(DevBuf& buf, const void* host, size_t bytes) {
+  int rc = buf.alloc(bytes);
+  if (rc) return rc;
+  P3_CUDA(cudaMemcpy(buf.p, host, bytes, cudaMemcpyHostToDevice));
+  return P3_OK;
+}
+int upload_f32(DevBuf& buf, const std::vector<float>& v) { return upload(buf, v.data(), v.size() * sizeof(float)); }
+int upload_bf16(DevBuf& buf, const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> h(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
+  return upload(buf, h.data(), h.size() * sizeof(__nv_bfloat16));
+}
+
+// conv kernel OIHW [cout][cin][k][k] -> tap-major copies; tap = i*k + j <-> (dy, dx) = (i - k/2, j - k/2)
+// (cross-correlation with "same" padding, Keras Conv2D / python/model.py:108-117).
+void conv_repack(const WeightTensor& w, std::vector<float>& tkn /*[taps][cin][cout]*/,
+                 std::vector<float>& tnk /*[taps][cout][cin]*/) {
+  const int cout = w.dims[0], cin = w.dims[1], k = w.dims[2], taps = k * k;
+  tkn.assign(static_cast<size_t>(taps) * cin * cout, 0.0f);
+  tnk.assign(static_cast<size_t>(taps) * cin * cout, 0.0f);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < taps; ++t) {
+        const float v = w.data[(static_cast<size_t>(o) * cin + c) * taps + t];
+        tkn[(static_cast<size_t>(t) * cin + c) * cout + o] = v;
+        tnk[(static_cast<size_t>(t) * cout + o) * cin + c] = v;
+      }
+}
+std::vector<int> tap_offsets(int k) {
+  std::vector<int> off;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) off.push_back((i - k / 2) * kRowPitch + (j - k / 2));
+  return off;
+}
+
+struct ConvLayer {
+  int cin = 0, cout = 0, ksize = 1, taps = 1;
+  std::vector<int> tap_off;
+  DevBuf w_f32, w_bf16;
+  DevBuf in_scale, in_shift;  // folded BN applied to this layer's INPUT (consumed by the producer's epilogue)
+  bool has_bn = false;
+  TcConvPlan* plan = nullptr;
+  ~ConvLayer() { if (plan) tc_conv_plan_destroy(plan); }
+};
+
+enum StepKind { kStepConv, kStepBroadcast };
+struct Step {
+  StepKind kind = kStepConv;
+  ConvLayer* layer = nullptr;
+  const void* in = nullptr;
+  ConvEpilogue ep;
+  // broadcast
+  const float* bw = nullptr;
+  const float* bb = nullptr;
+  void* b_out = nullptr;
+  const float* b_scale = nullptr;
+  const float* b_shift = nullptr;
+};
+
+}  // namespace
+}  // namespace p3
+
+using namespace p3;
+
+struct p3_engine {
+  std::string path;
+  int device = 0, batch = 0, version = 1, precision = P3_PRECISION_FP32;
+  bool bf16 = false;
+  int C = 0, Cb = 0, Ch = 0, Cv = 0, blocks = 0, nplanes = 15, nscalars = 8;
+  double flops_per_pos = 0.0;
+  int rows = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // host staging (pinned)
+  p3_go_features* h_feats = nullptr;
+  p3_infer_result* h_results = nullptr;
+  // device IO
+  DevBuf d_feats, d_planes, d_scalars, d_masks, d_results, d_aux;
+  // activations
+  DevBuf xraw, actA, actB, actS0, actS1, pgv;
+  // weights
+  DevBuf init_wt, gs_w, gs_b, ident_scale, ident_shift;
+  std::vector<std::unique_ptr<ConvLayer>> layers;
+  std::vector<DevBuf*> owned;
+  std::vector<std::unique_ptr<DevBuf>> misc;
+  HeadWeights hw{};
+  ConvLayer* head_conv = nullptr;
+  const float* first_scale = nullptr;
+  const float* first_shift = nullptr;
+  std::vector<Step> program;
+  Step head_step;
+
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  float stage_ms[3] = {0, 0, 0};
+  int launches = 0;
+  bool aux_host_valid = false;
+
+  ~p3_engine() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    if (h_feats) cudaFreeHost(h_feats);
+    if (h_results) cudaFreeHost(h_results);
+  }
+
+  const float* dev_vec(const std::vector<float>& v, int* rc) {
+    misc.emplace_back(new DevBuf());
+    int r = upload_f32(*misc.back(), v);
+    if (r && rc) *rc = r;
+    return misc.back()->as<float>();
+  }
+
+  int run_conv(const Step& s) {
+    ConvLayer& L = *s.layer;
+    if (bf16)
+      return tc_conv_launch(L.plan, s.ep, stream);
+    return conv_fp32_launch(reinterpret_cast<const float*>(s.in), L.w_f32.as<float>(), rows, L.cin, L.cout, L.taps,
+                            L.tap_off.data(), s.ep, stream);
+  }
+
+  // encode -> init conv -> tower -> head conv -> heads, all on `stream`; optional stage events
+  int enqueue_device(bool with_events) {
+    int rc;
+    if (with_events) P3_CUDA(cudaEventRecord(ev[0], stream));
+    rc = encode_launch(d_feats.as<p3_go_features>(), batch, version, d_planes.as<float>(), d_scalars.as<float>(),
+                       d_masks.as<uint16_t>(), stream);
+    if (rc) return rc;
+    if (with_events) P3_CUDA(cudaEventRecord(ev[1], stream));
+    rc = init_conv_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
+                          init_wt.as<float>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(), actA.p, bf16,
+                          first_scale, first_shift, stream);
+    if (rc) return rc;
+    for (const Step& s : program) {
+      if (s.kind == kStepConv) rc = run_conv(s);
+      else rc = broadcast_launch(s.in, s.bw, s.bb, batch, C, s.b_out, bf16, s.b_scale, s.b_shift, stream);
+      if (rc) return rc;
+    }
+    if (with_events) P3_CUDA(cudaEventRecord(ev[2], stream));
+    rc = run_conv(head_step);
+    if (rc) return rc;
+    rc = heads_launch(pgv.as<float>(), batch, hw, d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(), stream);
+    if (rc) return rc;
+    if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
+    return P3_OK;
+  }
+
+  int ensure_graph() {
+    if (graph_exec || !use_graph) return P3_OK;
+    cudaGraph_t graph = nullptr;
+    P3_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_device(false);
+    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(P3_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(P3_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    return P3_OK;
+  }
+
+  int enqueue_device_maybe_graph() {
+    if (use_graph) {
+      int rc = ensure_graph();
+      if (rc) return rc;
+      P3_CUDA(cudaGraphLaunch(graph_exec, stream));
+      return P3_OK;
+    }
+    return enqueue_device(false);
+  }
+};
+
+namespace p3 {
+namespace {
+
+struct Builder {
+  p3_engine& e;
+  const WeightFile& wf;
+  std::string err;
+
+  const WeightTensor* need(const std::string& name) {
+    const WeightTensor* t = wf.find(name);
+    if (!t && err.empty()) err = "weight file lacks tensor " + name;
+    return t;
+  }
+
+  // folded BN of tag/batch_norm -> (scale, shift)
+  bool fold_bn(const std::string& tag, std::vector<float>& scale, std::vector<float>& shift) {
+    const WeightTensor *g = need(tag + "/batch_norm/gamma"), *b = need(tag + "/batch_norm/beta"),
+                       *m = need(tag + "/batch_norm/moving_mean"), *v = need(tag + "/batch_norm/moving_variance"),
+                       *eps = need(tag + "/batch_norm/epsilon");
+    if (!g || !b || !m || !v || !eps) return false;
+    const size_t n = g->data.size();
+    scale.resize(n);
+    shift.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      // gamma * (x - mean) / sqrt(var + eps) + beta  (python/model.py:231, inference form)
+      const float s = g->data[i] / std::sqrt(v->data[i] + eps->data[0]);
+      scale[i] = s;
+      shift[i] = b->data[i] - m->data[i] * s;
+    }
+    return true;
+  }
+
+  ConvLayer* make_conv(const WeightTensor& w, const std::string& bn_tag, int* rc) {
+    e.layers.emplace_back(new ConvLayer());
+    ConvLayer* L = e.layers.back().get();
+    L->cout = w.dims[0];
+    L->cin = w.dims[1];
+    L->ksize = w.dims[2];
+    L->taps = L->ksize * L->ksize;
+    L->tap_off = tap_offsets(L->ksize);
+    std::vector<float> tkn, tnk;
+    conv_repack(w, tkn, tnk);
+    int r = e.bf16 ? upload_bf16(L->w_bf16, tnk) : upload_f32(L->w_f32, tkn);
+    if (r) { *rc = r; return L; }
+    if (!bn_tag.empty()) {
+      std::vector<float> sc, sh;
+      if (!fold_bn(bn_tag, sc, sh)) { *rc = P3_ERR_IO; return L; }
+      if ((r = upload_f32(L->in_scale, sc)) || (r = upload_f32(L->in_shift, sh))) { *rc = r; return L; }
+      L->has_bn = true;
+    }
+    return L;
+  }
+};
+
+std::string block_tag(int i, bool bcast, bool btl) {
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "model/trunk/%02d:%s", i, bcast ? "broadcast_res" : (btl ? "bottleneck_res" : "classic_res"));
+  return buf;
+}
+std::string sub_tag(const std::string& base, int j, const char* kind) {
+  char buf[32];
+  std::snprintf(buf, sizeof buf, "/%02d:%s", j, kind);
+  return base + buf;
+}
+
+int build_engine(p3_engine& e, const WeightFile& wf) {
+  Builder bd{e, wf, ""};
+  int rc = P3_OK;
+  const int P = e.nplanes = wf.meta_or("ninput_planes", 15);
+  e.nscalars = wf.meta_or("ninput_features", 8);
+  e.blocks = wf.meta_or("nlayers", 0);
+  const int C = e.C = wf.meta_or("nchannels", 0);
+  const int Cb = e.Cb = wf.meta_or("nbtl_channels", 0);
+  const int Ch = e.Ch = wf.meta_or("nhead_channels", 0);
+  const int Cv = e.Cv = wf.meta_or("nval_channels", 0);
+  const int nbtl = wf.meta_or("nbtl", 0);
+  const int ksz = wf.meta_or("conv_size", 3);
+  const int bint = wf.meta_or("broadcast_interval", 1 << 30);
+  const bool btl = wf.meta_or("trunk_block_type", 0) == 0;
+  if (wf.meta_or("board_len", 19) != 19) return fail(P3_ERR_UNSUPPORTED, "only 19x19 boards are supported");
+  if (C <= 0 || e.blocks <= 0 || Ch <= 0 || Cv <= 0) return fail(P3_ERR_IO, "weight file metadata incomplete");
+  if (e.version == 1 && (P != 15 || e.nscalars != 8)) return fail(P3_ERR_UNSUPPORTED, "feature version 1 needs 15 planes / 8 scalars");
+  if (e.version == 0 && (P != 13 || e.nscalars != 7)) return fail(P3_ERR_UNSUPPORTED, "feature version 0 needs 13 planes / 7 scalars");
+  if (e.bf16) {
+    bool ok = tc_conv_supported(C, C) && tc_conv_supported(C, 3 * Ch);
+    if (btl) ok = ok && tc_conv_supported(C, Cb) && tc_conv_supported(Cb, Cb) && tc_conv_supported(Cb, C);
+    if (!ok) return fail(P3_ERR_UNSUPPORTED, "P3_PRECISION_BF16 needs channel counts that are multiples of 64 "
+                                             "(and 3*head_channels a multiple of 32); use P3_PRECISION_FP32 for this net");
+  }
+  const int B = e.batch;
+  const size_t R = e.rows = B * kRowsPerPos;
+  const size_t esz = e.bf16 ? 2 : 4;
+
+  // ---- IO + activation buffers
+  P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e.h_feats), sizeof(p3_go_features) * B));
+  P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e.h_results), sizeof(p3_infer_result) * B));
+  std::memset(e.h_feats, 0, sizeof(p3_go_features) * B);
+  for (int b = 0; b < B; ++b) { e.h_feats[b].bsize = 19; e.h_feats[b].color = P3_BLACK; }
+  std::memset(e.h_results, 0, sizeof(p3_infer_result) * B);
+  if ((rc = e.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
+  P3_CUDA(cudaMemcpy(e.d_feats.p, e.h_feats, sizeof(p3_go_features) * B, cudaMemcpyHostToDevice));
+  if ((rc = e.d_planes.alloc(sizeof(float) * B * 361 * P))) return rc;
+  if ((rc = e.d_scalars.alloc(sizeof(float) * B * e.nscalars))) return rc;
+  if ((rc = e.d_masks.alloc(sizeof(uint16_t) * B * 361))) return rc;
+  if ((rc = e.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
+  if ((rc = e.d_aux.alloc(sizeof(p3_aux_result) * B))) return rc;
+  if ((rc = e.xraw.alloc(sizeof(float) * R * C))) return rc;
+  if ((rc = e.actA.alloc(esz * R * C))) return rc;
+  if ((rc = e.actB.alloc(esz * R * C))) return rc;
+  if (btl) {
+    if ((rc = e.actS0.alloc(esz * R * Cb))) return rc;
+    if ((rc = e.actS1.alloc(esz * R * Cb))) return rc;
+    P3_CUDA(cudaMemset(e.actS0.p, 0, e.actS0.bytes));
+    P3_CUDA(cudaMemset(e.actS1.p, 0, e.actS1.bytes));
+  }
+  if ((rc = e.pgv.alloc(sizeof(float) * R * 3 * Ch))) return rc;
+  P3_CUDA(cudaMemset(e.xraw.p, 0, e.xraw.bytes));
+  P3_CUDA(cudaMemset(e.actA.p, 0, e.actA.bytes));
+  P3_CUDA(cudaMemset(e.actB.p, 0, e.actB.bytes));
+  P3_CUDA(cudaMemset(e.pgv.p, 0, e.pgv.bytes));
+
+  // ---- init conv (model.py:1152-1161, 1230-1237): OIHW [C][P][5][5] -> [25][P][C]
+  {
+    const WeightTensor* w = bd.need("model/init_conv/conv/kernel");
+    const WeightTensor* gw = bd.need("model/init_game_state/dense/kernel");
+    const WeightTensor* gb = bd.need("model/init_game_state/dense/bias");
+    if (!w || !gw || !gb) return fail(P3_ERR_IO, bd.err);
+    if (w->dims.size() != 4 || static_cast<int>(w->dims[0]) != C || static_cast<int>(w->dims[1]) != P || w->dims[2] != 5)
+      return fail(P3_ERR_UNSUPPORTED, "init conv must be 5x5, planes -> channels");
+    std::vector<float> wt(static_cast<size_t>(25) * P * C);
+    for (int o = 0; o < C; ++o)
+      for (int c = 0; c < P; ++c)
+        for (int t = 0; t < 25; ++t) wt[(static_cast<size_t>(t) * P + c) * C + o] = w->data[(static_cast<size_t>(o) * P + c) * 25 + t];
+    if ((rc = upload_f32(e.init_wt, wt)) || (rc = upload_f32(e.gs_w, gw->data)) || (rc = upload_f32(e.gs_b, gb->data))) return rc;
+  }
+  {
+    std::vector<float> ones(std::max(C, 3 * Ch), 1.0f), zeros(std::max(C, 3 * Ch), 0.0f);
+    if ((rc = upload_f32(e.ident_scale, ones)) || (rc = upload_f32(e.ident_shift, zeros))) return rc;
+  }
+
+  // ---- trunk (model.py:1000-1047): build layers, then wire the program
+  struct BlockDesc { bool bcast; std::vector<ConvLayer*> convs; const float* bw = nullptr; const float* bb = nullptr; };
+  std::vector<BlockDesc> blocks(e.blocks);
+  for (int i = 0; i < e.blocks; ++i) {
+    const bool bcast = (i % bint) == bint - 1;  // model.py:1003
+    blocks[i].bcast = bcast;
+    const std::string bt = block_tag(i, bcast, btl);
+    std::vector<int> idx;
+    if (bcast) idx = {0, 2};
+    else if (btl) for (int j = 0; j < nbtl + 2; ++j) idx.push_back(j);
+    else idx = {0, 1};
+    for (int j : idx) {
+      const std::string tag = sub_tag(bt, j, "conv_block");
+      const WeightTensor* w = bd.need(tag + "/conv/kernel");
+      if (!w) return fail(P3_ERR_IO, bd.err);
+      ConvLayer* L = bd.make_conv(*w, tag, &rc);
+      if (rc) return rc == P3_ERR_IO ? fail(rc, bd.err) : rc;
+      blocks[i].convs.push_back(L);
+    }
+    if (bcast) {
+      const std::string tag = sub_tag(bt, 1, "broadcast");
+      const WeightTensor *w = bd.need(tag + "/dense/kernel"), *b = bd.need(tag + "/dense/bias");
+      if (!w || !b) return fail(P3_ERR_IO, bd.err);
+      blocks[i].bw = e.dev_vec(w->data, &rc);
+      blocks[i].bb = e.dev_vec(b->data, &rc);
+      if (rc) return rc;
+    }
+    (void)ksz;
+  }
+  // head conv: conv_p | conv_g | conv_v as one [3Ch][C][1][1] kernel (model.py:784-785, 889)
+  {
+    const WeightTensor *wp = bd.need("model/policy_head/conv_policy/conv/kernel"),
+                       *wg = bd.need("model/policy_head/conv_global/conv/kernel"),
+                       *wv = bd.need("model/value_head/conv_value/conv/kernel");
+    if (!wp || !wg || !wv) return fail(P3_ERR_IO, bd.err);
+    WeightTensor cat;
+    cat.dims = {static_cast<uint32_t>(3 * Ch), static_cast<uint32_t>(C), 1, 1};
+    cat.data.reserve(static_cast<size_t>(3) * Ch * C);
+    for (const WeightTensor* t : {wp, wg, wv}) cat.data.insert(cat.data.end(), t->data.begin(), t->data.end());
+    e.head_conv = bd.make_conv(cat, "", &rc);
+    if (rc) return rc;
+  }
+
+  // wire: `cur` holds the activated input of the next block
+  void* cur = e.actA.p;
+  void* other = e.actB.p;
+  e.first_scale = blocks[0].convs[0]->in_scale.as<float>();
+  e.first_shift = blocks[0].convs[0]->in_shift.as<float>();
+  auto add_conv = [&](ConvLayer* L, const void* in, const float* residual, float* raw, void* act, int mode,
+                      const ConvLayer* next) -> int {
+    Step s;
+    s.kind = kStepConv;
+    s.layer = L;
+    s.in = in;
+    s.ep.residual = residual;
+    s.ep.raw_out = raw;
+    s.ep.act_out = act;
+    s.ep.act_mode = mode;
+    if (mode == kActMishBN) {
+      s.ep.scale = next->in_scale.as<float>();
+      s.ep.shift = next->in_shift.as<float>();
+    }
+    if (e.bf16) {
+      int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(in), L->w_bf16.as<__nv_bfloat16>(), e.rows,
+                                  L->cin, L->cout, L->taps, L->tap_off.data(), &L->plan);
+      if (r) return r;
+    }
+    e.program.push_back(s);
+    return P3_OK;
+  };
+  for (int i = 0; i < e.blocks; ++i) {
+    BlockDesc& bk = blocks[i];
+    const bool last_block = i == e.blocks - 1;
+    const ConvLayer* next_first = last_block ? nullptr : blocks[i + 1].convs[0];
+    // what the block's final conv writes besides the raw residual stream
+    int end_mode = last_block ? (e.bf16 ? kActIdentity : kActNone) : kActMishBN;
+    void* end_act = (last_block && !e.bf16) ? nullptr : other;
+    if (bk.bcast) {  // BroadcastResidualBlock, model.py:583-607
+      if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMish, nullptr))) return rc;
+      Step s;
+      s.kind = kStepBroadcast;
+      s.in = other;
+      s.bw = bk.bw;
+      s.bb = bk.bb;
+      s.b_out = cur;
+      s.b_scale = bk.convs[1]->in_scale.as<float>();
+      s.b_shift = bk.convs[1]->in_shift.as<float>();
+      e.program.push_back(s);
+      if ((rc = add_conv(bk.convs[1], cur, e.xraw.as<float>(), e.xraw.as<float>(), end_act, end_mode, next_first))) return rc;
+    } else if (btl) {  // BottleneckResidualConvBlock, model.py:372-412
+      void* s0 = e.actS0.p;
+      void* s1 = e.actS1.p;
+      const int nc = static_cast<int>(bk.convs.size());
+      if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, s0, kActMishBN, bk.convs[1]))) return rc;
+      for (int j = 1; j < nc - 1; ++j) {
+        if ((rc = add_conv(bk.convs[j], s0, nullptr, nullptr, s1, kActMishBN, bk.convs[j + 1]))) return rc;
+        std::swap(s0, s1);
+      }
+      if ((rc = add_conv(bk.convs[nc - 1], s0, e.xraw.as<float>(), e.xraw.as<float>(), end_act, end_mode, next_first))) return rc;
+    } else {  // ClassicResidualBlock, model.py:330-354
+      if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMishBN, bk.convs[1]))) return rc;
+      // second conv reads `other`; `cur` is free again and becomes the block output
+      if ((rc = add_conv(bk.convs[1], other, e.xraw.as<float>(), e.xraw.as<float>(), last_block && !e.bf16 ? nullptr : cur,
+                         end_mode, next_first))) return rc;
+      continue;  // output already in `cur`
+    }
+    std::swap(cur, other);
+  }
+  // heads read the RAW trunk output (no leading BN: model.py:783-786, 887-889)
+  {
+    const void* head_in = e.bf16 ? cur : e.xraw.p;
+    Step s;
+    s.kind = kStepConv;
+    s.layer = e.head_conv;
+    s.in = head_in;
+    s.ep.raw_out = e.pgv.as<float>();
+    if (e.bf16) {
+      int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(head_in), e.head_conv->w_bf16.as<__nv_bfloat16>(),
+                                  e.rows, C, 3 * Ch, 1, e.head_conv->tap_off.data(), &e.head_conv->plan);
+      if (r) return r;
+    }
+    e.head_step = s;
+  }
+
+  // ---- head weights
+  {
+    HeadWeights& hw = e.hw;
+    hw.Ch = Ch;
+    hw.Cv = Cv;
+    const std::string ph = "model/policy_head", vh = "model/value_head";
+    std::vector<float> sc, sh;
+    if (!bd.fold_bn(ph + "/global_pool_bias", sc, sh)) return fail(P3_ERR_IO, bd.err);
+    hw.gp_scale = e.dev_vec(sc, &rc);
+    hw.gp_shift = e.dev_vec(sh, &rc);
+    auto T = [&](const std::string& n) { return bd.need(n); };
+    const WeightTensor *gdw = T(ph + "/global_pool_bias/dense/kernel"), *gdb = T(ph + "/global_pool_bias/dense/bias"),
+                       *mv = T(ph + "/conv_moves/conv/kernel"), *sm = T(ph + "/conv_soft_moves/conv/kernel"),
+                       *om = T(ph + "/conv_optimistic_moves/conv/kernel"), *pw = T(ph + "/dense_pass/dense/kernel"),
+                       *pb = T(ph + "/dense_pass/dense/bias"), *spw = T(ph + "/dense_soft_pass/dense/kernel"),
+                       *spb = T(ph + "/dense_soft_pass/dense/bias"), *opw = T(ph + "/dense_optimistic_pass/dense/kernel"),
+                       *opb = T(ph + "/dense_optimistic_pass/dense/bias");
+    const WeightTensor *opre = T(vh + "/dense_outcome_pre/dense/kernel"), *opreb = T(vh + "/dense_outcome_pre/dense/bias"),
+                       *ow = T(vh + "/dense_outcome/dense/kernel"), *ob = T(vh + "/dense_outcome/dense/bias"),
+                       *mw = T(vh + "/dense_mcts_dist/dense/kernel"), *mb = T(vh + "/dense_mcts_dist/dense/bias"),
+                       *own = T(vh + "/ownership/conv/kernel"), *gpw = T(vh + "/dense_gamma_pre/dense/kernel"),
+                       *gpb = T(vh + "/dense_gamma_pre/dense/bias"), *gw = T(vh + "/dense_gamma/dense/kernel"),
+                       *gb = T(vh + "/dense_gamma/dense/bias"), *spre = T(vh + "/dense_scores_pre/dense/kernel"),
+                       *spreb = T(vh + "/dense_scores_pre/dense/bias"), *sw = T(vh + "/dense_scores/dense/kernel"),
+                       *sb = T(vh + "/dense_scores/dense/bias"), *scores = T(vh + "/scores");
+    if (!bd.err.empty()) return fail(P3_ERR_IO, bd.err);
+    hw.gp_dense_w = e.dev_vec(gdw->data, &rc);
+    hw.gp_dense_b = e.dev_vec(gdb->data, &rc);
+    std::vector<float> moves(4 * Ch);  // conv_moves OIHW [2][Ch] rows 0,1; soft row 2; optimistic row 3
+    for (int c = 0; c < Ch; ++c) {
+      moves[c] = mv->data[c];
+      moves[Ch + c] = mv->data[Ch + c];
+      moves[2 * Ch + c] = sm->data[c];
+      moves[3 * Ch + c] = om->data[c];
+    }
+    hw.moves_w = e.dev_vec(moves, &rc);
+    std::vector<float> passw(2 * Ch * 4), passb(4);
+    for (int i = 0; i < 2 * Ch; ++i) {
+      passw[i * 4 + 0] = pw->data[i * 2 + 0];
+      passw[i * 4 + 1] = pw->data[i * 2 + 1];
+      passw[i * 4 + 2] = spw->data[i];
+      passw[i * 4 + 3] = opw->data[i];
+    }
+    passb[0] = pb->data[0] - 3.0f;  // model.py:795
+    passb[1] = pb->data[1] - 3.0f;
+    passb[2] = spb->data[0] - 3.0f;  // model.py:803
+    passb[3] = opb->data[0] - 3.0f;  // model.py:805
+    hw.pass_w = e.dev_vec(passw, &rc);
+    hw.pass_b = e.dev_vec(passb, &rc);
+    hw.outcome_pre_w = e.dev_vec(opre->data, &rc);
+    hw.outcome_pre_b = e.dev_vec(opreb->data, &rc);
+    hw.outcome_w = e.dev_vec(ow->data, &rc);
+    hw.outcome_b = e.dev_vec(ob->data, &rc);
+    hw.mcts_w = e.dev_vec(mw->data, &rc);
+    hw.mcts_b = e.dev_vec(mb->data, &rc);
+    hw.own_w = e.dev_vec(own->data, &rc);
+    hw.gamma_pre_w = e.dev_vec(gpw->data, &rc);
+    hw.gamma_pre_b = e.dev_vec(gpb->data, &rc);
+    hw.gamma_w = e.dev_vec(gw->data, &rc);
+    hw.gamma_b = e.dev_vec(gb->data, &rc);
+    hw.score_pre_w = e.dev_vec(spre->data, &rc);
+    hw.score_pre_b = e.dev_vec(spreb->data, &rc);
+    hw.score_w = e.dev_vec(sw->data, &rc);
+    hw.score_b = e.dev_vec(sb->data, &rc);
+    hw.scores = e.dev_vec(scores->data, &rc);
+    if (rc) return rc;
+  }
+
+  // algorithmic FLOPs
+  {
+    const double Pn = 361.0;
+    double mac = 25.0 * P * C * Pn + static_cast<double>(e.nscalars) * C;
+    for (int i = 0; i < e.blocks; ++i) {
+      if (blocks[i].bcast) mac += 2.0 * C * C * Pn + C * Pn * Pn;
+      else if (btl) mac += (2.0 * C * Cb + nbtl * 9.0 * Cb * Cb) * Pn;
+      else mac += 18.0 * C * C * Pn;
+    }
+    mac += 2.0 * C * Ch * Pn + 4.0 * Ch * Pn + 2.0 * Ch * (Ch + 4);
+    mac += C * Ch * Pn + Ch * Pn + 2.0 * 2 * Ch * Cv + Cv * 66.0 + 2.0 * Ch * Cv + 2.0 * 800 * Cv;
+    e.flops_per_pos = 2.0 * mac;
+  }
+  e.launches = 2 + static_cast<int>(e.program.size()) + 2;
+  return P3_OK;
+}
+
+}  // namespace
+}  // namespace p3
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* p3_last_error(void) { return p3::g_last_error.c_str(); }
+const char* p3_version(void) { return "p3achygo-b200 0.1 (sm_100a)"; }
+
+int p3_engine_create(const char* weights_path, int device, int batch_size, int feat_version, int precision,
+                     p3_engine** out) {
+  if (!weights_path || !out || batch_size <= 0) return fail(P3_ERR_INVALID_ARG, "p3_engine_create: bad argument");
+  if (precision != P3_PRECISION_FP32 && precision != P3_PRECISION_BF16)
+    return fail(P3_ERR_INVALID_ARG, "p3_engine_create: unknown precision");
+  if (feat_version != 0 && feat_version != 1) return fail(P3_ERR_INVALID_ARG, "p3_engine_create: feature version must be 0 or 1");
+  *out = nullptr;
+  WeightFile wf;
+  std::string err = wf.load(weights_path);
+  if (!err.empty()) return fail(P3_ERR_IO, err);
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::unique_ptr<p3_engine> e(new p3_engine());
+  e->path = weights_path;
+  e->device = device;
+  e->batch = batch_size;
+  e->version = feat_version;
+  e->precision = precision;
+  e->bf16 = precision == P3_PRECISION_BF16;
+  if (const char* g = std::getenv("P3_CUDA_GRAPH")) e->use_graph = std::atoi(g) != 0;
+  P3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev) P3_CUDA(cudaEventCreate(&ev));
+  rc = build_engine(*e, wf);
+  if (rc) return rc;
+  P3_CUDA(cudaDeviceSynchronize());
+  // warm-up run (the reference warms up and captures at construction, trt_engine.cc:162-166)
+  rc = e->enqueue_device(false);
+  if (rc) return rc;
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  rc = e->ensure_graph();
+  if (rc) return rc;
+  *out = e.release();
+  return P3_OK;
+}
+
+void p3_engine_destroy(p3_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  delete e;
+}
+
+int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* features) {
+  if (!e || !features || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "load_batch: bad argument");
+  std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
+  return P3_OK;
+}
+
+int p3_engine_run_inference(p3_engine* e) {
+  if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
+  int rc = e->enqueue_device_maybe_graph();
+  if (rc) return rc;
+  P3_CUDA(cudaMemcpyAsync(e->h_results, e->d_results.p, sizeof(p3_infer_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  return P3_OK;
+}
+
+int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result) {
+  if (!e || !result || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_batch: bad argument");
+  std::memcpy(result, &e->h_results[batch_id], sizeof(p3_infer_result));
+  return P3_OK;
+}
+
+int p3_engine_get_aux(p3_engine* e, int batch_id, p3_aux_result* aux) {
+  if (!e || !aux || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_aux: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaMemcpy(aux, e->d_aux.as<p3_aux_result>() + batch_id, sizeof(p3_aux_result), cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_engine_get_ownership(p3_engine* e, int batch_id, float own[P3_NUM_BOARD_LOCS]) {
+  if (!e || !own || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_ownership: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  const char* src = reinterpret_cast<const char*>(e->d_aux.as<p3_aux_result>() + batch_id) + offsetof(p3_aux_result, ownership);
+  P3_CUDA(cudaMemcpy(own, src, sizeof(float) * P3_NUM_BOARD_LOCS, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+const char* p3_engine_path(const p3_engine* e) { return e ? e->path.c_str() : ""; }
+int p3_engine_batch_size(const p3_engine* e) { return e ? e->batch : 0; }
+
+int p3_engine_get_planes(p3_engine* e, int batch_id, float* planes, float* scalars) {
+  if (!e || !planes || !scalars || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_planes: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  const size_t pn = static_cast<size_t>(361) * e->nplanes;
+  P3_CUDA(cudaMemcpy(planes, e->d_planes.as<float>() + batch_id * pn, sizeof(float) * pn, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(scalars, e->d_scalars.as<float>() + static_cast<size_t>(batch_id) * e->nscalars,
+                     sizeof(float) * e->nscalars, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_engine_run_device(p3_engine* e, float* ms_total) {
+  if (!e) return fail(P3_ERR_INVALID_ARG, "run_device: null engine");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaEventRecord(e->ev[0], e->stream));
+  int rc = e->enqueue_device_maybe_graph();
+  if (rc) return rc;
+  P3_CUDA(cudaEventRecord(e->ev[3], e->stream));
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0.0f;
+  P3_CUDA(cudaEventElapsedTime(&ms, e->ev[0], e->ev[3]));
+  if (ms_total) *ms_total = ms;
+  return P3_OK;
+}
+
+int p3_engine_stage_ms(p3_engine* e, float ms[3]) {
+  if (!e || !ms) return fail(P3_ERR_INVALID_ARG, "stage_ms: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  int rc = e->enqueue_device(true);
+  if (rc) return rc;
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < 3; ++i) P3_CUDA(cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]));
+  return P3_OK;
+}
+
+int p3_engine_launches_per_run(const p3_engine* e) { return e ? e->launches : 0; }
+double p3_engine_flops_per_position(const p3_engine* e) { return e ? e->flops_per_pos : 0.0; }
+
+int p3_engine_set_cuda_graph(p3_engine* e, int enabled) {
+  if (!e) return fail(P3_ERR_INVALID_ARG, "set_cuda_graph: null engine");
+  e->use_graph = enabled != 0;
+  return P3_OK;
+}
+
+// ---- stand-alone kernels -------------------------------------------------------------------------
+int p3_encode_features(int device, const p3_go_features* features, int n, int feat_version, float* planes,
+                       float* scalars) {
+  if (!features || !planes || !scalars || n < 0) return fail(P3_ERR_INVALID_ARG, "encode_features: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return P3_OK;
+  const int np = feat_version == 0 ? P3_NUM_PLANES_V0 : P3_NUM_PLANES_V1;
+  const int ns = feat_version == 0 ? P3_NUM_SCALARS_V0 : P3_NUM_SCALARS_V1;
+  DevBuf df, dp, ds;
+  if ((rc = upload(df, features, sizeof(p3_go_features) * n))) return rc;
+  if ((rc = dp.alloc(sizeof(float) * n * 361 * np)) || (rc = ds.alloc(sizeof(float) * n * ns))) return rc;
+  if ((rc = encode_launch(df.as<p3_go_features>(), n, feat_version, dp.as<float>(), ds.as<float>(), nullptr, 0))) return rc;
+  P3_CUDA(cudaMemcpy(planes, dp.p, dp.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(scalars, ds.p, ds.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_board_liberties(int device, const int8_t* boards, int n, int8_t* out) {
+  if (!boards || !out || n < 0) return fail(P3_ERR_INVALID_ARG, "board_liberties: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return P3_OK;
+  DevBuf db, dout;
+  if ((rc = upload(db, boards, static_cast<size_t>(n) * 361)) || (rc = dout.alloc(static_cast<size_t>(n) * 3 * 361))) return rc;
+  if ((rc = liberties_launch(db.as<int8_t>(), n, dout.as<int8_t>(), 0))) return rc;
+  P3_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const int8_t* forbidden, int n, uint8_t* out) {
+  if (!boards || !colors || !out || n < 0) return fail(P3_ERR_INVALID_ARG, "legal_mask: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return P3_OK;
+  DevBuf db, dc, dfb, dout;
+  if ((rc = upload(db, boards, static_cast<size_t>(n) * 361)) || (rc = upload(dc, colors, n)) ||
+      (rc = dout.alloc(static_cast<size_t>(n) * 362)))
+    return rc;
+  if (forbidden && (rc = upload(dfb, forbidden, static_cast<size_t>(n) * 361))) return rc;
+  if ((rc = legal_mask_launch(db.as<int8_t>(), dc.as<int8_t>(), forbidden ? dfb.as<int8_t>() : nullptr, n, dout.as<uint8_t>(), 0)))
+    return rc;
+  P3_CUDA(cudaMemcpy(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_gumbel_topk(int device, const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
+                   int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid) {
+  if (!logits || !legal || !prng_state || !out_moves || !out_scores || !out_kvalid || n < 0)
+    return fail(P3_ERR_INVALID_ARG, "gumbel_topk: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return P3_OK;
+  DevBuf dl, dm, dst, dmv, dsc, dkv;
+  if ((rc = upload(dl, logits, sizeof(float) * n * 362)) || (rc = upload(dm, legal, static_cast<size_t>(n) * 362)) ||
+      (rc = upload(dst, prng_state, sizeof(uint64_t) * n)) || (rc = dmv.alloc(sizeof(int32_t) * n * k)) ||
+      (rc = dsc.alloc(sizeof(float) * n * k)) || (rc = dkv.alloc(sizeof(int32_t) * n)))
+    return rc;
+  if ((rc = gumbel_launch(dl.as<float>(), dm.as<uint8_t>(), dst.as<uint64_t>(), n, noise_scaling, k, dmv.as<int32_t>(),
+                          dsc.as<float>(), dkv.as<int32_t>(), 0)))
+    return rc;
+  P3_CUDA(cudaMemcpy(out_moves, dmv.p, dmv.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(out_scores, dsc.p, dsc.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(out_kvalid, dkv.p, dkv.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(prng_state, dst.p, dst.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_conv_test(int device, int precision, const float* x, const float* w, int n, int cin, int cout, int ksize, float* y) {
+  if (!x || !w || !y || n <= 0 || (ksize != 1 && ksize != 3)) return fail(P3_ERR_INVALID_ARG, "conv_test: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  const bool bf16 = precision == P3_PRECISION_BF16;
+  if (bf16 && !tc_conv_supported(cin, cout)) return fail(P3_ERR_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 path");
+  const size_t R = static_cast<size_t>(n) * kRowsPerPos;
+  std::vector<float> xp(R * cin, 0.0f);
+  for (int b = 0; b < n; ++b)
+    for (int p = 0; p < 361; ++p)
+      std::memcpy(&xp[(static_cast<size_t>(b) * kRowsPerPos + board_row(p)) * cin], &x[(static_cast<size_t>(b) * 361 + p) * cin],
+                  sizeof(float) * cin);
+  WeightTensor wt;
+  wt.dims = {static_cast<uint32_t>(cout), static_cast<uint32_t>(cin), static_cast<uint32_t>(ksize), static_cast<uint32_t>(ksize)};
+  wt.data.assign(w, w + static_cast<size_t>(cout) * cin * ksize * ksize);
+  std::vector<float> tkn, tnk;
+  conv_repack(wt, tkn, tnk);
+  std::vector<int> off = tap_offsets(ksize);
+  DevBuf dx, dw, dy;
+  if ((rc = dy.alloc(sizeof(float) * R * cout))) return rc;
+  ConvEpilogue ep;
+  ep.raw_out = dy.as<float>();
+  if (bf16) {
+    if ((rc = upload_bf16(dx, xp)) || (rc = upload_bf16(dw, tnk))) return rc;
+    TcConvPlan* plan = nullptr;
+    if ((rc = tc_conv_plan_create(dx.as<__nv_bfloat16>(), dw.as<__nv_bfloat16>(), static_cast<int>(R), cin, cout, ksize * ksize,
+                                  off.data(), &plan)))
+      return rc;
+    rc = tc_conv_launch(plan, ep, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    tc_conv_plan_destroy(plan);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(P3_ERR_CUDA, std::string("tc_conv kernel: ") + cudaGetErrorString(se));
+  } else {
+    if ((rc = upload_f32(dx, xp)) || (rc = upload_f32(dw, tkn))) return rc;
+    if ((rc = conv_fp32_launch(dx.as<float>(), dw.as<float>(), static_cast<int>(R), cin, cout, ksize * ksize, off.data(), ep, 0)))
+      return rc;
+    P3_CUDA(cudaDeviceSynchronize());
+  }
+  std::vector<float> yp(R * cout);
+  P3_CUDA(cudaMemcpy(yp.data(), dy.p, dy.bytes, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < n; ++b)
+    for (int p = 0; p < 361; ++p)
+      std::memcpy(&y[(static_cast<size_t>(b) * 361 + p) * cout], &yp[(static_cast<size_t>(b) * kRowsPerPos + board_row(p)) * cout],
+                  sizeof(float) * cout);
+  return P3_OK;
+}
+
+}  // extern "C"

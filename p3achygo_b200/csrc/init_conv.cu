@@ -1,0 +1,111 @@
+// First layer of the tower (python/model.py:1230-1237):
+//     x = conv5x5(planes, 15 -> C, same, no bias) + dense(game_state, 8 -> C)   (broadcast over HW)
+// The planes are exactly {0,1}, so the 375-deep contraction is a sparse gather-add: for every
+// in-board tap, add the weight rows of the set plane bits.  Reading the 15-bit masks the encode
+// kernel produced (722 B / position) instead of fp32 planes (21 660 B) keeps this layer off HBM;
+// a typical point touches ~15 of the 375 rows.  fp32 accumulation in both precision modes.
+//
+// One CTA per position, one warp per point (strided), lanes over channels.  Writes the raw fp32
+// residual stream and the activated copy  mish(BN_0(x))  that the first trunk conv consumes, both in
+// the padded board-row layout (common.cuh), including the zero halo rows.
+#include "common.cuh"
+#include "math.cuh"
+
+namespace p3 {
+namespace {
+
+constexpr int kMaxCPerLane = 12;  // C <= 384
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+init_conv_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ scalars, int nplanes, int nscalars,
+                 int C, const float* __restrict__ wt, const float* __restrict__ gs_w, const float* __restrict__ gs_b,
+                 float* __restrict__ raw_out, void* __restrict__ act_out, const float* __restrict__ scale,
+                 const float* __restrict__ shift) {
+  extern __shared__ float s_gs[];  // [C] game-state bias of this position
+  __shared__ uint16_t s_mask[P3_NUM_BOARD_LOCS];
+  const int b = blockIdx.x;
+  for (int p = threadIdx.x; p < P3_NUM_BOARD_LOCS; p += blockDim.x)
+    s_mask[p] = masks[static_cast<size_t>(b) * P3_NUM_BOARD_LOCS + p];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = gs_b[c];
+    for (int s = 0; s < nscalars; ++s) acc = fmaf(scalars[b * nscalars + s], gs_w[s * C + c], acc);
+    s_gs[c] = acc;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int per_lane = (C + 31) / 32;
+  const size_t row0 = static_cast<size_t>(b) * kRowsPerPos;
+  __nv_bfloat16* act_bf = reinterpret_cast<__nv_bfloat16*>(act_out);
+  float* act_f = reinterpret_cast<float*>(act_out);
+
+  for (int q = warp; q < kRowsPerPos; q += nwarps) {
+    const size_t row = row0 + q;
+    if (!row_is_live(q)) {  // zero halo rows
+      for (int k = 0; k < per_lane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) {
+          raw_out[row * C + c] = 0.0f;
+          if (kBf16) act_bf[row * C + c] = __float2bfloat16(0.0f);
+          else act_f[row * C + c] = 0.0f;
+        }
+      }
+      continue;
+    }
+    const int p = row_point(q), r = p / 19, cc = p % 19;
+    float acc[kMaxCPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxCPerLane; ++k) acc[k] = 0.0f;
+    for (int di = 0; di < 5; ++di) {
+      const int rr = r + di - 2;
+      if (rr < 0 || rr >= 19) continue;
+      for (int dj = 0; dj < 5; ++dj) {
+        const int c2 = cc + dj - 2;
+        if (c2 < 0 || c2 >= 19) continue;
+        uint32_t m = s_mask[rr * 19 + c2];
+        const float* wtap = wt + static_cast<size_t>(di * 5 + dj) * nplanes * C;
+        while (m) {
+          const int ch = __ffs(m) - 1;
+          m &= m - 1;
+          const float* wr = wtap + static_cast<size_t>(ch) * C;
+#pragma unroll
+          for (int k = 0; k < kMaxCPerLane; ++k) {
+            const int c = lane + 32 * k;
+            if (k < per_lane && c < C) acc[k] += __ldg(wr + c);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxCPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (k < per_lane && c < C) {
+        const float x = acc[k] + s_gs[c];
+        raw_out[row * C + c] = x;
+        const float a = mish_f32<!kBf16>(fmaf(x, scale[c], shift[c]));
+        if (kBf16) act_bf[row * C + c] = __float2bfloat16(a);
+        else act_f[row * C + c] = a;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
+                     const float* wt, const float* gs_w, const float* gs_b, float* raw_out, void* act_out,
+                     bool act_bf16, const float* scale, const float* shift, cudaStream_t stream) {
+  if (C > 32 * kMaxCPerLane) return fail(P3_ERR_UNSUPPORTED, "init_conv: C > 384");
+  const size_t smem = sizeof(float) * C;
+  if (act_bf16)
+    init_conv_kernel<true><<<n, 256, smem, stream>>>(masks, scalars, nplanes, nscalars, C, wt, gs_w, gs_b, raw_out,
+                                                     act_out, scale, shift);
+  else
+    init_conv_kernel<false><<<n, 256, smem, stream>>>(masks, scalars, nplanes, nscalars, C, wt, gs_w, gs_b, raw_out,
+                                                      act_out, scale, shift);
+  P3_CUDA(cudaGetLastError());
+  return P3_OK;
+}
+
+}  // namespace p3

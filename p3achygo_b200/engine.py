@@ -1,0 +1,222 @@
+"""Host-side mirror of the reference's engine interface for the B200 evaluator.
+
+Same names, argument meaning and error behaviour as the reference's C++ ``nn::Engine``
+(``cc/nn/engine/engine.h:22-43``) and factory (``cc/nn/engine/engine_factory.cc:16-73``), so the
+parity tests read like the reference's own engine tests (``cc/nn/engine/benchmark_engine.cc:77-109``).
+Everything computes in libp3b200.so through the C ABI (``include/p3_b200.h``); PyTorch is not involved.
+The C++ adapter a reference maintainer would add (``B200Engine : nn::Engine``) is in INTEGRATION.md and
+mirrored by ``p3achygo_b200/host/b200_engine.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, NUM_LOCS, NUM_MOVES, PRECISION_BF16,
+                   PRECISION_FP32, P3Error, check, lib, ptr)
+
+
+class Kind(enum.IntEnum):
+    """``nn::Engine::Kind`` (engine.h:24-30) plus the one new kind this build adds."""
+    kUnknown = 0
+    kTrt = 1
+    kTF = 2
+    kTFTrt = 3
+    kTFXla = 4
+    kB200 = 5
+
+
+def KindToString(kind: Kind) -> str:
+    """engine.h:45-57"""
+    return {Kind.kTrt: "TensorRT", Kind.kTF: "TF", Kind.kTFTrt: "TF-TRT", Kind.kTFXla: "TF-XLA",
+            Kind.kB200: "B200"}.get(kind, "??")
+
+
+def KindFromEnginePath(path: str) -> Kind:
+    """engine_factory.cc:16-35, with ``.p3w`` (flat P3W1 weight file) -> kB200."""
+    if os.path.isfile(path):
+        ext = os.path.splitext(path)[1]
+        if ext == ".trt":
+            return Kind.kTrt
+        if ext == ".pb":
+            return Kind.kTFXla
+        if ext == ".p3w":
+            return Kind.kB200
+        return Kind.kUnknown
+    if os.path.basename(os.path.normpath(path)) == "_trt":
+        return Kind.kTFTrt
+    return Kind.kTF
+
+
+def GetVersionFromModelPath(path: str) -> int:
+    """engine_factory.cc:37-54: a ``VERSION`` file beside the model selects the feature version (default 1)."""
+    parent = os.path.dirname(path) if os.path.isfile(path) else path
+    vf = os.path.join(parent, "VERSION")
+    if os.path.isfile(vf):
+        try:
+            with open(vf) as f:
+                return int(f.read().split()[0])
+        except (ValueError, IndexError):
+            pass
+    return 1
+
+
+class B200Engine:
+    """``nn::Engine`` implemented by libp3b200 (replaces ``TrtEngineImpl``, trt_engine.cc:37-84)."""
+
+    def __init__(self, path: str, batch_size: int, version: int = 1, precision: Optional[int] = None, device: int = 0):
+        if precision is None:
+            precision = PRECISION_BF16 if os.environ.get("P3_PRECISION", "bf16") == "bf16" else PRECISION_FP32
+        self._h = ctypes.c_void_p()
+        self._path = path
+        self.batch_size = batch_size
+        self.version = version
+        self.precision = precision
+        self.num_planes = 13 if version == 0 else 15
+        self.num_scalars = 7 if version == 0 else 8
+        check(lib.p3_engine_create(path.encode(), device, batch_size, version, precision, ctypes.byref(self._h)))
+
+    # -- nn::Engine ---------------------------------------------------------------------------
+    def kind(self) -> Kind:
+        return Kind.kB200
+
+    def path(self) -> str:
+        return self._path
+
+    def LoadBatch(self, batch_id: int, features) -> None:
+        """engine.h:35. ``features``: a ``GoFeatures`` ctypes struct or a 1-record GO_FEATURES_DTYPE array."""
+        if isinstance(features, np.ndarray) or isinstance(features, np.void):
+            arr = np.ascontiguousarray(np.asarray(features, dtype=GO_FEATURES_DTYPE).reshape(1))
+            check(lib.p3_engine_load_batch(self._h, batch_id, ptr(arr)))
+        else:
+            check(lib.p3_engine_load_batch(self._h, batch_id, ctypes.cast(ctypes.byref(features), ctypes.c_void_p)))
+
+    def RunInference(self) -> None:
+        """engine.h:36"""
+        check(lib.p3_engine_run_inference(self._h))
+
+    def GetBatch(self, batch_id: int) -> np.ndarray:
+        """engine.h:37: returns one INFER_RESULT_DTYPE record (the caller-owned NNInferResult)."""
+        out = np.zeros(1, dtype=INFER_RESULT_DTYPE)
+        check(lib.p3_engine_get_batch(self._h, batch_id, ptr(out)))
+        return out[0]
+
+    def GetOwnership(self, batch_id: int) -> np.ndarray:
+        """engine.h:38-39"""
+        own = np.zeros(NUM_LOCS, dtype=np.float32)
+        check(lib.p3_engine_get_ownership(self._h, batch_id, ptr(own)))
+        return own
+
+    # -- parity / measurement hooks -------------------------------------------------------------
+    def LoadBatchAll(self, feats: np.ndarray) -> None:
+        for b in range(min(len(feats), self.batch_size)):
+            check(lib.p3_engine_load_batch(self._h, b, ctypes.c_void_p(feats[b:b + 1].ctypes.data)))
+
+    def GetPlanes(self, batch_id: int):
+        planes = np.zeros((19, 19, self.num_planes), dtype=np.float32)
+        scalars = np.zeros(self.num_scalars, dtype=np.float32)
+        check(lib.p3_engine_get_planes(self._h, batch_id, ptr(planes), ptr(scalars)))
+        return planes, scalars
+
+    def GetAux(self, batch_id: int) -> np.ndarray:
+        out = np.zeros(1, dtype=AUX_RESULT_DTYPE)
+        check(lib.p3_engine_get_aux(self._h, batch_id, ptr(out)))
+        return out[0]
+
+    def RunDevice(self) -> float:
+        ms = ctypes.c_float()
+        check(lib.p3_engine_run_device(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def StageMs(self):
+        arr = (ctypes.c_float * 3)()
+        check(lib.p3_engine_stage_ms(self._h, ctypes.byref(arr)))
+        return list(arr)
+
+    def launches_per_run(self) -> int:
+        return lib.p3_engine_launches_per_run(self._h)
+
+    def flops_per_position(self) -> float:
+        return lib.p3_engine_flops_per_position(self._h)
+
+    def set_cuda_graph(self, enabled: bool) -> None:
+        check(lib.p3_engine_set_cuda_graph(self._h, int(enabled)))
+
+    def close(self) -> None:
+        if self._h:
+            lib.p3_engine_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def CreateEngine(kind: Kind, path: str, batch_size: int, version: int, **kw) -> B200Engine:
+    """engine_factory.cc:56-73. Only the kind this build provides can be constructed here."""
+    if kind == Kind.kB200:
+        return B200Engine(path, batch_size, version, **kw)
+    raise RuntimeError("Unknown Engine Kind.")  # LOG(FATAL) in the reference
+
+
+# ---- stand-alone kernels ----------------------------------------------------------------------
+def encode_features(feats: np.ndarray, version: int = 1, device: int = 0):
+    feats = np.ascontiguousarray(feats, dtype=GO_FEATURES_DTYPE)
+    n = len(feats)
+    npl, ns = (13, 7) if version == 0 else (15, 8)
+    planes = np.zeros((n, 19, 19, npl), dtype=np.float32)
+    scalars = np.zeros((n, ns), dtype=np.float32)
+    check(lib.p3_encode_features(device, ptr(feats), n, version, ptr(planes), ptr(scalars)))
+    return planes, scalars
+
+
+def board_liberties(boards: np.ndarray, device: int = 0) -> np.ndarray:
+    boards = np.ascontiguousarray(boards, dtype=np.int8).reshape(-1, NUM_LOCS)
+    out = np.zeros((len(boards), 3, NUM_LOCS), dtype=np.int8)
+    check(lib.p3_board_liberties(device, ptr(boards), len(boards), ptr(out)))
+    return out
+
+
+def legal_mask(boards: np.ndarray, colors: np.ndarray, forbidden: Optional[np.ndarray] = None, device: int = 0):
+    boards = np.ascontiguousarray(boards, dtype=np.int8).reshape(-1, NUM_LOCS)
+    colors = np.ascontiguousarray(colors, dtype=np.int8)
+    out = np.zeros((len(boards), NUM_MOVES), dtype=np.uint8)
+    fb = None
+    if forbidden is not None:
+        forbidden = np.ascontiguousarray(forbidden, dtype=np.int8).reshape(-1, NUM_LOCS)
+        fb = ptr(forbidden)
+    check(lib.p3_legal_mask(device, ptr(boards), ptr(colors), fb, len(boards), ptr(out)))
+    return out
+
+
+def gumbel_topk(logits: np.ndarray, legal: np.ndarray, prng_state: np.ndarray, noise_scaling: float, k: int,
+                device: int = 0):
+    """cc/mcts/gumbel.cc:283-321 for n roots; ``prng_state`` (uint64[n]) is updated in place."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32).reshape(-1, NUM_MOVES)
+    legal = np.ascontiguousarray(legal, dtype=np.uint8).reshape(-1, NUM_MOVES)
+    n = len(logits)
+    assert prng_state.dtype == np.uint64 and prng_state.flags.c_contiguous and len(prng_state) == n
+    moves = np.zeros((n, k), dtype=np.int32)
+    scores = np.zeros((n, k), dtype=np.float32)
+    kvalid = np.zeros(n, dtype=np.int32)
+    check(lib.p3_gumbel_topk(device, ptr(logits), ptr(legal), ptr(prng_state), n, noise_scaling, k, ptr(moves),
+                             ptr(scores), ptr(kvalid)))
+    return moves, scores, kvalid
+
+
+def conv_test(x: np.ndarray, w: np.ndarray, precision: int, device: int = 0) -> np.ndarray:
+    """x [n,361,cin], w OIHW [cout,cin,k,k] -> y [n,361,cout] (no BN / activation)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    n, _, cin = x.shape
+    cout, _, k, _ = w.shape
+    y = np.zeros((n, NUM_LOCS, cout), dtype=np.float32)
+    check(lib.p3_conv_test(device, precision, ptr(x), ptr(w), n, cin, cout, k, ptr(y)))
+    return y
