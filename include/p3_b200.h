@@ -157,7 +157,16 @@ int p3_engine_get_aux(p3_engine* e, int batch_id, p3_aux_result* aux);
 /* Run encode -> tower -> heads on the game state already resident in HBM (last H2D), without any
  * host<->device copy; returns device time in ms measured with CUDA events on the engine's stream. */
 int p3_engine_run_device(p3_engine* e, float* ms_total);
-/* Per-stage device times of the most recent p3_engine_run_device (ms): [0] encode, [1] tower, [2] heads. */
+/* H2D of the pinned game-state staging area only (then stream sync): makes the inputs of the next
+ * p3_engine_run_device resident in HBM outside its timed region. */
+int p3_engine_upload(p3_engine* e);
+/* One eager (non-graph) pass with a CUDA event around every launch; accumulates device ms and launch counts
+ * per kernel class: [0] encode [1] init conv [2] conv 1x1 [3] conv 3x3 [4] broadcast mix [5] head conv [6] heads.
+ * flops[c] = algorithmic FLOPs (2*MAC) those launches performed for the whole batch. */
+#define P3_NUM_KERNEL_CLASSES 7
+int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
+                      double flops[P3_NUM_KERNEL_CLASSES]);
+/* Per-stage device times of one eager pass (ms): [0] encode, [1] tower, [2] heads. */
 int p3_engine_stage_ms(p3_engine* e, float ms[3]);
 /* Number of kernel launches one p3_engine_run_inference issues (for bench.py's gpu_launches). */
 int p3_engine_launches_per_run(const p3_engine* e);

@@ -78,7 +78,7 @@ assert ctypes.sizeof(GoFeatures) == 1860 and GO_FEATURES_DTYPE.itemsize == 1860
 EXPORTS = [
     "p3_engine_create", "p3_engine_destroy", "p3_engine_load_batch", "p3_engine_run_inference", "p3_engine_get_batch",
     "p3_engine_get_ownership", "p3_engine_path", "p3_engine_batch_size", "p3_engine_get_planes", "p3_engine_get_aux",
-    "p3_engine_run_device", "p3_engine_stage_ms", "p3_engine_launches_per_run", "p3_engine_flops_per_position",
+    "p3_engine_run_device", "p3_engine_upload", "p3_engine_profile", "p3_engine_stage_ms", "p3_engine_launches_per_run", "p3_engine_flops_per_position",
     "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_gumbel_topk",
     "p3_conv_test", "p3_last_error", "p3_version",
 ]
@@ -106,6 +106,8 @@ def _load() -> ctypes.CDLL:
     lib.p3_engine_get_planes.argtypes = [vp, ci, vp, vp]
     lib.p3_engine_get_aux.argtypes = [vp, ci, vp]
     lib.p3_engine_run_device.argtypes = [vp, ctypes.POINTER(cf)]
+    lib.p3_engine_upload.argtypes = [vp]
+    lib.p3_engine_profile.argtypes = [vp, vp, vp, vp]
     lib.p3_engine_stage_ms.argtypes = [vp, ctypes.POINTER(cf * 3)]
     lib.p3_engine_launches_per_run.argtypes = [vp]
     lib.p3_engine_flops_per_position.argtypes = [vp]

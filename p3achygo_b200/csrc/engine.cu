@@ -698,6 +698,67 @@ int p3_engine_run_device(p3_engine* e, float* ms_total) {
   return P3_OK;
 }
 
+int p3_engine_upload(p3_engine* e) {
+  if (!e) return fail(P3_ERR_INVALID_ARG, "upload: null engine");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  return P3_OK;
+}
+
+int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
+                      double flops[P3_NUM_KERNEL_CLASSES]) {
+  if (!e || !ms || !launches || !flops) return fail(P3_ERR_INVALID_ARG, "profile: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  const int n_launch = e->launches;
+  std::vector<cudaEvent_t> evs(n_launch + 1);
+  for (auto& v : evs) P3_CUDA(cudaEventCreate(&v));
+  std::vector<int> cls;
+  std::vector<double> fl;
+  int idx = 0, rc = P3_OK;
+  const double B = e->batch, Pn = 361.0;
+  auto rec = [&]() { return cudaEventRecord(evs[idx++], e->stream); };
+  P3_CUDA(rec());
+  rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
+                     e->d_masks.as<uint16_t>(), e->stream);
+  cls.push_back(0); fl.push_back(0.0);
+  P3_CUDA(rec());
+  if (!rc) rc = init_conv_launch(e->d_masks.as<uint16_t>(), e->d_scalars.as<float>(), e->batch, e->nplanes, e->nscalars, e->C,
+                                 e->init_wt.as<float>(), e->gs_w.as<float>(), e->gs_b.as<float>(), e->xraw.as<float>(), e->actA.p,
+                                 e->bf16, e->first_scale, e->first_shift, e->stream);
+  cls.push_back(1); fl.push_back(2.0 * (25.0 * e->nplanes * e->C * Pn + double(e->nscalars) * e->C) * B);
+  P3_CUDA(rec());
+  for (const Step& s : e->program) {
+    if (rc) break;
+    if (s.kind == kStepConv) {
+      rc = e->run_conv(s);
+      cls.push_back(s.layer->taps == 1 ? 2 : 3);
+      fl.push_back(2.0 * s.layer->taps * double(s.layer->cin) * s.layer->cout * Pn * B);
+    } else {
+      rc = broadcast_launch(s.in, s.bw, s.bb, e->batch, e->C, s.b_out, e->bf16, s.b_scale, s.b_shift, e->stream);
+      cls.push_back(4); fl.push_back(2.0 * e->C * Pn * Pn * B);
+    }
+    P3_CUDA(rec());
+  }
+  if (!rc) rc = e->run_conv(e->head_step);
+  cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
+  P3_CUDA(rec());
+  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream);
+  cls.push_back(6); fl.push_back(0.0);
+  P3_CUDA(rec());
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  for (int c = 0; c < P3_NUM_KERNEL_CLASSES; ++c) { ms[c] = 0.0f; launches[c] = 0; flops[c] = 0.0; }
+  for (size_t i = 0; i < cls.size() && !rc; ++i) {
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
+    ms[cls[i]] += t;
+    launches[cls[i]] += 1;
+    flops[cls[i]] += fl[i];
+  }
+  for (auto& v : evs) cudaEventDestroy(v);
+  return rc;
+}
+
 int p3_engine_stage_ms(p3_engine* e, float ms[3]) {
   if (!e || !ms) return fail(P3_ERR_INVALID_ARG, "stage_ms: bad argument");
   P3_CUDA(cudaSetDevice(e->device));

@@ -133,6 +133,19 @@ class B200Engine:
         check(lib.p3_engine_run_device(self._h, ctypes.byref(ms)))
         return ms.value
 
+    def Upload(self) -> None:
+        check(lib.p3_engine_upload(self._h))
+
+    KERNEL_CLASSES = ["encode", "init_conv", "conv1x1", "conv3x3", "broadcast", "head_conv", "heads"]
+
+    def Profile(self):
+        """One eager pass with an event around every launch -> {class: (ms, launches, flops)}."""
+        ms = np.zeros(7, dtype=np.float32)
+        launches = np.zeros(7, dtype=np.int32)
+        flops = np.zeros(7, dtype=np.float64)
+        check(lib.p3_engine_profile(self._h, ptr(ms), ptr(launches), ptr(flops)))
+        return {k: (float(ms[i]), int(launches[i]), float(flops[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def StageMs(self):
         arr = (ctypes.c_float * 3)()
         check(lib.p3_engine_stage_ms(self._h, ctypes.byref(arr)))

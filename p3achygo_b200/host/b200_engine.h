@@ -1,0 +1,33 @@
+// nn::B200Engine — the adapter a p3achygo maintainer drops next to trt_engine.{h,cc}: an nn::Engine
+// whose four virtuals forward to the C ABI of libp3b200.so.  Errors are fatal, as in the reference
+// (CUDA_OK / CHECK abort, cc/nn/engine/trt_engine.cc:27-35).
+#pragma once
+#include "engine_iface.h"
+
+namespace nn {
+
+class B200Engine final : public Engine {
+ public:
+  // precision: P3_PRECISION_BF16 (default; env P3_PRECISION=fp32 selects the parity path)
+  static std::unique_ptr<B200Engine> Create(std::string path, int batch_size, int version, int device = 0,
+                                            int precision = -1);
+  ~B200Engine() override;
+
+  Engine::Kind kind() override { return Engine::Kind::kB200; }
+  std::string path() override { return path_; }
+  void LoadBatch(int batch_id, const GoFeatures& features) override;
+  void RunInference() override;
+  void GetBatch(int batch_id, NNInferResult& result) override;
+  void GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) override;
+
+  p3_engine* handle() { return engine_; }
+  int batch_size() const { return batch_size_; }
+
+ private:
+  B200Engine(p3_engine* e, std::string path, int batch_size) : engine_(e), path_(std::move(path)), batch_size_(batch_size) {}
+  p3_engine* engine_;
+  std::string path_;
+  int batch_size_;
+};
+
+}  // namespace nn

@@ -1,0 +1,75 @@
+// Engine micro-benchmark with the shape of the reference's nn::Benchmark
+// (cc/nn/engine/benchmark_engine.cc:77-109): warm-up RunInference calls, then per batch
+//     LoadBatch x B  ->  RunInference (timed with steady_clock, as the reference does)  ->  GetBatch x B
+// over synthetic positions instead of the TFRecord dataset.  Also times the whole cycle, with the
+// LoadBatch / GetBatch calls spread over `threads` host threads the way NNInterface's workers issue them
+// (cc/nn/nn_interface.cc:245-277, cc/nn/nn_interface.h:251-290).
+#include <chrono>
+#include <functional>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+#include "b200_engine.h"
+
+namespace {
+using Clock = std::chrono::steady_clock;
+double us_since(Clock::time_point t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); }
+
+void parallel_for(int n, int threads, const std::function<void(int)>& fn) {
+  if (threads <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([=, &fn]() {
+      for (int i = t; i < n; i += threads) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" {
+
+// positions: n_positions GoFeatures records (HOST). Cycles through them `steps` times (after `warmup` untimed
+// cycles), batch slots filled from consecutive records.  Outputs (microseconds, per cycle averages):
+//   out[0] RunInference only   out[1] LoadBatch x B   out[2] GetBatch x B   out[3] whole cycle
+//   out[4] checksum of value_probs (keeps GetBatch honest)
+int p3_host_benchmark(const char* weights_path, int device, int batch, int version, int precision,
+                      const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
+  auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
+  std::vector<nn::NNInferResult> results(batch);
+  double t_run = 0, t_load = 0, t_get = 0, t_cycle = 0, checksum = 0;
+  int cursor = 0;
+  for (int it = 0; it < warmup + steps; ++it) {
+    const bool timed = it >= warmup;
+    const int base = cursor;
+    cursor = (cursor + batch) % n_positions;
+    auto c0 = Clock::now();
+    parallel_for(batch, threads, [&](int b) { engine->LoadBatch(b, positions[(base + b) % n_positions]); });
+    const double load_us = us_since(c0);
+    auto r0 = Clock::now();
+    engine->RunInference();
+    const double run_us = us_since(r0);
+    auto g0 = Clock::now();
+    parallel_for(batch, threads, [&](int b) { engine->GetBatch(b, results[b]); });
+    const double get_us = us_since(g0);
+    const double cycle_us = us_since(c0);
+    if (timed) {
+      t_run += run_us;
+      t_load += load_us;
+      t_get += get_us;
+      t_cycle += cycle_us;
+      for (int b = 0; b < batch; ++b) checksum += results[b].value_probs[1];
+    }
+  }
+  out[0] = t_run / steps;
+  out[1] = t_load / steps;
+  out[2] = t_get / steps;
+  out[3] = t_cycle / steps;
+  out[4] = checksum;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+"""GPU parity of the convolution kernels against a plain PyTorch fp32 reference (F.conv2d on CPU)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x, w):
+    n, _, cin = x.shape
+    xt = torch.from_numpy(x).reshape(n, 19, 19, cin).permute(0, 3, 1, 2).double()
+    y = F.conv2d(xt, torch.from_numpy(w).double(), padding=w.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1).reshape(n, 361, -1).numpy()
+
+
+def _bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("cin,cout,k", [(16, 8, 1), (8, 8, 3), (64, 128, 3), (256, 128, 1), (96, 40, 3)])
+def test_conv_fp32(cin, cout, k):
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(cin * 1000 + cout + k)
+    x = rng.standard_normal((3, 361, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+    y = E.conv_test(x, w, E.PRECISION_FP32)
+    ref = _ref_conv(x, w)
+    assert np.abs(y - ref).max() < 2e-5  # fp32 accumulation over K <= 2304
+
+
+@pytest.mark.parametrize("cin,cout,k,n", [(64, 64, 1, 2), (128, 128, 3, 3), (256, 128, 1, 2), (128, 256, 1, 5),
+                                          (256, 96, 1, 2), (192, 192, 3, 2), (384, 192, 1, 1), (192, 384, 1, 1),
+                                          (64, 64, 3, 40)])
+def test_conv_tcgen05(cin, cout, k, n):
+    """tcgen05 path: bf16 operands, fp32 accumulate. Against the fp64 conv of the SAME bf16-rounded operands the
+    only error is fp32 accumulation order, so the bound is tight (1e-3 would hide a wrong tap or swizzle)."""
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(cin * 1000 + cout + k)
+    x = _bf16_round(rng.standard_normal((n, 361, cin)).astype(np.float32))
+    w = _bf16_round((rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32))
+    y = E.conv_test(x, w, E.PRECISION_BF16)
+    ref = _ref_conv(x, w)
+    err = np.abs(y - ref).max()
+    assert err < 5e-5, f"max abs err {err}"
