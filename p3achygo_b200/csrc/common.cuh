@@ -71,9 +71,9 @@ int conv_fp32_launch(const float* in, const float* w, int rows, int cin, int cou
 // ---- tcgen05 path (conv_tc.cu) -----------------------------------------------------------------
 struct TcConvPlan;  // TMA maps + tile config for one layer (opaque; built once per layer)
 int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int cin, int cout,
-                        int taps, const int* tap_off_host, TcConvPlan** out);
+                        int taps, const int* tap_off_host, const ConvEpilogue& ep, TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* plan);
-int tc_conv_launch(const TcConvPlan* plan, const ConvEpilogue& ep, cudaStream_t stream);
+int tc_conv_launch(const TcConvPlan* plan, cudaStream_t stream);
 bool tc_conv_supported(int cin, int cout);
 
 // ---- encode (encode.cu) --------------------------------------------------------------------------

@@ -6,18 +6,24 @@
 // whose zero padding is the layout's zero rows plus TMA's out-of-bounds zero fill (negative and
 // past-the-end row coordinates).  No im2col matrix is materialised.
 //
-// Warp-specialised persistent kernel, one CTA per SM:
-//   warp 0    TMA producer: per (tap, 64-channel slab) one 128 x 64 bf16 A box and one N x 64 bf16
-//             weight box, 128B-swizzled, into a multi-stage shared-memory ring (mbarrier full/empty)
-//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=tile width, K=16) x 4 per slab into
-//             one of two fp32 accumulators in TMEM; tcgen05.commit releases the ring slot / publishes
-//             the accumulator
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp and step), add the
-//             fp32 residual, store the raw fp32 stream and/or the bf16 activated copy with the NEXT
-//             layer's BN + mish folded in (ConvEpilogue), zeros on halo rows.  Runs concurrently with
-//             the next tile's MMAs through the second accumulator.
+// Two warp-specialised persistent kernels (one CTA per SM, 320 threads):
+//   warp 0      TMA producer (one elected thread)
+//   warp 1      MMA issuer (one elected thread; also owns the TMEM allocation): tcgen05.mma M=128, K=16 into
+//               one of two fp32 accumulators in TMEM; tcgen05.commit releases smem slots / publishes accumulators
+//   warps 2-9   epilogue, two warps per TMEM lane quarter: tcgen05.ld -> (+ residual) -> raw fp32 stream
+//               and/or bf16 activated copy with the NEXT layer's BN + mish folded in (ConvEpilogue)
+//
+//   tc_conv_kernel          generic (1x1 layers, head conv, 3x3 layers whose weights do not fit on chip):
+//                           A and W slabs streamed through a smem ring; the epilogue's global I/O is ALL TMA:
+//                           residual tiles are bulk-loaded into smem ahead of use and outputs leave through
+//                           swizzled staging tiles + cp.async.bulk.tensor stores, because these layers are
+//                           HBM-bound and a few warps of ld/st.global cannot keep enough bytes in flight
+//                           (measured: 1.2 TB/s with per-thread accesses).
+//   tc_conv3x3_res_kernel   3x3 layers with resident weights and tap reuse (see below).
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -27,42 +33,71 @@
 namespace p3 {
 
 constexpr int kTileM = 128;
-constexpr int kSlabK = 64;                 // bf16 elements per 128-byte swizzled row
+constexpr int kSlabK = 64;  // bf16 elements per 128-byte swizzled row
 constexpr int kUmmaK = 16;
 constexpr int kMaxTapsTc = 9;
 constexpr int kABytes = kTileM * kSlabK * 2;  // 16 KB
-constexpr int kNumThreads = 192;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiThreads = kNumEpiWarps * 32;
+constexpr int kNumThreads = 64 + kNumEpiThreads;  // 320
+constexpr int kSmemBudget = 224 * 1024;
+constexpr int kBarBytes = 512;
+constexpr int kMaxNTile = 128;
+// generic kernel staging: 2 residual tiles + 1 raw tile (128 rows x 32 fp32) + 1 act tile (128 rows x 32 bf16)
+constexpr int kStageF32Bytes = kTileM * 32 * 4;   // 16 KB
+constexpr int kStageBf16Bytes = kTileM * 32 * 2;  // 8 KB
+constexpr int kStagingBytes = 3 * kStageF32Bytes + kStageBf16Bytes;  // 56 KB
 
 struct TcTaps {
   int off[kMaxTapsTc];
 };
 
 struct TcConvPlan {
-  CUtensorMap map_a;
-  CUtensorMap map_w;
+  CUtensorMap map_a, map_w, map_res, map_raw, map_act;
   int rows, cin, cout, taps, n_tile, stages, tmem_cols, grid;
   size_t smem_bytes;
   TcTaps tap;
+  ConvEpilogue ep;
+  bool resident = false;  // tc_conv3x3_res_kernel
 };
 
 namespace {
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int kMode>
+__device__ __forceinline__ float activate(float x, float sc, float sh) {
+  if (kMode == kActMishBN) return mish_f32<false>(fmaf(x, sc, sh));
+  if (kMode == kActMish) return mish_f32<false>(x);
+  return x;
+}
+
+// ===================================================================================================
+// generic kernel
+// ===================================================================================================
 __global__ void __launch_bounds__(kNumThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
-               int cin, int cout, int taps, TcTaps tap, int n_tile, int stages, int tmem_cols,
-               const float* residual, float* raw_out, __nv_bfloat16* act_out, const float* __restrict__ scale,
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
+               const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
+               int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
                const float* __restrict__ shift, int act_mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16 KB | B n_tile*128 B] | barriers | tmem ptr
+  // carve: [staging 56 KB] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = n_tile * kSlabK * 2;
-  const int stage_bytes = kABytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint8_t* st_res = smem;                         // 2 x 16 KB
+  uint8_t* st_raw = smem + 2 * kStageF32Bytes;    // 16 KB
+  uint8_t* st_act = smem + 3 * kStageF32Bytes;    // 8 KB
+  uint8_t* ring = smem + kStagingBytes;
+  const int stage_bytes = kABytes + n_tile * kSlabK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (rows + kTileM - 1) / kTileM;
@@ -70,6 +105,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int total_tiles = m_tiles * n_tiles;
   const int k_slabs = cin / kSlabK;
   const int k_steps = taps * k_slabs;
+  const int n_chunks = n_tile / 32;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -80,7 +116,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[s], kNumEpiWarps);
+      ptx::mbar_init(&res_full[s], 1);
     }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
@@ -102,7 +139,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int t = 0; t < taps; ++t) {
           for (int ks = 0; ks < k_slabs; ++ks) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
             ptx::tma_load_2d(sa, &map_a, &full_bar[stage], ks * kSlabK, m0 + tap.off[t]);
             ptx::tma_load_2d(sa + kABytes, &map_w, &full_bar[stage], ks * kSlabK, t * cout + n0);
@@ -130,7 +167,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int step = 0; step < k_steps; ++step) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sa = ptx::smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < kSlabK / kUmmaK; ++k) {
@@ -149,8 +186,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-    const int quarter = warp & 3;
+    // ===== epilogue: 8 warps; the warp pair of a quarter shares TMEM lanes [32q, 32q+32), each warp takes 16 of
+    // the 32 columns of a chunk.  Thread = one output row.  All global traffic goes through TMA. =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = (ew >> 2) & 1;     // which 16 columns of each 32-column chunk
+    const int r = quarter * 32 + lane;  // row within the tile
+    const bool leader = (threadIdx.x == 64);
+    // this thread's row inside a 128 B-row (fp32, 128B swizzle) / 64 B-row (bf16, 64B swizzle) staging tile
+    const uint32_t f32_row = static_cast<uint32_t>(r) * 128u;
+    const uint32_t bf_row = static_cast<uint32_t>(r) * 64u;
+    uint32_t g = 0;  // running chunk counter (residual double buffer + parity)
+
+    auto issue_res = [&](uint32_t gi, int tile_i, int ci) {
+      const int m0i = (tile_i / n_tiles) * kTileM, n0i = (tile_i % n_tiles) * n_tile;
+      const uint32_t b = gi & 1u;
+      ptx::mbar_arrive_expect_tx(&res_full[b], kStageF32Bytes);
+      ptx::tma_load_2d(st_res + b * kStageF32Bytes, &map_res, &res_full[b], n0i + ci * 32, m0i);
+    };
+    if (leader && has_res) {  // prefetch the residual tiles of the first two chunks
+      int t0 = blockIdx.x, c = 0;
+      for (uint32_t gi = 0; gi < 2 && t0 < total_tiles; ++gi) {
+        issue_res(gi, t0, c);
+        if (++c == n_chunks) {
+          c = 0;
+          t0 += gridDim.x;
+        }
+      }
+    }
+
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int m0 = (tile / n_tiles) * kTileM, n0 = (tile % n_tiles) * n_tile;
@@ -158,58 +222,83 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t acc_phase = (iter >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
-      const int m = m0 + quarter * 32 + lane;
-      const bool in_range = m < rows;
-      const bool live = in_range && row_is_live(m % kRowsPerPos);
-      const size_t row_off = static_cast<size_t>(m) * cout + n0;
-      for (int c0 = 0; c0 < n_tile; c0 += 32) {
-        uint32_t v[32];
+      const int m = m0 + r;
+      const bool live = m < rows && row_is_live(m % kRowsPerPos);
+
+      for (int c = 0; c < n_chunks; ++c, ++g) {
+        const uint32_t buf = g & 1u;
+        uint32_t v[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * n_tile + c0);
-        ptx::tmem_ld_32x32(taddr, v);
-        float r[32];
-        if (residual != nullptr && live) {
-          const float4* rp = reinterpret_cast<const float4*>(residual + row_off + c0);
+                               static_cast<uint32_t>(acc * n_tile + c * 32 + half * 16);
+        ptx::tmem_ld_32x16(taddr, v);
+        float x[16];
+        if (has_res) {
+          ptx::mbar_wait(&res_full[buf], (g >> 1) & 1u);
+          const uint8_t* rp = st_res + buf * kStageF32Bytes + f32_row;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t4 = rp[i];
-            r[4 * i] = t4.x; r[4 * i + 1] = t4.y; r[4 * i + 2] = t4.z; r[4 * i + 3] = t4.w;
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((half * 4 + j) ^ (r & 7)) << 4));
+            x[4 * j] = t4.x;
+            x[4 * j + 1] = t4.y;
+            x[4 * j + 2] = t4.z;
+            x[4 * j + 3] = t4.w;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0.0f;
+          for (int j = 0; j < 16; ++j) x[j] = 0.0f;
         }
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = live ? (__uint_as_float(v[i]) + r[i]) : 0.0f;
-        if (in_range) {
-          if (raw_out != nullptr) {
-            float4* op = reinterpret_cast<float4*>(raw_out + row_off + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        for (int j = 0; j < 16; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
+
+        // staging free? the previous chunk's bulk stores have read it, and everyone is done with st_res[buf]
+        if (leader) ptx::bulk_wait_read_all();
+        ptx::named_bar_sync(1, kNumEpiThreads);
+        if (leader && has_res) {  // refill the residual buffer just consumed with chunk g+2
+          int t2 = tile, c2 = c + 2;
+          while (c2 >= n_chunks) {
+            c2 -= n_chunks;
+            t2 += gridDim.x;
           }
-          if (act_out != nullptr) {
-            uint32_t packed[16];
+          if (t2 < total_tiles) issue_res(g + 2, t2, c2);
+        }
+        if (has_raw) {
+          uint8_t* wp = st_raw + f32_row;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a0 = r[2 * i], a1 = r[2 * i + 1];
-              if (act_mode == kActMishBN) {
-                const int n = n0 + c0 + 2 * i;
-                a0 = mish_f32<false>(fmaf(a0, __ldg(scale + n), __ldg(shift + n)));
-                a1 = mish_f32<false>(fmaf(a1, __ldg(scale + n + 1), __ldg(shift + n + 1)));
-              } else if (act_mode == kActMish) {
-                a0 = mish_f32<false>(a0);
-                a1 = mish_f32<false>(a1);
-              }
-              if (!live) a0 = a1 = 0.0f;
-              const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-              packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            uint4* ap = reinterpret_cast<uint4*>(act_out + row_off + c0);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(wp + (((half * 4 + j) ^ (r & 7)) << 4)) =
+                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+        if (has_act) {
+          const int nb = n0 + c * 32 + half * 16;
+          float a[16];
+          if (act_mode == kActMishBN) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              ap[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            for (int j = 0; j < 16; ++j) a[j] = activate<kActMishBN>(x[j], __ldg(scale + nb + j), __ldg(shift + nb + j));
+          } else if (act_mode == kActMish) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = activate<kActMish>(x[j], 1.0f, 0.0f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = x[j];
           }
+          uint8_t* wp = st_act + bf_row;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int o = 8 * j;
+            const uint4 pk = make_uint4(pack_bf16(live ? a[o] : 0.f, live ? a[o + 1] : 0.f),
+                                        pack_bf16(live ? a[o + 2] : 0.f, live ? a[o + 3] : 0.f),
+                                        pack_bf16(live ? a[o + 4] : 0.f, live ? a[o + 5] : 0.f),
+                                        pack_bf16(live ? a[o + 6] : 0.f, live ? a[o + 7] : 0.f));
+            *reinterpret_cast<uint4*>(wp + (((half * 2 + j) ^ ((r >> 1) & 3)) << 4)) = pk;
+          }
+        }
+        ptx::fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
+        ptx::named_bar_sync(2, kNumEpiThreads);
+        if (leader) {
+          if (has_raw) ptx::tma_store_2d(&map_raw, st_raw, n0 + c * 32, m0);
+          if (has_act) ptx::tma_store_2d(&map_act, st_act, n0 + c * 32, m0);
+          ptx::bulk_commit();
         }
       }
       // accumulator drained -> hand it back to the MMA warp
@@ -217,6 +306,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
     }
+    if (leader) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before_sync();
@@ -224,6 +314,189 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(tmem_cols));
+  }
+}
+
+// ===================================================================================================
+// 3x3 layers with RESIDENT weights and tap reuse (the dominant kernel of the tower).
+//
+// ncu on the streaming kernel showed the 3x3 layers bound by L2->SM traffic: every 128-row tile re-read its
+// A rows 9 times (once per tap) and streamed all 9*cin*cout weights again.  Here
+//   * each CTA owns a 64-wide slice of the output channels and keeps that slice of ALL taps' weights in
+//     shared memory for the whole launch (9 * cin * 64 bf16 <= 144 KB), loaded once by TMA;
+//   * per 64-channel slab ONE haloed A box of 176 rows (128 + 2*21 halo rows, padded to a multiple of 8)
+//     is loaded, and the 9 taps are 9 shifted views of it: the smem matrix descriptor's start address moves
+//     by (21 + dy*20 + dx) rows of 128 B inside the 128B-swizzled tile (the swizzle is a function of the
+//     absolute smem address, so a row-shifted start needs no base-offset correction — verified on B200).
+// L2->SM traffic per 128 output rows drops from 2 * 9 * cin * 256 B to (176/128) * cin * 256 B.
+// ===================================================================================================
+constexpr int kResN = 64;
+constexpr int kResHalo = 21;
+constexpr int kResRows = 176;
+constexpr int kResABytes = kResRows * 128;   // 22 528 B, a multiple of 1024
+constexpr int kResWSlabBytes = kResN * 128;  // 8 KB per (tap, 64-channel slab)
+constexpr int kResStages = 3;
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
+                      int cin, int cout, TcTaps tap, __nv_bfloat16* __restrict__ act_out,
+                      const float* __restrict__ scale, const float* __restrict__ shift, int act_mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int k_slabs = cin / kSlabK;
+  const int w_bytes = 9 * k_slabs * kResWSlabBytes;
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + w_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + kResStages * kResABytes);
+  uint64_t* empty_bar = full_bar + kResStages;
+  uint64_t* tmem_full = empty_bar + kResStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slices = cout / kResN;
+  const int slice = blockIdx.x % n_slices;
+  const int n0 = slice * kResN;
+  const int cta_in_slice = blockIdx.x / n_slices, ctas_per_slice = gridDim.x / n_slices;
+  const int m_tiles = (rows + kTileM - 1) / kTileM;
+  constexpr int kTmemCols = 2 * kResN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_w);
+    for (int s = 0; s < kResStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], kNumEpiWarps);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: all taps x slabs of this CTA's 64 output channels, once
+      ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(w_bytes));
+      for (int t = 0; t < 9; ++t)
+        for (int ks = 0; ks < k_slabs; ++ks)
+          ptx::tma_load_2d(smem_w + (t * k_slabs + ks) * kResWSlabBytes, &map_w, w_bar, ks * kSlabK, t * cout + n0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = cta_in_slice; mt < m_tiles; mt += ctas_per_slice) {
+        const int m0 = mt * kTileM;
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kResABytes);
+          ptx::tma_load_2d(smem_a + stage * kResABytes, &map_a, &full_bar[stage], ks * kSlabK, m0 - kResHalo);
+          if (++stage == kResStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kResN);
+      const uint32_t w_base = ptx::smem_u32(smem_w);
+      ptx::mbar_wait(w_bar, 0);
+      ptx::tc_fence_after_sync();
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int mt = cta_in_slice; mt < m_tiles; mt += ctas_per_slice, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kResN);
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_tile = ptx::smem_u32(smem_a + stage * kResABytes);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            // tap (dy,dx) = shifted view: skip (21 + dy*20 + dx) rows of 128 B inside the swizzled tile
+            const uint32_t a_view = a_tile + static_cast<uint32_t>(kResHalo + tap.off[t]) * 128u;
+            const uint32_t w_slab = w_base + static_cast<uint32_t>((t * k_slabs + ks) * kResWSlabBytes);
+#pragma unroll
+            for (int k = 0; k < kSlabK / kUmmaK; ++k) {
+              const uint64_t da = ptx::make_desc_sw128(a_view + k * kUmmaK * 2);
+              const uint64_t db = ptx::make_desc_sw128(w_slab + k * kUmmaK * 2);
+              ptx::umma_f16(tmem_d, da, db, idesc, (ks > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == kResStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // epilogue: 8 warps, thread = one output row, 32 of the slice's 64 columns each; writes only the bf16
+    // activated copy (16 KB per tile), so plain 16-byte stores are enough here
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = (ew >> 2) & 1;
+    int iter = 0;
+    for (int mt = cta_in_slice; mt < m_tiles; mt += ctas_per_slice, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const int m = mt * kTileM + quarter * 32 + lane;
+      const bool in_range = m < rows;
+      const bool live = in_range && row_is_live(m % kRowsPerPos);
+      const int nb = n0 + half * 32;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * kResN + half * 32);
+      ptx::tmem_ld_32x32(taddr, v);
+      ptx::tmem_ld_wait();
+      // accumulator values are in registers: release the TMEM stage before the math
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (in_range) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
+          if (act_mode == kActMishBN) {
+            a0 = activate<kActMishBN>(a0, __ldg(scale + nb + 2 * i), __ldg(shift + nb + 2 * i));
+            a1 = activate<kActMishBN>(a1, __ldg(scale + nb + 2 * i + 1), __ldg(shift + nb + 2 * i + 1));
+          } else if (act_mode == kActMish) {
+            a0 = activate<kActMish>(a0, 1.f, 0.f);
+            a1 = activate<kActMish>(a1, 1.f, 0.f);
+          }
+          packed[i] = pack_bf16(live ? a0 : 0.0f, live ? a1 : 0.0f);
+        }
+        uint4* ap = reinterpret_cast<uint4*>(act_out + static_cast<size_t>(m) * cout + nb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ap[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -243,25 +516,27 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [dim1, dim0] tensor, box [box1, 64], 128-byte swizzle, zero OOB fill.
-int make_map_2d(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box1) {
+// 2-D row-major [dim1, dim0] tensor of `elem_bytes` elements, box [box1, box0], zero OOB fill.
+int make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t dim0, uint64_t dim1,
+                uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(P3_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {dim0 * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSlabK), box1};
+  cuuint64_t gstride[1] = {dim0 * elem_bytes};
+  cuuint32_t box[2] = {box0, box1};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(P3_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
   return P3_OK;
 }
+int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box1) {
+  return make_map_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim0, dim1, kSlabK, box1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
 
-int pick_n_tile(int cout) {
-  if (cout <= 256) return cout;
-  if (cout % 2 == 0 && cout / 2 <= 256) return cout / 2;
-  if (cout % 3 == 0 && cout / 3 <= 256) return cout / 3;
+int pick_n_tile(int cout) {  // largest divisor of cout that is <= 128 and a multiple of 32
+  for (int n = kMaxNTile; n >= 32; n -= 32)
+    if (cout % n == 0) return n;
   return 0;
 }
 
@@ -269,41 +544,80 @@ int pick_n_tile(int cout) {
 
 bool tc_conv_supported(int cin, int cout) {
   if (cin <= 0 || cin % kSlabK != 0) return false;
-  const int n = pick_n_tile(cout);
-  return n >= 32 && n % 32 == 0;
+  return pick_n_tile(cout) >= 32;
 }
 
 int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int cin, int cout, int taps,
-                        const int* tap_off_host, TcConvPlan** out) {
+                        const int* tap_off_host, const ConvEpilogue& ep, TcConvPlan** out) {
   if (!tc_conv_supported(cin, cout)) return fail(P3_ERR_UNSUPPORTED, "tc_conv: cin % 64 != 0 or cout not tileable");
   if (taps > kMaxTapsTc) return fail(P3_ERR_INVALID_ARG, "tc_conv: too many taps");
   TcConvPlan* p = new TcConvPlan();
-  p->rows = rows; p->cin = cin; p->cout = cout; p->taps = taps;
-  p->n_tile = pick_n_tile(cout);
+  p->rows = rows;
+  p->cin = cin;
+  p->cout = cout;
+  p->taps = taps;
+  p->ep = ep;
   for (int t = 0; t < taps; ++t) p->tap.off[t] = tap_off_host[t];
-  const int stage_bytes = kABytes + p->n_tile * kSlabK * 2;
-  p->stages = std::min(8, (kSmemBudget - 1024 - 256) / stage_bytes);
-  p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  int cols = 32;
-  while (cols < 2 * p->n_tile) cols *= 2;
-  p->tmem_cols = cols;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int total_tiles = ((rows + kTileM - 1) / kTileM) * (cout / p->n_tile);
-  p->grid = std::min(total_tiles, sms);
-  int rc = make_map_2d(&p->map_a, in, cin, rows, kTileM);
-  if (rc == P3_OK) rc = make_map_2d(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_tile);
+  const char* env_res = std::getenv("P3_TC_RESIDENT");
+  const size_t res_smem =
+      static_cast<size_t>(9) * (cin / kSlabK) * kResWSlabBytes + kResStages * kResABytes + 1024 + kBarBytes;
+  bool shifts_ok = taps == 9;
+  for (int t = 0; t < taps && shifts_ok; ++t) shifts_ok = std::abs(tap_off_host[t]) <= kResHalo;
+  // the resident kernel writes only the activated copy (all 3x3 layers except a classic block's second conv)
+  p->resident = shifts_ok && cout % kResN == 0 && res_smem <= static_cast<size_t>(kSmemBudget) && ep.residual == nullptr &&
+                ep.raw_out == nullptr && ep.act_out != nullptr && !(env_res && std::atoi(env_res) == 0);
+  int rc;
+  if (p->resident) {
+    p->n_tile = kResN;
+    p->stages = kResStages;
+    p->smem_bytes = res_smem;
+    p->tmem_cols = 2 * kResN;
+    const int n_slices = cout / kResN;
+    const int m_tiles = (rows + kTileM - 1) / kTileM;
+    p->grid = std::max(n_slices, std::min(sms, m_tiles * n_slices) / n_slices * n_slices);
+    rc = make_map_bf16_k64(&p->map_a, in, cin, rows, kResRows);
+    if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, kResN);
+    if (rc == P3_OK) {
+      cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+    }
+  } else {
+    p->n_tile = pick_n_tile(cout);
+    const int stage_bytes = kABytes + p->n_tile * kSlabK * 2;
+    p->stages = std::min(8, (kSmemBudget - 1024 - kBarBytes - kStagingBytes) / stage_bytes);
+    p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 /*align slack*/ + kBarBytes + kStagingBytes;
+    int cols = 32;
+    while (cols < 2 * p->n_tile) cols *= 2;
+    p->tmem_cols = cols;
+    const int total_tiles = ((rows + kTileM - 1) / kTileM) * (cout / p->n_tile);
+    p->grid = std::min(total_tiles, sms);
+    rc = make_map_bf16_k64(&p->map_a, in, cin, rows, kTileM);
+    if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_tile);
+    // epilogue maps: fp32 [rows, cout] boxes of 128 rows x 32 cols (128 B rows, 128B swizzle);
+    //                bf16 [rows, cout] boxes of 128 rows x 32 cols (64 B rows, 64B swizzle)
+    if (rc == P3_OK && ep.residual)
+      rc = make_map_2d(&p->map_res, ep.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, rows, 32, kTileM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == P3_OK && ep.raw_out)
+      rc = make_map_2d(&p->map_raw, ep.raw_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, rows, 32, kTileM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == P3_OK && ep.act_out)
+      rc = make_map_2d(&p->map_act, ep.act_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cout, rows, 32, kTileM,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+    if (!ep.residual) p->map_res = p->map_a;  // never dereferenced (has_res = 0); keeps the kernel parameter well-formed
+    if (!ep.raw_out) p->map_raw = p->map_a;
+    if (!ep.act_out) p->map_act = p->map_a;
+    if (rc == P3_OK) {
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+    }
+  }
   if (rc != P3_OK) {
     delete p;
     return rc;
-  }
-  {  // per-device attribute; cheap, so set it for every plan
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) {
-      delete p;
-      return fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
-    }
   }
   *out = p;
   return P3_OK;
@@ -311,10 +625,18 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
 
-int tc_conv_launch(const TcConvPlan* p, const ConvEpilogue& ep, cudaStream_t stream) {
-  tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
-      p->map_a, p->map_w, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile, p->stages, p->tmem_cols, ep.residual,
-      ep.raw_out, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode);
+int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
+  const ConvEpilogue& ep = p->ep;
+  if (p->resident) {
+    tc_conv3x3_res_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
+        p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
+        ep.shift, ep.act_mode);
+  } else {
+    tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
+        p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
+        p->stages, p->tmem_cols, ep.residual != nullptr, ep.raw_out != nullptr, ep.act_out != nullptr, ep.scale, ep.shift,
+        ep.act_mode);
+  }
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

@@ -172,7 +172,7 @@ struct p3_engine {
   int run_conv(const Step& s) {
     ConvLayer& L = *s.layer;
     if (bf16)
-      return tc_conv_launch(L.plan, s.ep, stream);
+      return tc_conv_launch(L.plan, stream);
     return conv_fp32_launch(reinterpret_cast<const float*>(s.in), L.w_f32.as<float>(), rows, L.cin, L.cout, L.taps,
                             L.tap_off.data(), s.ep, stream);
   }
@@ -435,7 +435,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     }
     if (e.bf16) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(in), L->w_bf16.as<__nv_bfloat16>(), e.rows,
-                                  L->cin, L->cout, L->taps, L->tap_off.data(), &L->plan);
+                                  L->cin, L->cout, L->taps, L->tap_off.data(), s.ep, &L->plan);
       if (r) return r;
     }
     e.program.push_back(s);
@@ -489,7 +489,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.ep.raw_out = e.pgv.as<float>();
     if (e.bf16) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(head_in), e.head_conv->w_bf16.as<__nv_bfloat16>(),
-                                  e.rows, C, 3 * Ch, 1, e.head_conv->tap_off.data(), &e.head_conv->plan);
+                                  e.rows, C, 3 * Ch, 1, e.head_conv->tap_off.data(), s.ep, &e.head_conv->plan);
       if (r) return r;
     }
     e.head_step = s;
@@ -871,10 +871,28 @@ int p3_conv_test(int device, int precision, const float* x, const float* w, int 
   if (bf16) {
     if ((rc = upload_bf16(dx, xp)) || (rc = upload_bf16(dw, tnk))) return rc;
     TcConvPlan* plan = nullptr;
+    // a 3x3 test layer with only the activated copy requested exercises the resident-weight kernel (identity act),
+    // otherwise the streaming kernel writes the raw fp32 sum
+    DevBuf dact;
+    const bool want_act = std::getenv("P3_CONV_TEST_ACT") != nullptr;
+    if (want_act) {
+      if ((rc = dact.alloc(sizeof(__nv_bfloat16) * R * cout))) return rc;
+      ep.raw_out = nullptr;
+      ep.act_out = dact.p;
+      ep.act_mode = kActIdentity;
+    }
     if ((rc = tc_conv_plan_create(dx.as<__nv_bfloat16>(), dw.as<__nv_bfloat16>(), static_cast<int>(R), cin, cout, ksize * ksize,
-                                  off.data(), &plan)))
+                                  off.data(), ep, &plan)))
       return rc;
-    rc = tc_conv_launch(plan, ep, 0);
+    rc = tc_conv_launch(plan, 0);
+    if (want_act && !rc) {
+      cudaDeviceSynchronize();
+      std::vector<__nv_bfloat16> ha(R * cout);
+      cudaMemcpy(ha.data(), dact.p, dact.bytes, cudaMemcpyDeviceToHost);
+      std::vector<float> hf(R * cout);
+      for (size_t i = 0; i < hf.size(); ++i) hf[i] = __bfloat162float(ha[i]);
+      cudaMemcpy(dy.p, hf.data(), dy.bytes, cudaMemcpyHostToDevice);
+    }
     cudaError_t se = cudaDeviceSynchronize();
     tc_conv_plan_destroy(plan);
     if (rc) return rc;

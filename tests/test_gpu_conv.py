@@ -43,3 +43,17 @@ def test_conv_tcgen05(cin, cout, k, n):
     ref = _ref_conv(x, w)
     err = np.abs(y - ref).max()
     assert err < 5e-5, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("cin,cout,n", [(64, 64, 3), (128, 128, 40), (128, 64, 2), (64, 128, 5)])
+def test_conv_tcgen05_resident_weights(cin, cout, n, monkeypatch):
+    """The resident-weight / tap-reuse 3x3 kernel (shifted shared-memory views of one haloed A tile). It only writes the
+    bf16 activated copy, so the comparison allows one bf16 rounding of the output (2^-8 relative)."""
+    from p3achygo_b200 import engine as E
+    monkeypatch.setenv("P3_CONV_TEST_ACT", "1")
+    rng = np.random.default_rng(cin * 7 + cout)
+    x = _bf16_round(rng.standard_normal((n, 361, cin)).astype(np.float32))
+    w = _bf16_round((rng.standard_normal((cout, cin, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))
+    y = E.conv_test(x, w, E.PRECISION_BF16)
+    ref = _ref_conv(x, w)
+    assert np.all(np.abs(y - ref) <= np.abs(ref) * 2.0 ** -8 + 1e-4), f"max abs err {np.abs(y - ref).max()}"
