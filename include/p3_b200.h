@@ -207,6 +207,10 @@ int p3_gumbel_topk(int device, const float* logits, const uint8_t* legal, uint64
 int p3_conv_test(int device, int precision, const float* x, const float* w, int n, int cin, int cout,
                  int ksize, float* y);
 
+/* The broadcast mix of a BroadcastResidualBlock (python/model.py:570-581) for kernel unit tests:
+ * x [n,361,C] fp32 (HOST, already activated), w [361,361] (in, out), bias [361]; y [n,361,C] = mish(W^T x + bias). */
+int p3_broadcast_test(int device, int precision, const float* x, const float* w, const float* bias, int n, int C, float* y);
+
 const char* p3_last_error(void);
 const char* p3_version(void);
 

@@ -97,6 +97,14 @@ int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int npl
 int broadcast_launch(const void* x, const float* w, const float* bias, int n, int C, void* act_out,
                      bool bf16, const float* scale, const float* shift, cudaStream_t stream);
 
+// tcgen05 version (broadcast_tc.cu): W^T as the K-major A operand, the NHWC activation as an MN-major B operand.
+struct TcBcastPlan;
+bool tc_broadcast_supported(int C);
+int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const void* x, void* act_out, int B, int C,
+                             const float* scale, const float* shift, TcBcastPlan** out);
+void tc_broadcast_plan_destroy(TcBcastPlan* p);
+int tc_broadcast_launch(const TcBcastPlan* p, cudaStream_t stream);
+
 // ---- heads (heads.cu) ------------------------------------------------------------------------------------
 struct HeadWeights {
   int Ch, Cv;

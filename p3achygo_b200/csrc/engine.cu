@@ -112,6 +112,7 @@ struct Step {
   void* b_out = nullptr;
   const float* b_scale = nullptr;
   const float* b_shift = nullptr;
+  TcBcastPlan* bplan = nullptr;  // tcgen05 broadcast mix (bf16 mode)
 };
 
 }  // namespace
@@ -155,6 +156,7 @@ struct p3_engine {
   bool aux_host_valid = false;
 
   ~p3_engine() {
+    for (Step& s : program) if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -177,6 +179,11 @@ struct p3_engine {
                             L.tap_off.data(), s.ep, stream);
   }
 
+  int run_broadcast(const Step& s) {
+    if (s.bplan) return tc_broadcast_launch(s.bplan, stream);
+    return broadcast_launch(s.in, s.bw, s.bb, batch, C, s.b_out, bf16, s.b_scale, s.b_shift, stream);
+  }
+
   // encode -> init conv -> tower -> head conv -> heads, all on `stream`; optional stage events
   int enqueue_device(bool with_events) {
     int rc;
@@ -191,7 +198,7 @@ struct p3_engine {
     if (rc) return rc;
     for (const Step& s : program) {
       if (s.kind == kStepConv) rc = run_conv(s);
-      else rc = broadcast_launch(s.in, s.bw, s.bb, batch, C, s.b_out, bf16, s.b_scale, s.b_shift, stream);
+      else rc = run_broadcast(s);
       if (rc) return rc;
     }
     if (with_events) P3_CUDA(cudaEventRecord(ev[2], stream));
@@ -372,7 +379,14 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   }
 
   // ---- trunk (model.py:1000-1047): build layers, then wire the program
-  struct BlockDesc { bool bcast; std::vector<ConvLayer*> convs; const float* bw = nullptr; const float* bb = nullptr; };
+  struct BlockDesc {
+    bool bcast;
+    std::vector<ConvLayer*> convs;
+    const float* bw = nullptr;
+    const float* bb = nullptr;
+    const WeightTensor* bw_host = nullptr;
+    const WeightTensor* bb_host = nullptr;
+  };
   std::vector<BlockDesc> blocks(e.blocks);
   for (int i = 0; i < e.blocks; ++i) {
     const bool bcast = (i % bint) == bint - 1;  // model.py:1003
@@ -396,6 +410,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       if (!w || !b) return fail(P3_ERR_IO, bd.err);
       blocks[i].bw = e.dev_vec(w->data, &rc);
       blocks[i].bb = e.dev_vec(b->data, &rc);
+      blocks[i].bw_host = w;
+      blocks[i].bb_host = b;
       if (rc) return rc;
     }
     (void)ksz;
@@ -458,6 +474,12 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       s.b_out = cur;
       s.b_scale = bk.convs[1]->in_scale.as<float>();
       s.b_shift = bk.convs[1]->in_shift.as<float>();
+      const char* env_tb = std::getenv("P3_TC_BROADCAST");
+      if (e.bf16 && tc_broadcast_supported(C) && !(env_tb && std::atoi(env_tb) == 0)) {
+        if ((rc = tc_broadcast_plan_create(bk.bw_host->data.data(), bk.bb_host->data.data(), other, cur, B, C, s.b_scale,
+                                           s.b_shift, &s.bplan)))
+          return rc;
+      }
       e.program.push_back(s);
       if ((rc = add_conv(bk.convs[1], cur, e.xraw.as<float>(), e.xraw.as<float>(), end_act, end_mode, next_first))) return rc;
     } else if (btl) {  // BottleneckResidualConvBlock, model.py:372-412
@@ -735,7 +757,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
       cls.push_back(s.layer->taps == 1 ? 2 : 3);
       fl.push_back(2.0 * s.layer->taps * double(s.layer->cin) * s.layer->cout * Pn * B);
     } else {
-      rc = broadcast_launch(s.in, s.bw, s.bb, e->batch, e->C, s.b_out, e->bf16, s.b_scale, s.b_shift, e->stream);
+      rc = e->run_broadcast(s);
       cls.push_back(4); fl.push_back(2.0 * e->C * Pn * Pn * B);
     }
     P3_CUDA(rec());
@@ -843,6 +865,50 @@ int p3_gumbel_topk(int device, const float* logits, const uint8_t* legal, uint64
   P3_CUDA(cudaMemcpy(out_scores, dsc.p, dsc.bytes, cudaMemcpyDeviceToHost));
   P3_CUDA(cudaMemcpy(out_kvalid, dkv.p, dkv.bytes, cudaMemcpyDeviceToHost));
   P3_CUDA(cudaMemcpy(prng_state, dst.p, dst.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_broadcast_test(int device, int precision, const float* x, const float* w, const float* bias, int n, int C, float* y) {
+  if (!x || !w || !bias || !y || n <= 0) return fail(P3_ERR_INVALID_ARG, "broadcast_test: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  const bool bf16 = precision == P3_PRECISION_BF16;
+  if (bf16 && !tc_broadcast_supported(C)) return fail(P3_ERR_UNSUPPORTED, "broadcast_test: C % 64 != 0");
+  const size_t R = static_cast<size_t>(n) * kRowsPerPos;
+  std::vector<float> xp(R * C, 0.0f);
+  for (int b = 0; b < n; ++b)
+    for (int p = 0; p < 361; ++p)
+      std::memcpy(&xp[(static_cast<size_t>(b) * kRowsPerPos + board_row(p)) * C], &x[(static_cast<size_t>(b) * 361 + p) * C], sizeof(float) * C);
+  std::vector<float> ones(C, 1.0f), zeros(C, 0.0f), wv(w, w + 361 * 361), bv(bias, bias + 361);
+  DevBuf dx, dy, dsc, dsh, dw, db;
+  if ((rc = upload_f32(dsc, ones)) || (rc = upload_f32(dsh, zeros))) return rc;
+  std::vector<float> yp(R * C);
+  if (bf16) {
+    if ((rc = upload_bf16(dx, xp)) || (rc = dy.alloc(R * C * 2))) return rc;
+    P3_CUDA(cudaMemset(dy.p, 0xff, dy.bytes));  // halo rows must be overwritten with zeros
+    TcBcastPlan* plan = nullptr;
+    if ((rc = tc_broadcast_plan_create(w, bias, dx.p, dy.p, n, C, dsc.as<float>(), dsh.as<float>(), &plan))) return rc;
+    rc = tc_broadcast_launch(plan, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    tc_broadcast_plan_destroy(plan);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(P3_ERR_CUDA, std::string("tc_broadcast kernel: ") + cudaGetErrorString(se));
+    std::vector<__nv_bfloat16> hb(R * C);
+    P3_CUDA(cudaMemcpy(hb.data(), dy.p, dy.bytes, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < yp.size(); ++i) yp[i] = __bfloat162float(hb[i]);
+  } else {
+    if ((rc = upload_f32(dx, xp)) || (rc = dy.alloc(R * C * 4)) || (rc = upload_f32(dw, wv)) || (rc = upload_f32(db, bv))) return rc;
+    if ((rc = broadcast_launch(dx.p, dw.as<float>(), db.as<float>(), n, C, dy.p, false, dsc.as<float>(), dsh.as<float>(), 0))) return rc;
+    P3_CUDA(cudaDeviceSynchronize());
+    P3_CUDA(cudaMemcpy(yp.data(), dy.p, dy.bytes, cudaMemcpyDeviceToHost));
+  }
+  for (size_t row = 0; row < R; ++row)  // halo rows are part of the contract: they must come back as zeros
+    if (!row_is_live(static_cast<int>(row % kRowsPerPos)))
+      for (int c = 0; c < C; ++c)
+        if (yp[row * C + c] != 0.0f) return fail(P3_ERR_CUDA, "broadcast_test: halo row not zero");
+  for (int b = 0; b < n; ++b)
+    for (int p = 0; p < 361; ++p)
+      std::memcpy(&y[(static_cast<size_t>(b) * 361 + p) * C], &yp[(static_cast<size_t>(b) * kRowsPerPos + board_row(p)) * C], sizeof(float) * C);
   return P3_OK;
 }
 

@@ -233,3 +233,14 @@ def conv_test(x: np.ndarray, w: np.ndarray, precision: int, device: int = 0) -> 
     y = np.zeros((n, NUM_LOCS, cout), dtype=np.float32)
     check(lib.p3_conv_test(device, precision, ptr(x), ptr(w), n, cin, cout, k, ptr(y)))
     return y
+
+
+def broadcast_test(x: np.ndarray, w: np.ndarray, bias: np.ndarray, precision: int, device: int = 0) -> np.ndarray:
+    """x [n,361,C], w [361,361] (in, out), bias [361] -> mish(W^T x + bias) [n,361,C]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    bias = np.ascontiguousarray(bias, dtype=np.float32)
+    n, _, C = x.shape
+    y = np.zeros((n, NUM_LOCS, C), dtype=np.float32)
+    check(lib.p3_broadcast_test(device, precision, ptr(x), ptr(w), ptr(bias), n, C, ptr(y)))
+    return y

@@ -57,3 +57,26 @@ def test_conv_tcgen05_resident_weights(cin, cout, n, monkeypatch):
     y = E.conv_test(x, w, E.PRECISION_BF16)
     ref = _ref_conv(x, w)
     assert np.all(np.abs(y - ref) <= np.abs(ref) * 2.0 ** -8 + 1e-4), f"max abs err {np.abs(y - ref).max()}"
+
+
+def _mish(x):
+    return x * np.tanh(np.log1p(np.exp(x)))
+
+
+@pytest.mark.parametrize("C,n,prec", [(16, 2, "fp32"), (128, 3, "fp32"), (128, 3, "bf16"), (256, 5, "bf16"), (384, 2, "bf16"),
+                                      (192, 2, "bf16")])
+def test_broadcast_mix(C, n, prec):
+    """Board-mixing Dense(361->361) of the broadcast block (python/model.py:570-581) vs numpy in fp64."""
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(C + n)
+    x = rng.standard_normal((n, 361, C)).astype(np.float32)
+    w = (rng.standard_normal((361, 361)) / 19.0).astype(np.float32)
+    bias = (rng.standard_normal(361) * 0.1).astype(np.float32)
+    if prec == "bf16":
+        x, w = _bf16_round(x), _bf16_round(w)
+    y = E.broadcast_test(x, w, bias, E.PRECISION_BF16 if prec == "bf16" else E.PRECISION_FP32)
+    ref = _mish(np.einsum("pq,bpc->bqc", w.astype(np.float64), x.astype(np.float64)) + bias[None, :, None])
+    if prec == "fp32":
+        assert np.abs(y - ref).max() < 2e-5
+    else:
+        assert np.all(np.abs(y - ref) <= np.abs(ref) * 2.0 ** -8 + 2e-4), f"max abs err {np.abs(y - ref).max()}"
