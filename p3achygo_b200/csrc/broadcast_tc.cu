@@ -30,6 +30,7 @@ constexpr int kBMTotal = 512;    // 4 M tiles
 constexpr int kBThreads = 64 + 256;
 constexpr int kBSmemBudget = 224 * 1024;
 constexpr int kBActStage = kBM * 32 * 2;  // 8 KB
+constexpr int kBNumOut = 2;               // double-buffered output staging
 constexpr int kBXBoxBytes = kBK * 128;    // [64 p-rows][64 channels] bf16 = 8 KB
 }  // namespace
 
@@ -81,7 +82,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* st_act = smem;  // 8 KB
-  uint8_t* ring = smem + kBActStage;
+  uint8_t* ring = smem + kBNumOut * kBActStage;
   const int a_bytes = kBM * kBK * 2;  // 16 KB
   const int n_boxes = n_tile / 64;
   const int stage_bytes = a_bytes + n_boxes * kBXBoxBytes;
@@ -128,7 +129,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -136,11 +137,14 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
         decode(tile, b, nt, mt);
         for (int ks = 0; ks < k_steps; ++ks) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          ptx::tma_load_2d(sa, &map_wt, &full_bar[stage], ks * kBK, mt * kBM);
-          for (int j = 0; j < n_boxes; ++j)
-            tma_load_3d(sa + a_bytes + j * kBXBoxBytes, &map_x, &full_bar[stage], nt * n_tile + j * 64, ks * kBK, b);
+          if (ptx::elect_one()) {
+            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            ptx::tma_load_2d(sa, &map_wt, &full_bar[stage], ks * kBK, mt * kBM);
+            for (int j = 0; j < n_boxes; ++j)
+              tma_load_3d(sa + a_bytes + j * kBXBoxBytes, &map_x, &full_bar[stage], nt * n_tile + j * 64, ks * kBK, b);
+          }
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -149,7 +153,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // A K-major, B MN-major (bit 16)
       const uint32_t idesc = ptx::make_idesc_bf16(kBM, n_tile) | (1u << 16);
       int stage = 0;
@@ -165,21 +169,25 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t a_lo = ptx::desc_lo_sw128(sa);
+          const uint64_t db0 = make_desc_mn_sw128(sa + a_bytes, kBXBoxBytes, 1024);
+          const uint32_t b_lo = static_cast<uint32_t>(db0), b_hi = static_cast<uint32_t>(db0 >> 32);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = ptx::make_desc_sw128(sa + k * 32);
-            // 16 K rows = two 8-row groups, 2048 B further down the [rows][128 B] box
-            const uint64_t db = make_desc_mn_sw128(sb + k * 2048, kBXBoxBytes, 1024);
-            ptx::umma_f16(tmem_d, da, db, idesc, (step > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k)
+              // A: +32 B along K; B: 16 K rows = two 8-row groups = 2048 B (128 x 16 B) further down the [rows][128 B] box
+              ptx::umma_f16_lohi(tmem_d, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 128 * k, b_hi, idesc,
+                                 (step > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit(&empty_bar[stage]);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {
@@ -190,6 +198,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
     const bool leader = (threadIdx.x == 64);
     const uint32_t bf_row = static_cast<uint32_t>(r) * 64u;
     const int n_chunks = n_tile / 32;
+    uint32_t g = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       int b, nt, mt;
@@ -201,7 +210,8 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
       const int q = mt * kBM + r;
       const bool live = q < kRowsPerPos && row_is_live(q);
       const float bq = bias_pad[q];
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = 0; c < n_chunks; ++c, ++g) {
+        uint8_t* st_buf = st_act + (g % kBNumOut) * kBActStage;
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc * n_tile + c * 32 + half * 16);
@@ -218,9 +228,9 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           a[j] = live ? mish_f32<false>(fmaf(__uint_as_float(v[j]) + bq, sc[j], sh[j])) : 0.0f;
-        if (leader) ptx::bulk_wait_read_all();
+        if (leader) ptx::bulk_wait_read<kBNumOut - 1>();
         ptx::named_bar_sync(1, 256);
-        uint8_t* wp = st_act + bf_row;
+        uint8_t* wp = st_buf + bf_row;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int o = 8 * j;
@@ -231,7 +241,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
         ptx::fence_proxy_async();
         ptx::named_bar_sync(2, 256);
         if (leader) {
-          tma_store_3d(&map_act, st_act, nt * n_tile + c * 32, mt * kBM, b);  // rows >= 400 are clipped
+          tma_store_3d(&map_act, st_buf, nt * n_tile + c * 32, mt * kBM, b);  // rows >= 400 are clipped
           ptx::bulk_commit();
         }
       }
@@ -305,8 +315,8 @@ int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const 
 
   const int a_bytes = kBM * kBK * 2;
   const int stage_bytes = a_bytes + (p->n_tile / 64) * kBXBoxBytes;
-  p->stages = std::min(6, (kBSmemBudget - 1024 - 512 - kBActStage) / stage_bytes);
-  p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 + 512 + kBActStage;
+  p->stages = std::min(6, (kBSmemBudget - 1024 - 512 - kBNumOut * kBActStage) / stage_bytes);
+  p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 + 512 + kBNumOut * kBActStage;
   int cols = 32;
   while (cols < 2 * p->n_tile) cols *= 2;
   p->tmem_cols = cols;

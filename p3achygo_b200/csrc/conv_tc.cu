@@ -37,16 +37,25 @@ constexpr int kSlabK = 64;  // bf16 elements per 128-byte swizzled row
 constexpr int kUmmaK = 16;
 constexpr int kMaxTapsTc = 9;
 constexpr int kABytes = kTileM * kSlabK * 2;  // 16 KB
-constexpr int kNumEpiWarps = 8;
+// BN + mish in the epilogue is latency-bound unless every scheduler interleaves several warps (ablation on B200):
+// 16 epilogue warps = 4 per scheduler
+constexpr int kNumEpiWarps = 16;
 constexpr int kNumEpiThreads = kNumEpiWarps * 32;
-constexpr int kNumThreads = 64 + kNumEpiThreads;  // 320
+constexpr int kNumThreads = 64 + kNumEpiThreads;  // 576
+constexpr int kMaxCout = 512;
 constexpr int kSmemBudget = 224 * 1024;
-constexpr int kBarBytes = 512;
+constexpr int kBarBytes = 512 + 2 * kMaxCout * 4;  // barriers + tmem ptr, then folded-BN scale / shift of this layer
 constexpr int kMaxNTile = 128;
-// generic kernel staging: 2 residual tiles + 1 raw tile (128 rows x 32 fp32) + 1 act tile (128 rows x 32 bf16)
+// generic kernel staging tiles: 128 rows x 32 columns.  Residual tiles are prefetched kNumResBuf chunks ahead (TMA
+// load latency ~1.5 us vs ~1 us of HBM time per chunk); output tiles are double-buffered so the epilogue never waits
+// for a bulk store to drain (measured: single-buffered staging cost ~1.5 us per chunk).
 constexpr int kStageF32Bytes = kTileM * 32 * 4;   // 16 KB
 constexpr int kStageBf16Bytes = kTileM * 32 * 2;  // 8 KB
-constexpr int kStagingBytes = 3 * kStageF32Bytes + kStageBf16Bytes;  // 56 KB
+constexpr int kNumResBuf = 4;
+constexpr int kNumOutBuf = 2;
+__host__ __device__ constexpr int staging_bytes(bool res, bool raw, bool act) {
+  return (res ? kNumResBuf * kStageF32Bytes : 0) + (raw ? kNumOutBuf * kStageF32Bytes : 0) + (act ? kNumOutBuf * kStageBf16Bytes : 0);
+}
 
 struct TcTaps {
   int off[kMaxTapsTc];
@@ -59,6 +68,7 @@ struct TcConvPlan {
   TcTaps tap;
   ConvEpilogue ep;
   bool resident = false;  // tc_conv3x3_res_kernel
+  int debug = 0;          // P3_TC_DEBUG ablation bits (perf experiments only; results are wrong when set)
 };
 
 namespace {
@@ -85,19 +95,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
                const float* __restrict__ shift, int act_mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [staging 56 KB] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
+  // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* st_res = smem;                         // 2 x 16 KB
-  uint8_t* st_raw = smem + 2 * kStageF32Bytes;    // 16 KB
-  uint8_t* st_act = smem + 3 * kStageF32Bytes;    // 8 KB
-  uint8_t* ring = smem + kStagingBytes;
+  uint8_t* st_res = smem;
+  uint8_t* st_raw = st_res + (has_res ? kNumResBuf * kStageF32Bytes : 0);
+  uint8_t* st_act = st_raw + (has_raw ? kNumOutBuf * kStageF32Bytes : 0);
+  uint8_t* ring = smem + staging_bytes(has_res, has_raw, has_act);
   const int stage_bytes = kABytes + n_tile * kSlabK * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + kNumResBuf);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);
+  float* s_shift = s_scale + kMaxCout;
+  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+    s_scale[c] = act_mode == kActMishBN ? scale[c] : 1.0f;
+    s_shift[c] = act_mode == kActMishBN ? shift[c] : 0.0f;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (rows + kTileM - 1) / kTileM;
@@ -117,8 +133,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], kNumEpiWarps);
-      ptx::mbar_init(&res_full[s], 1);
     }
+    for (int s = 0; s < kNumResBuf; ++s) ptx::mbar_init(&res_full[s], 1);
     ptx::fence_mbar_init();
   } else if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr, static_cast<uint32_t>(tmem_cols));
@@ -130,8 +146,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -139,10 +155,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int t = 0; t < taps; ++t) {
           for (int ks = 0; ks < k_slabs; ++ks) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            ptx::tma_load_2d(sa, &map_a, &full_bar[stage], ks * kSlabK, m0 + tap.off[t]);
-            ptx::tma_load_2d(sa + kABytes, &map_w, &full_bar[stage], ks * kSlabK, t * cout + n0);
+            if (ptx::elect_one()) {
+              uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              ptx::tma_load_2d(sa, &map_a, &full_bar[stage], ks * kSlabK, m0 + tap.off[t]);
+              ptx::tma_load_2d(sa + kABytes, &map_w, &full_bar[stage], ks * kSlabK, t * cout + n0);
+            }
+            __syncwarp();
             if (++stage == stages) {
               stage = 0;
               phase ^= 1;
@@ -152,8 +171,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-converged loop, tcgen05.mma / commit issued by one elected lane =====
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(kTileM, n_tile);
       int stage = 0;
       uint32_t phase = 0;
@@ -168,45 +187,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t a_lo = ptx::desc_lo_sw128(sa), b_lo = ptx::desc_lo_sw128(sa + kABytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kSlabK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzled row
-            const uint64_t da = ptx::make_desc_sw128(sa + k * kUmmaK * 2);
-            const uint64_t db = ptx::make_desc_sw128(sb + k * kUmmaK * 2);
-            ptx::umma_f16(tmem_d, da, db, idesc, (step > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kSlabK / kUmmaK; ++k)  // +32 bytes (2 x 16 B) along K inside the 128-byte swizzled row
+              ptx::umma_f16_lohi(tmem_d, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 2 * k, ptx::desc_hi_sw128(), idesc,
+                                 (step > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs have read it
           }
-          ptx::umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {
-    // ===== epilogue: 8 warps; the warp pair of a quarter shares TMEM lanes [32q, 32q+32), each warp takes 16 of
-    // the 32 columns of a chunk.  Thread = one output row.  All global traffic goes through TMA. =====
+    // ===== epilogue: 16 warps; the 4 warps of a quarter share TMEM lanes [32q, 32q+32), each takes 8 of the 32
+    // columns of a chunk.  Thread = one output row.  All global traffic goes through TMA. =====
     const int ew = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int half = (ew >> 2) & 1;     // which 16 columns of each 32-column chunk
+    const int cg = ew >> 2;             // which 8 columns of each 32-column chunk
     const int r = quarter * 32 + lane;  // row within the tile
     const bool leader = (threadIdx.x == 64);
     // this thread's row inside a 128 B-row (fp32, 128B swizzle) / 64 B-row (bf16, 64B swizzle) staging tile
     const uint32_t f32_row = static_cast<uint32_t>(r) * 128u;
     const uint32_t bf_row = static_cast<uint32_t>(r) * 64u;
-    uint32_t g = 0;  // running chunk counter (residual double buffer + parity)
+    uint32_t g = 0;  // running chunk counter (residual ring + parity)
 
     auto issue_res = [&](uint32_t gi, int tile_i, int ci) {
       const int m0i = (tile_i / n_tiles) * kTileM, n0i = (tile_i % n_tiles) * n_tile;
-      const uint32_t b = gi & 1u;
+      const uint32_t b = gi % kNumResBuf;
       ptx::mbar_arrive_expect_tx(&res_full[b], kStageF32Bytes);
       ptx::tma_load_2d(st_res + b * kStageF32Bytes, &map_res, &res_full[b], n0i + ci * 32, m0i);
     };
-    if (leader && has_res) {  // prefetch the residual tiles of the first two chunks
+    if (leader && has_res) {  // prefetch the residual tiles of the first kNumResBuf chunks
       int t0 = blockIdx.x, c = 0;
-      for (uint32_t gi = 0; gi < 2 && t0 < total_tiles; ++gi) {
+      for (uint32_t gi = 0; gi < kNumResBuf && t0 < total_tiles; ++gi) {
         issue_res(gi, t0, c);
         if (++c == n_chunks) {
           c = 0;
@@ -226,18 +246,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
 
       for (int c = 0; c < n_chunks; ++c, ++g) {
-        const uint32_t buf = g & 1u;
-        uint32_t v[16];
+        const uint32_t buf = g % kNumResBuf;
+        const uint32_t obuf = g % kNumOutBuf;
+        uint32_t v[8];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * n_tile + c * 32 + half * 16);
-        ptx::tmem_ld_32x16(taddr, v);
-        float x[16];
+                               static_cast<uint32_t>(acc * n_tile + c * 32 + cg * 8);
+        ptx::tmem_ld_32x8(taddr, v);
+        float x[8];
         if (has_res) {
-          ptx::mbar_wait(&res_full[buf], (g >> 1) & 1u);
+          ptx::mbar_wait(&res_full[buf], (g / kNumResBuf) & 1u);
           const uint8_t* rp = st_res + buf * kStageF32Bytes + f32_row;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((half * 4 + j) ^ (r & 7)) << 4));
+          for (int j = 0; j < 2; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((cg * 2 + j) ^ (r & 7)) << 4));
             x[4 * j] = t4.x;
             x[4 * j + 1] = t4.y;
             x[4 * j + 2] = t4.z;
@@ -245,59 +266,50 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = 0.0f;
+          for (int j = 0; j < 8; ++j) x[j] = 0.0f;
         }
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
+        for (int j = 0; j < 8; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
+        uint4 pk = make_uint4(0, 0, 0, 0);
+        if (has_act) {  // activation math before the barrier: it overlaps other warps' staging traffic
+          const int nb = n0 + c * 32 + cg * 8;
+          float a[8];
+          if (act_mode == kActIdentity) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = x[j];
+          } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = live ? mish_f32<false>(fmaf(x[j], s_scale[nb + j], s_shift[nb + j])) : 0.0f;
+          }
+          pk = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+        }
 
-        // staging free? the previous chunk's bulk stores have read it, and everyone is done with st_res[buf]
-        if (leader) ptx::bulk_wait_read_all();
+        // output staging buffer `obuf` free? (the bulk stores issued kNumOutBuf chunks ago have read it), and
+        // everyone is done with st_res[buf]
+        if (leader) ptx::bulk_wait_read<kNumOutBuf - 1>();
         ptx::named_bar_sync(1, kNumEpiThreads);
-        if (leader && has_res) {  // refill the residual buffer just consumed with chunk g+2
-          int t2 = tile, c2 = c + 2;
+        if (leader && has_res) {  // refill the residual buffer just consumed with chunk g + kNumResBuf
+          int t2 = tile, c2 = c + kNumResBuf;
           while (c2 >= n_chunks) {
             c2 -= n_chunks;
             t2 += gridDim.x;
           }
-          if (t2 < total_tiles) issue_res(g + 2, t2, c2);
+          if (t2 < total_tiles) issue_res(g + kNumResBuf, t2, c2);
         }
         if (has_raw) {
-          uint8_t* wp = st_raw + f32_row;
+          uint8_t* wp = st_raw + obuf * kStageF32Bytes + f32_row;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(wp + (((half * 4 + j) ^ (r & 7)) << 4)) =
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<float4*>(wp + (((cg * 2 + j) ^ (r & 7)) << 4)) =
                 make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
         }
-        if (has_act) {
-          const int nb = n0 + c * 32 + half * 16;
-          float a[16];
-          if (act_mode == kActMishBN) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = activate<kActMishBN>(x[j], __ldg(scale + nb + j), __ldg(shift + nb + j));
-          } else if (act_mode == kActMish) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = activate<kActMish>(x[j], 1.0f, 0.0f);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = x[j];
-          }
-          uint8_t* wp = st_act + bf_row;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int o = 8 * j;
-            const uint4 pk = make_uint4(pack_bf16(live ? a[o] : 0.f, live ? a[o + 1] : 0.f),
-                                        pack_bf16(live ? a[o + 2] : 0.f, live ? a[o + 3] : 0.f),
-                                        pack_bf16(live ? a[o + 4] : 0.f, live ? a[o + 5] : 0.f),
-                                        pack_bf16(live ? a[o + 6] : 0.f, live ? a[o + 7] : 0.f));
-            *reinterpret_cast<uint4*>(wp + (((half * 2 + j) ^ ((r >> 1) & 3)) << 4)) = pk;
-          }
-        }
+        if (has_act) *reinterpret_cast<uint4*>(st_act + obuf * kStageBf16Bytes + bf_row + ((cg ^ ((r >> 1) & 3)) << 4)) = pk;
         ptx::fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
         ptx::named_bar_sync(2, kNumEpiThreads);
         if (leader) {
-          if (has_raw) ptx::tma_store_2d(&map_raw, st_raw, n0 + c * 32, m0);
-          if (has_act) ptx::tma_store_2d(&map_act, st_act, n0 + c * 32, m0);
+          if (has_raw) ptx::tma_store_2d(&map_raw, st_raw + obuf * kStageF32Bytes, n0 + c * 32, m0);
+          if (has_act) ptx::tma_store_2d(&map_act, st_act + obuf * kStageBf16Bytes, n0 + c * 32, m0);
           ptx::bulk_commit();
         }
       }
@@ -336,11 +348,15 @@ constexpr int kResRows = 176;
 constexpr int kResABytes = kResRows * 128;   // 22 528 B, a multiple of 1024
 constexpr int kResWSlabBytes = kResN * 128;  // 8 KB per (tap, 64-channel slab)
 constexpr int kResStages = 3;
+// the epilogue is BN + mish on 8192 elements per tile: latency-bound unless every scheduler has several warps to
+// interleave (ablation on B200: math alone took 1.8x the MMA time with 8 epilogue warps) -> 16 warps, 4 per scheduler
+constexpr int kResEpiWarps = 16;
+constexpr int kResThreads = 64 + kResEpiWarps * 32;  // 576
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kResThreads, 1)
 tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
                       int cin, int cout, TcTaps tap, __nv_bfloat16* __restrict__ act_out,
-                      const float* __restrict__ scale, const float* __restrict__ shift, int act_mode) {
+                      const float* __restrict__ scale, const float* __restrict__ shift, int act_mode, int debug) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k_slabs = cin / kSlabK;
@@ -371,7 +387,7 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], kNumEpiWarps);
+      ptx::mbar_init(&tmem_empty[s], kResEpiWarps);
     }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_mbar_init();
@@ -385,20 +401,30 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // resident weights: all taps x slabs of this CTA's 64 output channels, once
-      ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(w_bytes));
-      for (int t = 0; t < 9; ++t)
-        for (int ks = 0; ks < k_slabs; ++ks)
-          ptx::tma_load_2d(smem_w + (t * k_slabs + ks) * kResWSlabBytes, &map_w, w_bar, ks * kSlabK, t * cout + n0);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(w_bytes));
+        for (int t = 0; t < 9; ++t)
+          for (int ks = 0; ks < k_slabs; ++ks)
+            ptx::tma_load_2d(smem_w + (t * k_slabs + ks) * kResWSlabBytes, &map_w, w_bar, ks * kSlabK, t * cout + n0);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int mt = cta_in_slice; mt < m_tiles; mt += ctas_per_slice) {
         const int m0 = mt * kTileM;
         for (int ks = 0; ks < k_slabs; ++ks) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], kResABytes);
-          ptx::tma_load_2d(smem_a + stage * kResABytes, &map_a, &full_bar[stage], ks * kSlabK, m0 - kResHalo);
+          if (ptx::elect_one()) {
+            if (debug & 2) {
+              ptx::mbar_arrive(&full_bar[stage]);  // ablation: no A traffic
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], kResABytes);
+              ptx::tma_load_2d(smem_a + stage * kResABytes, &map_a, &full_bar[stage], ks * kSlabK, m0 - kResHalo);
+            }
+          }
+          __syncwarp();
           if (++stage == kResStages) {
             stage = 0;
             phase ^= 1;
@@ -407,9 +433,13 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kResN);
-      const uint32_t w_base = ptx::smem_u32(smem_w);
+      const uint32_t w_lo_base = ptx::desc_lo_sw128(ptx::smem_u32(smem_w));
+      const uint32_t w_tap_stride = static_cast<uint32_t>(k_slabs) * (kResWSlabBytes / 16);
+      uint32_t tap_lo[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_lo[t] = static_cast<uint32_t>(kResHalo + tap.off[t]) * 8u;
       ptx::mbar_wait(w_bar, 0);
       ptx::tc_fence_after_sync();
       int stage = 0;
@@ -424,34 +454,46 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int ks = 0; ks < k_slabs; ++ks) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
-          const uint32_t a_tile = ptx::smem_u32(smem_a + stage * kResABytes);
+          const uint32_t a_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a + stage * kResABytes));
+          const uint32_t w_lo = w_lo_base + static_cast<uint32_t>(ks) * (kResWSlabBytes / 16);
+          if (ptx::elect_one()) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            // tap (dy,dx) = shifted view: skip (21 + dy*20 + dx) rows of 128 B inside the swizzled tile
-            const uint32_t a_view = a_tile + static_cast<uint32_t>(kResHalo + tap.off[t]) * 128u;
-            const uint32_t w_slab = w_base + static_cast<uint32_t>((t * k_slabs + ks) * kResWSlabBytes);
+            if (debug & 4) continue;  // ablation: no MMAs
+            // tap (dy,dx) = shifted view: skip (21 + dy*20 + dx) rows of 128 B (8 x 16 B) inside the swizzled tile;
+            // weights of (tap t, slab ks) sit (t*k_slabs + ks) * 8 KB into the resident block
+            const uint32_t a_t = a_lo + tap_lo[t];
+            const uint32_t w_t = w_lo + static_cast<uint32_t>(t) * w_tap_stride;
 #pragma unroll
-            for (int k = 0; k < kSlabK / kUmmaK; ++k) {
-              const uint64_t da = ptx::make_desc_sw128(a_view + k * kUmmaK * 2);
-              const uint64_t db = ptx::make_desc_sw128(w_slab + k * kUmmaK * 2);
-              ptx::umma_f16(tmem_d, da, db, idesc, (ks > 0 || t > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < kSlabK / kUmmaK; ++k)
+              ptx::umma_f16_lohi(tmem_d, a_t + 2 * k, ptx::desc_hi_sw128(), w_t + 2 * k, ptx::desc_hi_sw128(), idesc,
+                                 (ks > 0 || t > 0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kResStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {
-    // epilogue: 8 warps, thread = one output row, 32 of the slice's 64 columns each; writes only the bf16
-    // activated copy (16 KB per tile), so plain 16-byte stores are enough here
+    // epilogue: 16 warps (4 per TMEM lane quarter), thread = one output row x 16 of the slice's 64 columns; writes only
+    // the bf16 activated copy (16 KB per tile).  The folded BN of the 16 columns lives in registers for the whole launch.
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int half = (ew >> 2) & 1;
+    const int cg = ew >> 2;  // column group 0..3
+    const int nb = n0 + cg * 16;
+    float sc[16], sh[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      sc[i] = act_mode == kActMishBN ? __ldg(scale + nb + i) : 1.0f;
+      sh[i] = act_mode == kActMishBN ? __ldg(shift + nb + i) : 0.0f;
+    }
     int iter = 0;
     for (int mt = cta_in_slice; mt < m_tiles; mt += ctas_per_slice, ++iter) {
       const int acc = iter & 1;
@@ -461,33 +503,34 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int m = mt * kTileM + quarter * 32 + lane;
       const bool in_range = m < rows;
       const bool live = in_range && row_is_live(m % kRowsPerPos);
-      const int nb = n0 + half * 32;
-      uint32_t v[32];
+      uint32_t v[16];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * kResN + half * 32);
-      ptx::tmem_ld_32x32(taddr, v);
+                             static_cast<uint32_t>(acc * kResN + cg * 16);
+      ptx::tmem_ld_32x16(taddr, v);
       ptx::tmem_ld_wait();
       // accumulator values are in registers: release the TMEM stage before the math
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      if (in_range) {
-        uint32_t packed[16];
+      if (in_range && !(debug & 1)) {  // ablation bit 0: no epilogue math / stores
+        uint32_t packed[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
-          if (act_mode == kActMishBN) {
-            a0 = activate<kActMishBN>(a0, __ldg(scale + nb + 2 * i), __ldg(shift + nb + 2 * i));
-            a1 = activate<kActMishBN>(a1, __ldg(scale + nb + 2 * i + 1), __ldg(shift + nb + 2 * i + 1));
-          } else if (act_mode == kActMish) {
-            a0 = activate<kActMish>(a0, 1.f, 0.f);
-            a1 = activate<kActMish>(a1, 1.f, 0.f);
+          if (debug & 16) {
+            // ablation: no activation math
+          } else if (act_mode == kActIdentity) {
+          } else {  // kActMishBN (scale/shift) or kActMish (1, 0)
+            a0 = mish_f32<false>(fmaf(a0, sc[2 * i], sh[2 * i]));
+            a1 = mish_f32<false>(fmaf(a1, sc[2 * i + 1], sh[2 * i + 1]));
           }
           packed[i] = pack_bf16(live ? a0 : 0.0f, live ? a1 : 0.0f);
         }
         uint4* ap = reinterpret_cast<uint4*>(act_out + static_cast<size_t>(m) * cout + nb);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ap[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        if (!(debug & 8) || packed[0] == 0x12345678u) {  // ablation bit 3: no stores
+          ap[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          ap[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
       }
     }
   }
@@ -562,6 +605,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const char* env_res = std::getenv("P3_TC_RESIDENT");
+  if (const char* dbg = std::getenv("P3_TC_DEBUG")) p->debug = std::atoi(dbg);
   const size_t res_smem =
       static_cast<size_t>(9) * (cin / kSlabK) * kResWSlabBytes + kResStages * kResABytes + 1024 + kBarBytes;
   bool shifts_ok = taps == 9;
@@ -587,8 +631,9 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   } else {
     p->n_tile = pick_n_tile(cout);
     const int stage_bytes = kABytes + p->n_tile * kSlabK * 2;
-    p->stages = std::min(8, (kSmemBudget - 1024 - kBarBytes - kStagingBytes) / stage_bytes);
-    p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 /*align slack*/ + kBarBytes + kStagingBytes;
+    const int staging = staging_bytes(ep.residual != nullptr, ep.raw_out != nullptr, ep.act_out != nullptr);
+    p->stages = std::min(8, (kSmemBudget - 1024 - kBarBytes - staging) / stage_bytes);
+    p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 /*align slack*/ + kBarBytes + staging;
     int cols = 32;
     while (cols < 2 * p->n_tile) cols *= 2;
     p->tmem_cols = cols;
@@ -628,9 +673,9 @@ void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
   if (p->resident) {
-    tc_conv3x3_res_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
+    tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
-        ep.shift, ep.act_mode);
+        ep.shift, ep.act_mode, p->debug);
   } else {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
