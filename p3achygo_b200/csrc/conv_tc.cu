@@ -93,7 +93,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
-               const float* __restrict__ shift, int act_mode) {
+               const float* __restrict__ shift, int act_mode, int debug) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -157,9 +157,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (ptx::elect_one()) {
               uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-              ptx::tma_load_2d(sa, &map_a, &full_bar[stage], ks * kSlabK, m0 + tap.off[t]);
-              ptx::tma_load_2d(sa + kABytes, &map_w, &full_bar[stage], ks * kSlabK, t * cout + n0);
+              if (debug & 2) {
+                ptx::mbar_arrive(&full_bar[stage]);  // ablation: no A / W traffic
+              } else {
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+                ptx::tma_load_2d(sa, &map_a, &full_bar[stage], ks * kSlabK, m0 + tap.off[t]);
+                ptx::tma_load_2d(sa + kABytes, &map_w, &full_bar[stage], ks * kSlabK, t * cout + n0);
+              }
             }
             __syncwarp();
             if (++stage == stages) {
@@ -191,8 +195,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < kSlabK / kUmmaK; ++k)  // +32 bytes (2 x 16 B) along K inside the 128-byte swizzled row
-              ptx::umma_f16_lohi(tmem_d, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 2 * k, ptx::desc_hi_sw128(), idesc,
-                                 (step > 0 || k > 0) ? 1u : 0u);
+              if (!(debug & 4))
+                ptx::umma_f16_lohi(tmem_d, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 2 * k, ptx::desc_hi_sw128(), idesc,
+                                   (step > 0 || k > 0) ? 1u : 0u);
             ptx::umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs have read it
           }
           __syncwarp();
@@ -206,33 +211,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: 16 warps; the 4 warps of a quarter share TMEM lanes [32q, 32q+32), each takes 8 of the 32
-    // columns of a chunk.  Thread = one output row.  All global traffic goes through TMA. =====
+    // ===== epilogue: 16 warps in TWO independent groups of 8.  The chunks (32 output columns) of this CTA's tiles are
+    // numbered G = 0, 1, 2, ...; group `grp` handles the chunks with G % 2 == grp, so two chunks are always in flight
+    // (one chunk is a serial chain: tcgen05.ld -> residual -> BN+mish -> staging -> fence -> TMA store; measured
+    // ~1.5 us end to end, which bounded the 1x1 layers when all 16 warps marched through it in lock step).
+    // Within a group: 2 warps per TMEM lane quarter, 16 columns each; thread = one output row.  All global traffic
+    // goes through TMA; each group owns its staging tiles, named barriers, residual ring and bulk-store groups. =====
     const int ew = warp - 2;
-    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int cg = ew >> 2;             // which 8 columns of each 32-column chunk
-    const int r = quarter * 32 + lane;  // row within the tile
-    const bool leader = (threadIdx.x == 64);
+    const int grp = ew >> 3;              // epilogue group 0 / 1
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = (ew >> 2) & 1;       // which 16 columns of the 32-column chunk
+    const int r = quarter * 32 + lane;    // row within the tile
+    const bool leader = (ew & 7) == 0 && lane == 0;
+    const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+    constexpr int kGrpThreads = 256;
     // this thread's row inside a 128 B-row (fp32, 128B swizzle) / 64 B-row (bf16, 64B swizzle) staging tile
     const uint32_t f32_row = static_cast<uint32_t>(r) * 128u;
     const uint32_t bf_row = static_cast<uint32_t>(r) * 64u;
-    uint32_t g = 0;  // running chunk counter (residual ring + parity)
+    uint8_t* my_res = st_res + grp * (2 * kStageF32Bytes);   // 2-deep residual ring per group
+    uint8_t* my_raw = st_raw + grp * kStageF32Bytes;
+    uint8_t* my_act = st_act + grp * kStageBf16Bytes;
+    uint64_t* my_res_full = res_full + 2 * grp;
 
-    auto issue_res = [&](uint32_t gi, int tile_i, int ci) {
+    // residual tile of global chunk G -> ring slot (G/2) & 1 of this group
+    auto issue_res = [&](uint32_t G) {
+      const int tile_i = blockIdx.x + static_cast<int>(G / n_chunks) * gridDim.x;
+      if (tile_i >= total_tiles) return;
+      const int ci = static_cast<int>(G % n_chunks);
       const int m0i = (tile_i / n_tiles) * kTileM, n0i = (tile_i % n_tiles) * n_tile;
-      const uint32_t b = gi % kNumResBuf;
-      ptx::mbar_arrive_expect_tx(&res_full[b], kStageF32Bytes);
-      ptx::tma_load_2d(st_res + b * kStageF32Bytes, &map_res, &res_full[b], n0i + ci * 32, m0i);
+      const uint32_t b = (G >> 1) & 1u;
+      ptx::mbar_arrive_expect_tx(&my_res_full[b], kStageF32Bytes);
+      ptx::tma_load_2d(my_res + b * kStageF32Bytes, &map_res, &my_res_full[b], n0i + ci * 32, m0i);
     };
-    if (leader && has_res) {  // prefetch the residual tiles of the first kNumResBuf chunks
-      int t0 = blockIdx.x, c = 0;
-      for (uint32_t gi = 0; gi < kNumResBuf && t0 < total_tiles; ++gi) {
-        issue_res(gi, t0, c);
-        if (++c == n_chunks) {
-          c = 0;
-          t0 += gridDim.x;
-        }
-      }
+    if (leader && has_res) {  // prefetch this group's first two chunks
+      issue_res(grp);
+      issue_res(grp + 2);
     }
 
     int iter = 0;
@@ -240,25 +253,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m0 = (tile / n_tiles) * kTileM, n0 = (tile % n_tiles) * n_tile;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after_sync();
       const int m = m0 + r;
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
+      bool waited = false;
 
-      for (int c = 0; c < n_chunks; ++c, ++g) {
-        const uint32_t buf = g % kNumResBuf;
-        const uint32_t obuf = g % kNumOutBuf;
-        uint32_t v[8];
+      for (int c = 0; c < ((debug & 1) ? 0 : n_chunks); ++c) {
+        const uint32_t G = static_cast<uint32_t>(iter) * n_chunks + c;
+        if ((G & 1u) != static_cast<uint32_t>(grp)) continue;
+        if (!waited) {
+          ptx::mbar_wait(&tmem_full[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+          waited = true;
+        }
+        const uint32_t k = G >> 1;  // this group's chunk ordinal
+        const uint32_t buf = k & 1u;
+        uint32_t v[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * n_tile + c * 32 + cg * 8);
-        ptx::tmem_ld_32x8(taddr, v);
-        float x[8];
+                               static_cast<uint32_t>(acc * n_tile + c * 32 + half * 16);
+        ptx::tmem_ld_32x16(taddr, v);
+        float x[16];
         if (has_res) {
-          ptx::mbar_wait(&res_full[buf], (g / kNumResBuf) & 1u);
-          const uint8_t* rp = st_res + buf * kStageF32Bytes + f32_row;
+          ptx::mbar_wait(&my_res_full[buf], (k >> 1) & 1u);
+          const uint8_t* rp = my_res + buf * kStageF32Bytes + f32_row;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((cg * 2 + j) ^ (r & 7)) << 4));
+          for (int j = 0; j < 4; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((half * 4 + j) ^ (r & 7)) << 4));
             x[4 * j] = t4.x;
             x[4 * j + 1] = t4.y;
             x[4 * j + 2] = t4.z;
@@ -266,54 +285,55 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+          for (int j = 0; j < 16; ++j) x[j] = 0.0f;
         }
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
-        uint4 pk = make_uint4(0, 0, 0, 0);
-        if (has_act) {  // activation math before the barrier: it overlaps other warps' staging traffic
-          const int nb = n0 + c * 32 + cg * 8;
-          float a[8];
-          if (act_mode == kActIdentity) {
+        for (int j = 0; j < 16; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
+        uint4 pk0 = make_uint4(0, 0, 0, 0), pk1 = pk0;
+        if (has_act) {
+          const int nb = n0 + c * 32 + half * 16;
+          float a[16];
+          if (act_mode == kActIdentity || (debug & 16)) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = x[j];
+            for (int j = 0; j < 16; ++j) a[j] = x[j];
           } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = live ? mish_f32<false>(fmaf(x[j], s_scale[nb + j], s_shift[nb + j])) : 0.0f;
+            for (int j = 0; j < 16; ++j) a[j] = live ? mish_f32<false>(fmaf(x[j], s_scale[nb + j], s_shift[nb + j])) : 0.0f;
           }
-          pk = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+          pk0 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+          pk1 = make_uint4(pack_bf16(a[8], a[9]), pack_bf16(a[10], a[11]), pack_bf16(a[12], a[13]), pack_bf16(a[14], a[15]));
         }
 
-        // output staging buffer `obuf` free? (the bulk stores issued kNumOutBuf chunks ago have read it), and
-        // everyone is done with st_res[buf]
-        if (leader) ptx::bulk_wait_read<kNumOutBuf - 1>();
-        ptx::named_bar_sync(1, kNumEpiThreads);
-        if (leader && has_res) {  // refill the residual buffer just consumed with chunk g + kNumResBuf
-          int t2 = tile, c2 = c + kNumResBuf;
-          while (c2 >= n_chunks) {
-            c2 -= n_chunks;
-            t2 += gridDim.x;
-          }
-          if (t2 < total_tiles) issue_res(g + kNumResBuf, t2, c2);
-        }
+        // group staging free? (the group's previous bulk stores have read it) and everyone is done with my_res[buf]
+        if (leader) ptx::bulk_wait_read<0>();
+        ptx::named_bar_sync(bar_a, kGrpThreads);
+        if (leader && has_res) issue_res(G + 4);  // refill the ring slot just consumed with this group's chunk k + 2
         if (has_raw) {
-          uint8_t* wp = st_raw + obuf * kStageF32Bytes + f32_row;
+          uint8_t* wp = my_raw + f32_row;
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<float4*>(wp + (((cg * 2 + j) ^ (r & 7)) << 4)) =
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(wp + (((half * 4 + j) ^ (r & 7)) << 4)) =
                 make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
         }
-        if (has_act) *reinterpret_cast<uint4*>(st_act + obuf * kStageBf16Bytes + bf_row + ((cg ^ ((r >> 1) & 3)) << 4)) = pk;
+        if (has_act) {
+          uint8_t* wp = my_act + bf_row;
+          *reinterpret_cast<uint4*>(wp + (((half * 2 + 0) ^ ((r >> 1) & 3)) << 4)) = pk0;
+          *reinterpret_cast<uint4*>(wp + (((half * 2 + 1) ^ ((r >> 1) & 3)) << 4)) = pk1;
+        }
         ptx::fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
-        ptx::named_bar_sync(2, kNumEpiThreads);
-        if (leader) {
-          if (has_raw) ptx::tma_store_2d(&map_raw, st_raw + obuf * kStageF32Bytes, n0 + c * 32, m0);
-          if (has_act) ptx::tma_store_2d(&map_act, st_act + obuf * kStageBf16Bytes, n0 + c * 32, m0);
+        ptx::named_bar_sync(bar_b, kGrpThreads);
+        if (leader && !(debug & 8)) {
+          if (has_raw) ptx::tma_store_2d(&map_raw, my_raw, n0 + c * 32, m0);
+          if (has_act) ptx::tma_store_2d(&map_act, my_act, n0 + c * 32, m0);
           ptx::bulk_commit();
         }
       }
-      // accumulator drained -> hand it back to the MMA warp
+      if (!waited) {  // (only with the ablation that skips all chunks) still consume the accumulator
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+      }
+      // this warp is done with the accumulator -> hand it back to the MMA warp (16 arrivals)
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -675,12 +695,12 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
-        ep.shift, ep.act_mode, p->debug);
+        ep.shift, ep.act_mode, p->debug & 0xff);
   } else {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
-        p->stages, p->tmem_cols, ep.residual != nullptr, ep.raw_out != nullptr, ep.act_out != nullptr, ep.scale, ep.shift,
-        ep.act_mode);
+        p->stages, p->tmem_cols, ep.residual != nullptr && !(p->debug & 32), ep.raw_out != nullptr, ep.act_out != nullptr,
+        ep.scale, ep.shift, ep.act_mode, p->debug >> 8);
   }
   P3_CUDA(cudaGetLastError());
   return P3_OK;
