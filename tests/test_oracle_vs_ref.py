@@ -1,0 +1,113 @@
+"""CPU (only where the compiled reference is available: oracle/_ref/libp3ref.so, built from /root/reference by
+oracle/Makefile): pins the C restatement against the reference's own code on FRESH seeded positions, beyond the committed
+golden vectors — including the 10-move position of cc/nn/__tests__/nn_board_utils_test.cc."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle_lib
+from oracle.oracle_lib import P
+
+R = oracle_lib.ref()
+pytestmark = pytest.mark.skipif(R is None, reason="compiled reference not available on this machine")
+
+FEAT = np.dtype({"names": ["bsize", "color", "komi", "board", "last_moves", "a", "b", "c", "d"],
+                 "formats": ["<i4", "i1", "<f4", ("i1", 361), ("<i4", (5, 2)), ("i1", 361), ("i1", 361), ("i1", 361), ("i1", 361)],
+                 "offsets": [0, 4, 8, 12, 376, 416, 777, 1138, 1499], "itemsize": 1860})
+
+
+def _playout(rng, n_moves, komi=7.5):
+    g = R.ref_game_new(komi, 1)
+    mask = np.zeros(362, dtype=np.uint8)
+    color = 1
+    for _ in range(n_moves):
+        R.ref_game_legal_mask(g, color, P(mask))
+        cand = np.flatnonzero(mask[:361])
+        if len(cand) == 0 or rng.random() < 0.03:
+            R.ref_game_play(g, 19, 0, color)
+        else:
+            m = int(rng.choice(cand))
+            assert R.ref_game_play(g, m // 19, m % 19, color) == 1
+        color = -color
+        if R.ref_game_is_over(g):
+            break
+    return g, color
+
+
+def test_features_planes_liberties_legal_on_fresh_positions():
+    rng = np.random.default_rng(4242)
+    L = oracle_lib.oracle()
+    for trial in range(40):
+        g, color = _playout(rng, int(rng.integers(1, 280)), komi=float(rng.choice([0.5, 6.5, 7.5])))
+        sym = int(rng.integers(0, 8))
+        f = np.zeros(1, dtype=FEAT)
+        R.ref_game_features(g, color, sym, P(f))
+        for version, (npl, ns) in ((1, (15, 8)), (0, (13, 7))):
+            rp, rs = np.empty((1, 19, 19, npl), np.float32), np.empty((1, ns), np.float32)
+            R.ref_load_go_features(P(f), 1, version, P(rp), P(rs))
+            op, os_ = oracle_lib.load_go_features(f, version)
+            assert np.array_equal(rp, op) and np.array_equal(rs.view(np.uint32), os_.view(np.uint32))
+        board = np.zeros(361, np.int8)
+        R.ref_game_board(g, P(board))
+        for n in (1, 2, 3):
+            ref_grid, got = np.zeros(361, np.int8), np.zeros(361, np.int8)
+            R.ref_game_liberties(g, n, P(ref_grid))
+            L.orc_stones_with_liberties(P(board), n, P(got))
+            assert np.array_equal(ref_grid, got)
+        legal = np.zeros(362, np.uint8)
+        R.ref_game_legal_mask(g, color, P(legal))
+        got = oracle_lib.legal_mask_nohist(board[None], np.array([color], np.int8))[0]
+        assert np.all(got >= legal)
+        forb = (got != legal)[:361].astype(np.int8)
+        assert np.array_equal(oracle_lib.legal_mask_nohist(board[None], np.array([color], np.int8), forb[None])[0], legal)
+        R.ref_game_free(g)
+
+
+def test_nn_board_utils_position():
+    """cc/nn/__tests__/nn_board_utils_test.cc:55-125: B(0,0) W(1,0) B(0,1) W(1,1) ... 10 alternating moves; identity symmetry."""
+    g = R.ref_game_new(7.5, 1)
+    moves = [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2), (0, 3), (1, 3), (0, 4), (1, 4)]
+    color = 1
+    for (i, j) in moves:
+        assert R.ref_game_play(g, i, j, color) == 1
+        color = -color
+    f = np.zeros(1, dtype=FEAT)
+    R.ref_game_features(g, 1, 0, P(f))
+    planes, scalars = oracle_lib.load_go_features(f, 1)
+    rp, rs = np.empty((1, 19, 19, 15), np.float32), np.empty((1, 8), np.float32)
+    R.ref_load_go_features(P(f), 1, 1, P(rp), P(rs))
+    assert np.array_equal(planes, rp) and np.array_equal(scalars, rs)
+    assert planes[0, :, :, 0].sum() == 5 and planes[0, :, :, 1].sum() == 5       # own / opponent stones
+    for k, (i, j) in enumerate(moves[-5:]):                                       # history oldest -> newest on planes 2..6
+        assert planes[0, i, j, 2 + k] == 1.0
+    assert list(scalars[0]) == [1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -0.5]          # black to move, komi 7.5 -> -7.5/15
+    R.ref_game_free(g)
+
+
+def test_symmetry_prng_softmax_gumbel_direct():
+    L = oracle_lib.oracle()
+    for s in range(8):
+        for i in range(0, 361, 7):
+            assert L.orc_transform_index(s, i) == R.ref_transform_index(s, i)
+            assert L.orc_transform_inv(s, i) == R.ref_transform_inv(s, i)
+    rng = np.random.default_rng(5)
+    for seed in (3, 99, 2 ** 50 + 1):
+        p = R.ref_prob_new(seed)
+        st = ctypes.c_uint64(L.orc_prng_seed(seed))
+        for _ in range(200):
+            assert np.float32(R.ref_prob_gumbel(p)) == np.float32(L.orc_gumbel(ctypes.byref(st)))
+        R.ref_prob_free(p)
+    logits = (rng.standard_normal(362) * 3).astype(np.float32)
+    a, b = np.zeros(362, np.float32), np.zeros(362, np.float32)
+    R.ref_softmax362(P(logits), P(a))
+    L.orc_softmax(362, P(logits), P(b))
+    assert np.array_equal(a, b)
+    legal = (rng.random(362) < 0.7).astype(np.uint8)
+    for k in (1, 4, 16, 64):
+        p = R.ref_prob_new(17)
+        rm, rsc = np.full(k, -1, np.int32), np.zeros(k, np.float32)
+        kv = R.ref_gumbel_topk(p, P(logits), P(legal), 1.0, k, P(rm), P(rsc))
+        R.ref_prob_free(p)
+        om, osc, okv, _ = oracle_lib.gumbel_topk(L.orc_prng_seed(17), logits, legal, 1.0, k)
+        assert kv == okv and np.array_equal(rm[:min(k, kv)], om[:min(k, kv)]) and np.array_equal(rsc[:min(k, kv)], osc[:min(k, kv)])
