@@ -109,8 +109,11 @@ def dist_setup(n_gpus: int):
     backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(local)
-    dist.init_process_group(backend=backend)
     dev = torch.device("cuda", local) if backend == "nccl" else torch.device("cpu")
+    if backend == "nccl":
+        dist.init_process_group(backend=backend, device_id=dev)
+    else:
+        dist.init_process_group(backend=backend)
 
     def reduce_max(x: float) -> float:
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -134,12 +137,13 @@ def cpu_leaf_evals(feats, cfg, tensors, n_sample: int, threads: int):
     from oracle.model_ref import RefModel
     torch.set_num_threads(threads)
     model = RefModel(cfg, tensors, dtype=torch.float32)
-    sample = feats[:n_sample]
+    sample = np.resize(feats, n_sample) if n_sample > len(feats) else feats[:n_sample]
     t0 = time.perf_counter()
-    planes, scalars = oracle_lib.load_go_features(sample, 1)
-    out = model.forward(planes, scalars)
+    for lo in range(0, n_sample, 128):  # slices bound the activation memory of the CPU forward
+        planes, scalars = oracle_lib.load_go_features(sample[lo:lo + 128], 1)
+        out = model.forward(planes, scalars)
+        assert np.isfinite(out["pi_logits"]).all()
     dt = time.perf_counter() - t0
-    assert np.isfinite(out["pi_logits"]).all()
     return n_sample / dt, dt
 
 
@@ -152,9 +156,10 @@ def run_reference_arm(args):
     tensors = W.synthetic_weights(cfg, 0)
     feats = load_positions()
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("P3_CPU_SAMPLE", "64"))
-    for _ in range(max(args.warmup, 1)):
-        cpu_leaf_evals(feats, cfg, tensors, min(n_sample, 16), cores)
+    # one step = one full batch of the workload (1024 positions, ~3 s on 24 cores), evaluated in slices of 128
+    n_sample = int(os.environ.get("P3_CPU_SAMPLE", str(BATCH)))
+    for _ in range(max(min(args.warmup, 2), 1)):
+        cpu_leaf_evals(feats, cfg, tensors, 64, cores)
     total_t, total_n = 0.0, 0
     for s in range(args.steps):
         _, dt = cpu_leaf_evals(np.roll(feats, -s * n_sample), cfg, tensors, n_sample, cores)
@@ -298,8 +303,8 @@ def main():
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        n_sample = int(os.environ.get("P3_CPU_SAMPLE", "64"))
-        cpu_leaf_evals(feats, cfg, tensors, 8, cores)  # warm-up
+        n_sample = int(os.environ.get("P3_CPU_SAMPLE", "4096"))  # ~10-15 s of CPU work
+        cpu_leaf_evals(feats, cfg, tensors, 64, cores)  # warm-up
         v, dt = cpu_leaf_evals(feats, cfg, tensors, n_sample, cores)
         line["cpu_baseline"] = {"value": v, "unit": "positions/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_sample} positions of the same workload in {dt:.1f} s; features: C restatement of "
