@@ -92,6 +92,12 @@ int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int npl
                      const float* wt, const float* gs_w, const float* gs_b, float* raw_out, void* act_out,
                      bool act_bf16, const float* scale, const float* shift, cudaStream_t stream);
 
+// bf16-mode variant with the (bf16-rounded) weight table resident in shared memory; C <= 256.
+bool init_conv_smem_supported(int nplanes, int C);
+int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
+                          const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, float* raw_out,
+                          __nv_bfloat16* act_out, const float* scale, const float* shift, cudaStream_t stream);
+
 // ---- broadcast mix (broadcast.cu) -------------------------------------------------------------------
 // y[b,q,c] = sum_p W[p,q] * x[b,p,c] + bias[q], then act = mish(BN(y)); x, act in the operand type.
 int broadcast_launch(const void* x, const float* w, const float* bias, int n, int C, void* act_out,

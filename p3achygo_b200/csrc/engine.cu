@@ -138,7 +138,8 @@ struct p3_engine {
   // activations
   DevBuf xraw, actA, actB, actS0, actS1, pgv;
   // weights
-  DevBuf init_wt, gs_w, gs_b, ident_scale, ident_shift;
+  DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
+  bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
   std::vector<std::unique_ptr<ConvLayer>> layers;
   std::vector<DevBuf*> owned;
   std::vector<std::unique_ptr<DevBuf>> misc;
@@ -179,6 +180,15 @@ struct p3_engine {
                             L.tap_off.data(), s.ep, stream);
   }
 
+  int run_init() {
+    if (init_smem)
+      return init_conv_smem_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
+                                   init_wt_bf16.as<__nv_bfloat16>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(),
+                                   actA.as<__nv_bfloat16>(), first_scale, first_shift, stream);
+    return init_conv_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C, init_wt.as<float>(),
+                            gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(), actA.p, bf16, first_scale, first_shift, stream);
+  }
+
   int run_broadcast(const Step& s) {
     if (s.bplan) return tc_broadcast_launch(s.bplan, stream);
     return broadcast_launch(s.in, s.bw, s.bb, batch, C, s.b_out, bf16, s.b_scale, s.b_shift, stream);
@@ -192,9 +202,7 @@ struct p3_engine {
                        d_masks.as<uint16_t>(), stream);
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[1], stream));
-    rc = init_conv_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
-                          init_wt.as<float>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(), actA.p, bf16,
-                          first_scale, first_shift, stream);
+    rc = run_init();
     if (rc) return rc;
     for (const Step& s : program) {
       if (s.kind == kStepConv) rc = run_conv(s);
@@ -372,6 +380,9 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       for (int c = 0; c < P; ++c)
         for (int t = 0; t < 25; ++t) wt[(static_cast<size_t>(t) * P + c) * C + o] = w->data[(static_cast<size_t>(o) * P + c) * 25 + t];
     if ((rc = upload_f32(e.init_wt, wt)) || (rc = upload_f32(e.gs_w, gw->data)) || (rc = upload_f32(e.gs_b, gb->data))) return rc;
+    const char* env_ic = std::getenv("P3_INIT_SMEM");
+    e.init_smem = e.bf16 && init_conv_smem_supported(P, C) && !(env_ic && std::atoi(env_ic) == 0);
+    if (e.init_smem && (rc = upload_bf16(e.init_wt_bf16, wt))) return rc;
   }
   {
     std::vector<float> ones(std::max(C, 3 * Ch), 1.0f), zeros(std::max(C, 3 * Ch), 0.0f);
@@ -745,9 +756,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
                      e->d_masks.as<uint16_t>(), e->stream);
   cls.push_back(0); fl.push_back(0.0);
   P3_CUDA(rec());
-  if (!rc) rc = init_conv_launch(e->d_masks.as<uint16_t>(), e->d_scalars.as<float>(), e->batch, e->nplanes, e->nscalars, e->C,
-                                 e->init_wt.as<float>(), e->gs_w.as<float>(), e->gs_b.as<float>(), e->xraw.as<float>(), e->actA.p,
-                                 e->bf16, e->first_scale, e->first_shift, e->stream);
+  if (!rc) rc = e->run_init();
   cls.push_back(1); fl.push_back(2.0 * (25.0 * e->nplanes * e->C * Pn + double(e->nscalars) * e->C) * B);
   P3_CUDA(rec());
   for (const Step& s : e->program) {
