@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -69,6 +70,7 @@ struct TcConvPlan {
   ConvEpilogue ep;
   bool resident = false;  // tc_conv3x3_res_kernel
   int debug = 0;          // P3_TC_DEBUG ablation bits (perf experiments only; results are wrong when set)
+  unsigned long long* trace = nullptr;  // P3_TC_TRACE: per-phase clock64 sums of one epilogue leader (perf experiments)
 };
 
 namespace {
@@ -93,7 +95,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
-               const float* __restrict__ shift, int act_mode, int debug) {
+               const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -267,6 +269,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         const uint32_t k = G >> 1;  // this group's chunk ordinal
         const uint32_t buf = k & 1u;
+        const bool tr = trace != nullptr && blockIdx.x == 3 && leader && grp == 0;
+        long long tc[8];
+        if (tr) tc[0] = clock64();
         uint32_t v[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc * n_tile + c * 32 + half * 16);
@@ -274,10 +279,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float x[16];
         if (has_res) {
           ptx::mbar_wait(&my_res_full[buf], (k >> 1) & 1u);
-          const uint8_t* rp = my_res + buf * kStageF32Bytes + f32_row;
+          const uint32_t rp = ptx::smem_u32(my_res) + buf * kStageF32Bytes + f32_row;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 t4 = *reinterpret_cast<const float4*>(rp + (((half * 4 + j) ^ (r & 7)) << 4));
+            const float4 t4 = ptx::lds_f4(rp + (((half * 4 + j) ^ (r & 7)) << 4));
             x[4 * j] = t4.x;
             x[4 * j + 1] = t4.y;
             x[4 * j + 2] = t4.z;
@@ -287,7 +292,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) x[j] = 0.0f;
         }
+        if (tr) tc[1] = clock64();
         ptx::tmem_ld_wait();
+        if (tr) tc[2] = clock64();
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = live ? (__uint_as_float(v[j]) + x[j]) : 0.0f;
         uint4 pk0 = make_uint4(0, 0, 0, 0), pk1 = pk0;
@@ -298,35 +305,55 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = x[j];
           } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
+            const uint32_t sca = ptx::smem_u32(s_scale + nb), sha = ptx::smem_u32(s_shift + nb);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = live ? mish_f32<false>(fmaf(x[j], s_scale[nb + j], s_shift[nb + j])) : 0.0f;
+            for (int j = 0; j < 4; ++j) {
+              const float4 s4 = ptx::lds_f4_const(sca + 16 * j), h4 = ptx::lds_f4_const(sha + 16 * j);
+              a[4 * j] = mish_f32<false>(fmaf(x[4 * j], s4.x, h4.x));
+              a[4 * j + 1] = mish_f32<false>(fmaf(x[4 * j + 1], s4.y, h4.y));
+              a[4 * j + 2] = mish_f32<false>(fmaf(x[4 * j + 2], s4.z, h4.z));
+              a[4 * j + 3] = mish_f32<false>(fmaf(x[4 * j + 3], s4.w, h4.w));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = live ? a[j] : 0.0f;
           }
           pk0 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
           pk1 = make_uint4(pack_bf16(a[8], a[9]), pack_bf16(a[10], a[11]), pack_bf16(a[12], a[13]), pack_bf16(a[14], a[15]));
         }
 
         // group staging free? (the group's previous bulk stores have read it) and everyone is done with my_res[buf]
+        if (tr) tc[3] = clock64() + (pk0.x & 0);
         if (leader) ptx::bulk_wait_read<0>();
+        if (tr) tc[4] = clock64();
         ptx::named_bar_sync(bar_a, kGrpThreads);
+        if (tr) tc[5] = clock64();
         if (leader && has_res) issue_res(G + 4);  // refill the ring slot just consumed with this group's chunk k + 2
         if (has_raw) {
-          uint8_t* wp = my_raw + f32_row;
+          const uint32_t wp = ptx::smem_u32(my_raw) + f32_row;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(wp + (((half * 4 + j) ^ (r & 7)) << 4)) =
-                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            ptx::sts_f4(wp + (((half * 4 + j) ^ (r & 7)) << 4), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
         }
         if (has_act) {
-          uint8_t* wp = my_act + bf_row;
-          *reinterpret_cast<uint4*>(wp + (((half * 2 + 0) ^ ((r >> 1) & 3)) << 4)) = pk0;
-          *reinterpret_cast<uint4*>(wp + (((half * 2 + 1) ^ ((r >> 1) & 3)) << 4)) = pk1;
+          const uint32_t wp = ptx::smem_u32(my_act) + bf_row;
+          ptx::sts_u4(wp + (((half * 2 + 0) ^ ((r >> 1) & 3)) << 4), pk0);
+          ptx::sts_u4(wp + (((half * 2 + 1) ^ ((r >> 1) & 3)) << 4), pk1);
         }
         ptx::fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
+        if (tr) tc[6] = clock64();
         ptx::named_bar_sync(bar_b, kGrpThreads);
         if (leader && !(debug & 8)) {
           if (has_raw) ptx::tma_store_2d(&map_raw, my_raw, n0 + c * 32, m0);
           if (has_act) ptx::tma_store_2d(&map_act, my_act, n0 + c * 32, m0);
           ptx::bulk_commit();
+        }
+        if (tr) {
+          tc[7] = clock64();
+          // phases: 0 res-wait  1 tmem ld wait  2 math  3 bulk_wait_read  4 barrier A  5 staging+fence  6 barrier B + TMA issue
+          for (int i = 0; i < 7; ++i) atomicAdd(&trace[i], static_cast<unsigned long long>(tc[i + 1] - tc[i]));
+          atomicAdd(&trace[7], 1ull);
+          if (trace[8] != 0) atomicAdd(&trace[9], static_cast<unsigned long long>(tc[0]) - trace[8]);  // gap since previous chunk end
+          trace[8] = static_cast<unsigned long long>(tc[7]);
         }
       }
       if (!waited) {  // (only with the ablation that skips all chunks) still consume the accumulator
@@ -626,6 +653,10 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const char* env_res = std::getenv("P3_TC_RESIDENT");
   if (const char* dbg = std::getenv("P3_TC_DEBUG")) p->debug = std::atoi(dbg);
+  if (std::getenv("P3_TC_TRACE")) {
+    cudaMalloc(&p->trace, 10 * sizeof(unsigned long long));
+    cudaMemset(p->trace, 0, 10 * sizeof(unsigned long long));
+  }
   const size_t res_smem =
       static_cast<size_t>(9) * (cin / kSlabK) * kResWSlabBytes + kResStages * kResABytes + 1024 + kBarBytes;
   bool shifts_ok = taps == 9;
@@ -688,7 +719,19 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   return P3_OK;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+void tc_conv_plan_destroy(TcConvPlan* plan) {
+  if (plan && plan->trace) {
+    unsigned long long h[10];
+    cudaMemcpy(h, plan->trace, sizeof h, cudaMemcpyDeviceToHost);
+    if (h[7])
+      std::fprintf(stderr, "[p3 trace] cin=%d cout=%d taps=%d res=%d raw=%d act=%d chunks=%llu cycles/chunk: res_wait %llu  tmem_ld %llu  math %llu  "
+                           "bulk_wait %llu  barA %llu  stage+fence %llu  barB+tma %llu  | gap-between-chunks %llu\n",
+                   plan->cin, plan->cout, plan->taps, plan->ep.residual != nullptr, plan->ep.raw_out != nullptr, plan->ep.act_out != nullptr,
+                   h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7], h[9] / h[7]);
+    cudaFree(plan->trace);
+  }
+  delete plan;
+}
 
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
@@ -700,7 +743,7 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
         p->stages, p->tmem_cols, ep.residual != nullptr && !(p->debug & 32), ep.raw_out != nullptr, ep.act_out != nullptr,
-        ep.scale, ep.shift, ep.act_mode, p->debug >> 8);
+        ep.scale, ep.shift, ep.act_mode, p->debug >> 8, p->trace);
   }
   P3_CUDA(cudaGetLastError());
   return P3_OK;

