@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -69,6 +70,8 @@ struct TcConvPlan {
   TcTaps tap;
   ConvEpilogue ep;
   bool resident = false;  // tc_conv3x3_res_kernel
+  bool pair = false;      // tc_conv3x3_pair_kernel (CTA pairs, cta_group::2)
+  int n_half = 0;         // pair kernel: output channels held per CTA
   int debug = 0;          // P3_TC_DEBUG ablation bits (perf experiments only; results are wrong when set)
   unsigned long long* trace = nullptr;  // P3_TC_TRACE: per-phase clock64 sums of one epilogue leader (perf experiments)
 };
@@ -590,6 +593,229 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
 }
 
+// ===================================================================================================
+// 3x3 layers on a CTA PAIR (cta_group::2): the same resident-weight / shifted-view scheme, but one tcgen05.mma covers
+// M = 256 rows (128 per CTA) x N = 2 * n_half output channels, with each CTA holding only ITS half of the weights' N
+// rows.  Per MMA each SM now reads A 4 KB + B n_half*32 B from its shared memory for twice the math of the single-CTA
+// N = 64 kernel above, which was capped by shared-memory operand reads (ablation: MMA pipeline alone 1.06 PFLOP/s).
+//   rank 0 (leader): warp 1 issues every MMA and the multicast commits; its full / tmem_empty / weight barriers collect
+//                    the TMA bytes and the epilogue releases of BOTH CTAs
+//   both ranks     : warp 0 TMA-loads its own 176-row haloed A box and its own weight half (cp.async.bulk.tensor
+//                    .cta_group::2, completion counted on the leader's barrier); 16 epilogue warps drain the CTA's own
+//                    128 x N accumulator (4 warps per TMEM lane quarter, N/4 columns each)
+// ===================================================================================================
+constexpr int kPairThreads = 64 + 16 * 32;  // 576
+constexpr int kPairMaxN = 128;
+
+template <int kCpw>  // epilogue columns per warp = N / 4
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
+                       int cin, int cout, int n_half, int stages, int tmem_cols, TcTaps tap,
+                       __nv_bfloat16* __restrict__ act_out, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int act_mode, int debug) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int k_slabs = cin / kSlabK;
+  const int w_slab_bytes = n_half * 128;
+  const int w_bytes = 9 * k_slabs * w_slab_bytes;
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + stages * kResABytes);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* tmem_full = empty_bar + 4;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);
+  float* s_shift = s_scale + kPairMaxN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int N = 2 * n_half;
+  const int n_slices = cout / N;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int slice = pair % n_slices;
+  const int n0 = slice * N;
+  const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
+  const int m_tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    s_scale[c] = act_mode == kActMishBN ? scale[n0 + c] : 1.0f;
+    s_shift[c] = act_mode == kActMishBN ? shift[n0 + c] : 0.0f;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_w);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // leader's is the live one: one arrive.expect_tx for both CTAs' bytes
+      ptx::mbar_init(&empty_bar[s], 1);  // multicast commit arrives on both CTAs' copies
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 2 * kResEpiWarps);  // leader's: epilogue warps of both CTAs
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, static_cast<uint32_t>(tmem_cols));
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    const uint32_t w_bar_leader = ptx::mapa_shared(ptx::smem_u32(w_bar), 0);
+    if (ptx::elect_one()) {
+      if (rank == 0) ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(2 * w_bytes));
+      for (int t = 0; t < 9; ++t)
+        for (int ks = 0; ks < k_slabs; ++ks)
+          ptx::tma_load_2d_pair(smem_w + (t * k_slabs + ks) * w_slab_bytes, &map_w, w_bar_leader, ks * kSlabK,
+                                t * cout + n0 + static_cast<int>(rank) * n_half);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice) {
+      const int m0 = mt * 2 * kTileM + static_cast<int>(rank) * kTileM;
+      for (int ks = 0; ks < k_slabs; ++ks) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (debug & 2) {
+            if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);  // ablation: no A traffic
+          } else {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kResABytes);
+            ptx::tma_load_2d_pair(smem_a + stage * kResABytes, &map_a, ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0),
+                                  ks * kSlabK, m0 - kResHalo);
+          }
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * kTileM, N);
+      const uint32_t w_lo_base = ptx::desc_lo_sw128(ptx::smem_u32(smem_w));
+      const uint32_t w_slab16 = static_cast<uint32_t>(w_slab_bytes / 16);
+      const uint32_t w_tap_stride = static_cast<uint32_t>(k_slabs) * w_slab16;
+      uint32_t tap_lo[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_lo[t] = static_cast<uint32_t>(kResHalo + tap.off[t]) * 8u;
+      ptx::mbar_wait_cluster(w_bar, 0);
+      ptx::tc_fence_after_sync();
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * N);
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          ptx::mbar_wait_cluster(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a + stage * kResABytes));
+          const uint32_t w_lo = w_lo_base + static_cast<uint32_t>(ks) * w_slab16;
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (debug & 4) continue;  // ablation: no MMAs
+              const uint32_t a_t = a_lo + tap_lo[t];
+              const uint32_t w_t = w_lo + static_cast<uint32_t>(t) * w_tap_stride;
+#pragma unroll
+              for (int k = 0; k < kSlabK / kUmmaK; ++k)
+                ptx::umma_f16_pair_lohi(tmem_d, a_t + 2 * k, ptx::desc_hi_sw128(), w_t + 2 * k, ptx::desc_hi_sw128(), idesc,
+                                        (ks > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit_pair(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(&tmem_full[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): thread = one of the CTA's 128 rows x N/4 columns =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int c0 = (ew >> 2) * kCpw;  // first column (within the slice) of this warp
+    const uint32_t sca = ptx::smem_u32(s_scale + c0), sha = ptx::smem_u32(s_shift + c0);
+    const uint32_t empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);
+    const uint32_t empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[1]), 0);
+    int iter = 0;
+    for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const int m = mt * 2 * kTileM + static_cast<int>(rank) * kTileM + quarter * 32 + lane;
+      const bool in_range = m < rows;
+      const bool live = in_range && row_is_live(m % kRowsPerPos);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * N + c0);
+      __nv_bfloat16* ap = act_out + static_cast<size_t>(m) * cout + n0 + c0;
+      // passes of 16 (then 8) columns keep the live registers small; the TMEM stage is released to the leader's barrier
+      // as soon as the LAST pass's values are in registers (the other accumulator stage covers the wait)
+      auto pass = [&](const int col, auto width_tag, const bool last) {
+        constexpr int kW = decltype(width_tag)::value;
+        uint32_t v[kW];
+        if (kW == 16) ptx::tmem_ld_32x16(taddr + col, v);
+        else ptx::tmem_ld_32x8(taddr + col, v);
+        ptx::tmem_ld_wait();
+        if (last) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(acc ? empty_leader1 : empty_leader0);
+        }
+        if (in_range && !(debug & 1)) {
+#pragma unroll
+          for (int g = 0; g < kW / 8; ++g) {
+            const uint32_t o = static_cast<uint32_t>(col + g * 8) * 4u;
+            const float4 s0 = ptx::lds_f4_const(sca + o), s1 = ptx::lds_f4_const(sca + o + 16);
+            const float4 h0 = ptx::lds_f4_const(sha + o), h1 = ptx::lds_f4_const(sha + o + 16);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = __uint_as_float(v[g * 8 + i]);
+              a[i] = (act_mode == kActIdentity || (debug & 16)) ? x : mish_f32<false>(fmaf(x, sc[i], sh[i]));
+              a[i] = live ? a[i] : 0.0f;
+            }
+            if (!(debug & 8) || a[0] == 1234.5f)
+              *reinterpret_cast<uint4*>(ap + col + g * 8) =
+                  make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+          }
+        }
+      };
+#pragma unroll 1
+      for (int h = 0; h < kCpw / 16; ++h) pass(h * 16, std::integral_constant<int, 16>{}, (kCpw & 8) == 0 && h == kCpw / 16 - 1);
+      if (kCpw & 8) pass(kCpw & 16, std::integral_constant<int, 8>{}, true);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();  // the peer's MMAs / TMEM traffic are complete before either CTA frees its columns
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(tmem_cols));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -622,6 +848,17 @@ int make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int 
 }
 int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint32_t box1) {
   return make_map_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim0, dim1, kSlabK, box1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, int, int, int, int, int, int, TcTaps, __nv_bfloat16*,
+                             const float*, const float*, int, int);
+PairKernelFn pair_kernel_for(int N) {
+  switch (N) {
+    case 128: return tc_conv3x3_pair_kernel<32>;
+    case 96: return tc_conv3x3_pair_kernel<24>;
+    case 64: return tc_conv3x3_pair_kernel<16>;
+    default: return tc_conv3x3_pair_kernel<8>;
+  }
 }
 
 int pick_n_tile(int cout) {  // largest divisor of cout that is <= 128 and a multiple of 32
@@ -664,8 +901,55 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   // the resident kernel writes only the activated copy (all 3x3 layers except a classic block's second conv)
   p->resident = shifts_ok && cout % kResN == 0 && res_smem <= static_cast<size_t>(kSmemBudget) && ep.residual == nullptr &&
                 ep.raw_out == nullptr && ep.act_out != nullptr && !(env_res && std::atoi(env_res) == 0);
+  // CTA-pair kernel: largest N = 2 * n_half in {128, 96, 64, 32} dividing cout whose weight half fits next to >= 2 A stages
+  const char* env_pair = std::getenv("P3_TC_PAIR");
+  if (shifts_ok && ep.residual == nullptr && ep.raw_out == nullptr && ep.act_out != nullptr &&
+      !(env_pair && std::atoi(env_pair) == 0) && !(env_res && std::atoi(env_res) == 0)) {
+    for (int N = kPairMaxN; N >= 32 && !p->pair; N -= 32) {
+      if (cout % N != 0) continue;
+      const size_t wb = (static_cast<size_t>(9) * (cin / kSlabK) * (N / 2) * 128 + 1023) & ~size_t(1023);
+      for (int st = 3; st >= 2; --st) {
+        const size_t need = wb + static_cast<size_t>(st) * kResABytes + 1024 + 128 + 2 * kPairMaxN * 4;
+        if (need <= static_cast<size_t>(kSmemBudget)) {
+          p->pair = true;
+          p->n_half = N / 2;
+          p->n_tile = N;
+          p->stages = st;
+          p->smem_bytes = need;
+          break;
+        }
+      }
+    }
+  }
   int rc;
-  if (p->resident) {
+  if (p->pair) {
+    p->resident = false;
+    int cols = 32;
+    while (cols < 2 * p->n_tile) cols *= 2;
+    p->tmem_cols = cols;
+    const int n_slices = cout / p->n_tile;
+    const int m_tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+    rc = make_map_bf16_k64(&p->map_a, in, cin, rows, kResRows);
+    if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_half);
+    if (rc == P3_OK) {
+      cudaError_t e = cudaFuncSetAttribute(pair_kernel_for(p->n_tile), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+    }
+    int max_pairs = sms / 2;
+    if (rc == P3_OK) {  // how many CTA pairs can be co-resident (one CTA per SM, both SMs of a TPC)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+      cfg.blockDim = dim3(kPairThreads);
+      cfg.dynamicSmemBytes = p->smem_bytes;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, pair_kernel_for(p->n_tile), &cfg) == cudaSuccess && n_clusters > 0)
+        max_pairs = std::min(max_pairs, n_clusters);
+      else
+        cudaGetLastError();
+    }
+    const int pairs = std::max(n_slices, std::min(max_pairs, m_tiles * n_slices) / n_slices * n_slices);
+    p->grid = 2 * pairs;
+  } else if (p->resident) {
     p->n_tile = kResN;
     p->stages = kResStages;
     p->smem_bytes = res_smem;
@@ -735,7 +1019,11 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
 
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
-  if (p->resident) {
+  if (p->pair) {
+    pair_kernel_for(p->n_tile)<<<p->grid, kPairThreads, p->smem_bytes, stream>>>(
+        p->map_a, p->map_w, p->rows, p->cin, p->cout, p->n_half, p->stages, p->tmem_cols, p->tap,
+        reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff);
+  } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
         ep.shift, ep.act_mode, p->debug & 0xff);

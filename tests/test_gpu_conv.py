@@ -45,7 +45,8 @@ def test_conv_tcgen05(cin, cout, k, n):
     assert err < 5e-5, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("cin,cout,n", [(64, 64, 3), (128, 128, 40), (128, 64, 2), (64, 128, 5)])
+@pytest.mark.parametrize("cin,cout,n", [(64, 64, 3), (128, 128, 40), (128, 64, 2), (64, 128, 5), (192, 192, 3), (128, 128, 1),
+                                        (64, 32, 2), (128, 256, 7)])
 def test_conv_tcgen05_resident_weights(cin, cout, n, monkeypatch):
     """The resident-weight / tap-reuse 3x3 kernel (shifted shared-memory views of one haloed A tile). It only writes the
     bf16 activated copy, so the comparison allows one bf16 rounding of the output (2^-8 relative)."""
