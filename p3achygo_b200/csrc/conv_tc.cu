@@ -72,6 +72,7 @@ struct TcConvPlan {
   bool resident = false;  // tc_conv3x3_res_kernel
   bool pair = false;      // tc_conv3x3_pair_kernel (CTA pairs, cta_group::2)
   int n_half = 0;         // pair kernel: output channels held per CTA
+  bool staged = false;    // pair kernel: output leaves through per-warp smem staging + TMA stores (map_raw = the box map)
   int debug = 0;          // P3_TC_DEBUG ablation bits (perf experiments only; results are wrong when set)
   unsigned long long* trace = nullptr;  // P3_TC_TRACE: per-phase clock64 sums of one epilogue leader (perf experiments)
 };
@@ -605,28 +606,45 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 //                    128 x N accumulator (4 warps per TMEM lane quarter, N/4 columns each)
 // ===================================================================================================
 constexpr int kPairThreads = 64 + 16 * 32;  // 576
+__device__ unsigned long long g_last_kernel_end = 0;  // P3_TC_TRACE only
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 constexpr int kPairMaxN = 128;
 
 template <int kCpw>  // epilogue columns per warp = N / 4
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
-                       int cin, int cout, int n_half, int stages, int tmem_cols, TcTaps tap,
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ CUtensorMap map_o64, const __grid_constant__ CUtensorMap map_o32, int rows,
+                       int cin, int cout, int n_half, int stages, int staged, int tmem_cols, TcTaps tap,
                        __nv_bfloat16* __restrict__ act_out, const float* __restrict__ scale,
-                       const float* __restrict__ shift, int act_mode, int debug) {
+                       const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // P3_TC_TRACE: globaltimer stamps of CTA 0 (ns since its first instruction), summed over launches
+  const bool tr = trace != nullptr && blockIdx.x == 0;
+  const unsigned long long t_start = tr ? global_timer() : 0ull;
+  if (tr && threadIdx.x == 0) {
+    atomicAdd(&trace[0], 1ull);
+    if (g_last_kernel_end != 0) atomicAdd(&trace[1], t_start - g_last_kernel_end);
+  }
   const int k_slabs = cin / kSlabK;
   const int w_slab_bytes = n_half * 128;
   const int w_bytes = 9 * k_slabs * w_slab_bytes;
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + stages * kResABytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_a + stages * kResABytes + (staged ? kResEpiWarps * 2048 : 0));
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* tmem_full = empty_bar + 4;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* w_bar = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint64_t* w_bar = tmem_empty + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 128);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  // accumulator stages in TMEM: as many N-column accumulators as the allocation holds (4 at N <= 128), so that
+  // epilogue / MMA jitter is absorbed instead of stalling the tensor pipe
+  const int acc_stages = (tmem_cols / (2 * n_half)) >= 4 ? 4 : 2;
   float* s_shift = s_scale + kPairMaxN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -650,7 +668,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       ptx::mbar_init(&full_bar[s], 1);   // leader's is the live one: one arrive.expect_tx for both CTAs' bytes
       ptx::mbar_init(&empty_bar[s], 1);  // multicast commit arrives on both CTAs' copies
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < acc_stages; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 2 * kResEpiWarps);  // leader's: epilogue warps of both CTAs
     }
@@ -665,6 +683,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tr && threadIdx.x == 0) atomicAdd(&trace[2], global_timer() - t_start);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -711,12 +730,13 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int t = 0; t < 9; ++t) tap_lo[t] = static_cast<uint32_t>(kResHalo + tap.off[t]) * 8u;
       ptx::mbar_wait_cluster(w_bar, 0);
       ptx::tc_fence_after_sync();
+      if (tr && lane == 0) atomicAdd(&trace[3], global_timer() - t_start);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
       for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
         ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * N);
@@ -746,6 +766,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         if (ptx::elect_one()) ptx::umma_commit_pair(&tmem_full[acc]);
         __syncwarp();
+        if (++acc == acc_stages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
@@ -754,21 +778,23 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int quarter = warp & 3;
     const int c0 = (ew >> 2) * kCpw;  // first column (within the slice) of this warp
     const uint32_t sca = ptx::smem_u32(s_scale + c0), sha = ptx::smem_u32(s_shift + c0);
-    const uint32_t empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);
-    const uint32_t empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[1]), 0);
+    const uint32_t empty_leader = ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0);
+    const uint32_t my_stage = ptx::smem_u32(smem_a + stages * kResABytes) + static_cast<uint32_t>(ew) * 2048u;  // 2 KB per warp
     int iter = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
     for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice, ++iter) {
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
+      if (tr && iter == 0 && ew == 0 && lane == 0) atomicAdd(&trace[4], global_timer() - t_start);
       const int m = mt * 2 * kTileM + static_cast<int>(rank) * kTileM + quarter * 32 + lane;
       const bool in_range = m < rows;
       const bool live = in_range && row_is_live(m % kRowsPerPos);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * N + c0);
       __nv_bfloat16* ap = act_out + static_cast<size_t>(m) * cout + n0 + c0;
       // passes of 16 (then 8) columns keep the live registers small; the TMEM stage is released to the leader's barrier
-      // as soon as the LAST pass's values are in registers (the other accumulator stage covers the wait)
+      // as soon as the LAST pass's values are in registers (the other accumulator stages cover the wait)
+      bool first_pass = true;
       auto pass = [&](const int col, auto width_tag, const bool last) {
         constexpr int kW = decltype(width_tag)::value;
         uint32_t v[kW];
@@ -778,33 +804,63 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (last) {
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(acc ? empty_leader1 : empty_leader0);
+          if (lane == 0) ptx::mbar_arrive_cluster(empty_leader + 8u * static_cast<uint32_t>(acc));
         }
-        if (in_range && !(debug & 1)) {
+        if (debug & 1) return;  // ablation: no epilogue math / stores
+        uint4 pk[kW / 8];
+#pragma unroll
+        for (int g = 0; g < kW / 8; ++g) {
+          const uint32_t o = static_cast<uint32_t>(col + g * 8) * 4u;
+          const float4 s0 = ptx::lds_f4_const(sca + o), s1 = ptx::lds_f4_const(sca + o + 16);
+          const float4 h0 = ptx::lds_f4_const(sha + o), h1 = ptx::lds_f4_const(sha + o + 16);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = __uint_as_float(v[g * 8 + i]);
+            a[i] = (act_mode == kActIdentity || (debug & 16)) ? x : mish_f32<false>(fmaf(x, sc[i], sh[i]));
+          }
+          const uint4 q = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+          pk[g] = live ? q : make_uint4(0, 0, 0, 0);  // padding rows / columns of the layout stay zero
+        }
+        if (staged) {
+          if (first_pass) {  // this warp's previous bulk store has read the staging tile
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int g = 0; g < kW / 8; ++g) {
-            const uint32_t o = static_cast<uint32_t>(col + g * 8) * 4u;
-            const float4 s0 = ptx::lds_f4_const(sca + o), s1 = ptx::lds_f4_const(sca + o + 16);
-            const float4 h0 = ptx::lds_f4_const(sha + o), h1 = ptx::lds_f4_const(sha + o + 16);
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float x = __uint_as_float(v[g * 8 + i]);
-              a[i] = (act_mode == kActIdentity || (debug & 16)) ? x : mish_f32<false>(fmaf(x, sc[i], sh[i]));
-              a[i] = live ? a[i] : 0.0f;
-            }
-            if (!(debug & 8) || a[0] == 1234.5f)
-              *reinterpret_cast<uint4*>(ap + col + g * 8) =
-                  make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+            const uint32_t k = static_cast<uint32_t>(col / 8 + g);  // 16-byte chunk of this warp's row
+            const uint32_t ks = kCpw == 32 ? (k ^ ((lane >> 1) & 3u)) : kCpw == 16 ? (k ^ ((lane >> 2) & 1u)) : k;
+            ptx::sts_u4(my_stage + static_cast<uint32_t>(lane) * (kCpw * 2) + (ks << 4), pk[g]);
           }
+        } else if (in_range && (!(debug & 8) || pk[0].x == 0x12345678u)) {
+          // direct stores: one full, aligned 32-byte sector per thread where the column offset allows it
+          if (kW == 16 && kCpw % 16 == 0) ptx::stg_u8(ap + col, pk[0], pk[kW / 8 - 1]);
+          else if (kW == 16) { *reinterpret_cast<uint4*>(ap + col) = pk[0]; *reinterpret_cast<uint4*>(ap + col + 8) = pk[kW / 8 - 1]; }
+          else *reinterpret_cast<uint4*>(ap + col) = pk[0];
         }
+        first_pass = false;
       };
 #pragma unroll 1
       for (int h = 0; h < kCpw / 16; ++h) pass(h * 16, std::integral_constant<int, 16>{}, (kCpw & 8) == 0 && h == kCpw / 16 - 1);
       if (kCpw & 8) pass(kCpw & 16, std::integral_constant<int, 8>{}, true);
+      if (staged && !(debug & 1)) {
+        // this warp's 32 rows x kCpw columns leave as ONE TMA bulk store (no per-thread global stores, no CTA barrier)
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(debug & 8)) {
+          ptx::tma_store_2d(&map_o64, nullptr, 0, 0, my_stage, n0 + c0, mt * 2 * kTileM + static_cast<int>(rank) * kTileM + quarter * 32);
+          ptx::bulk_commit();
+        }
+      }
+      if (++acc == acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
+    if (staged && lane == 0) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before_sync();
@@ -813,6 +869,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(tmem_cols));
+  }
+  if (trace != nullptr && threadIdx.x == 0) {
+    const unsigned long long t_end = global_timer();
+    if (tr) atomicAdd(&trace[5], t_end - t_start);
+    atomicMax(&g_last_kernel_end, t_end);
   }
 }
 
@@ -850,8 +911,9 @@ int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_
   return make_map_2d(map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim0, dim1, kSlabK, box1, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, int, int, int, int, int, int, TcTaps, __nv_bfloat16*,
-                             const float*, const float*, int, int);
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int,
+                             int, int, int, TcTaps, __nv_bfloat16*,
+                             const float*, const float*, int, int, unsigned long long*);
 PairKernelFn pair_kernel_for(int N) {
   switch (N) {
     case 128: return tc_conv3x3_pair_kernel<32>;
@@ -908,29 +970,48 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
     for (int N = kPairMaxN; N >= 32 && !p->pair; N -= 32) {
       if (cout % N != 0) continue;
       const size_t wb = (static_cast<size_t>(9) * (cin / kSlabK) * (N / 2) * 128 + 1023) & ~size_t(1023);
-      for (int st = 3; st >= 2; --st) {
-        const size_t need = wb + static_cast<size_t>(st) * kResABytes + 1024 + 128 + 2 * kPairMaxN * 4;
-        if (need <= static_cast<size_t>(kSmemBudget)) {
-          p->pair = true;
-          p->n_half = N / 2;
-          p->n_tile = N;
-          p->stages = st;
-          p->smem_bytes = need;
-          break;
+      const char* env_st = std::getenv("P3_TC_PAIR_STAGES");  // perf experiments
+      const char* env_sg = std::getenv("P3_TC_PAIR_STAGED");
+      // preferred: 2 A stages (measured as fast as 3: the A boxes mostly hit L2) + an N x 128 staging tile for TMA stores;
+      // else direct per-thread stores with up to 3 A stages
+      const size_t fixed = wb + 1024 + 256 + 2 * kPairMaxN * 4;
+      const size_t need_staged = fixed + 2 * static_cast<size_t>(kResABytes) + static_cast<size_t>(kResEpiWarps) * 2048;
+      if (need_staged <= static_cast<size_t>(kSmemBudget) && !(env_sg && std::atoi(env_sg) == 0)) {
+        p->pair = true;
+        p->staged = true;
+        p->stages = 2;
+        p->smem_bytes = need_staged;
+      } else {
+        for (int st = env_st ? std::atoi(env_st) : 3; st >= 2 && !p->pair; --st) {
+          const size_t need = fixed + static_cast<size_t>(st) * kResABytes;
+          if (need <= static_cast<size_t>(kSmemBudget)) {
+            p->pair = true;
+            p->stages = st;
+            p->smem_bytes = need;
+          }
         }
+      }
+      if (p->pair) {
+        p->n_half = N / 2;
+        p->n_tile = N;
       }
     }
   }
   int rc;
   if (p->pair) {
     p->resident = false;
-    int cols = 32;
-    while (cols < 2 * p->n_tile) cols *= 2;
-    p->tmem_cols = cols;
+    p->tmem_cols = 512;  // one CTA per SM: take all columns -> 4 accumulator stages at N <= 128
     const int n_slices = cout / p->n_tile;
     const int m_tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
     rc = make_map_bf16_k64(&p->map_a, in, cin, rows, kResRows);
     if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_half);
+    p->map_raw = p->map_a;  // placeholders unless staged
+    p->map_act = p->map_a;
+    if (rc == P3_OK && p->staged) {  // per-warp output boxes: 32 rows x N/4 columns
+      const int cpw = p->n_tile / 4;
+      rc = make_map_2d(&p->map_raw, ep.act_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cout, rows, cpw, 32,
+                       cpw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : cpw == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
     if (rc == P3_OK) {
       cudaError_t e = cudaFuncSetAttribute(pair_kernel_for(p->n_tile), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
       if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
@@ -1007,7 +1088,11 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
   if (plan && plan->trace) {
     unsigned long long h[10];
     cudaMemcpy(h, plan->trace, sizeof h, cudaMemcpyDeviceToHost);
-    if (h[7])
+    if (plan->pair && h[0])
+      std::fprintf(stderr, "[p3 trace] pair 3x3 cin=%d cout=%d launches=%llu ns/launch (CTA 0): gap-since-previous-kernel-end %llu  "
+                           "prologue %llu  weights-ready %llu  first-accumulator %llu  kernel %llu\n",
+                   plan->cin, plan->cout, h[0], h[1] / h[0], h[2] / h[0], h[3] / h[0], h[4] / h[0], h[5] / h[0]);
+    else if (h[7])
       std::fprintf(stderr, "[p3 trace] cin=%d cout=%d taps=%d res=%d raw=%d act=%d chunks=%llu cycles/chunk: res_wait %llu  tmem_ld %llu  math %llu  "
                            "bulk_wait %llu  barA %llu  stage+fence %llu  barB+tma %llu  | gap-between-chunks %llu\n",
                    plan->cin, plan->cout, plan->taps, plan->ep.residual != nullptr, plan->ep.raw_out != nullptr, plan->ep.act_out != nullptr,
@@ -1021,8 +1106,9 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
   if (p->pair) {
     pair_kernel_for(p->n_tile)<<<p->grid, kPairThreads, p->smem_bytes, stream>>>(
-        p->map_a, p->map_w, p->rows, p->cin, p->cout, p->n_half, p->stages, p->tmem_cols, p->tap,
-        reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff);
+        p->map_a, p->map_w, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0,
+        p->tmem_cols, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff,
+        p->trace);
   } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
