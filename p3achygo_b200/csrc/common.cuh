@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,8 +56,9 @@ enum ActMode : int {
 };
 
 struct ConvEpilogue {
-  const float* residual = nullptr;  // [rows, cout] fp32, added to the accumulator (may alias raw_out)
-  float* raw_out = nullptr;         // [rows, cout] fp32 raw sum (residual stream), or null
+  const void* residual = nullptr;   // [rows, cout] fp32 (fp16 if raw_f16), added to the accumulator (may alias raw_out)
+  void* raw_out = nullptr;          // [rows, cout] fp32 (fp16 if raw_f16) raw sum (residual stream), or null
+  bool raw_f16 = false;             // the residual stream is stored as IEEE fp16 (bf16 engine)
   void* act_out = nullptr;          // [rows, cout] activated copy in the operand type, or null
   const float* scale = nullptr;     // [cout] next layer's folded BN (kActMishBN)
   const float* shift = nullptr;
@@ -89,13 +91,13 @@ int legal_mask_launch(const int8_t* boards, const int8_t* colors, const int8_t* 
 // 5x5 conv over the binary planes as a sparse gather-add of weight rows + game-state dense.
 // wt [25][P][C] fp32, gs_w [S][C], gs_b [C]; writes raw fp32 [n*400, C] and the activated copy.
 int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
-                     const float* wt, const float* gs_w, const float* gs_b, float* raw_out, void* act_out,
-                     bool act_bf16, const float* scale, const float* shift, cudaStream_t stream);
+                     const float* wt, const float* gs_w, const float* gs_b, void* raw_out, void* act_out,
+                     bool act_bf16, const float* scale, const float* shift, cudaStream_t stream);  // act_bf16 => raw is fp16
 
 // bf16-mode variant with the (bf16-rounded) weight table resident in shared memory; C <= 256.
 bool init_conv_smem_supported(int nplanes, int C);
 int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
-                          const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, float* raw_out,
+                          const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, __half* raw_out,
                           __nv_bfloat16* act_out, const float* scale, const float* shift, cudaStream_t stream);
 
 // ---- broadcast mix (broadcast.cu) -------------------------------------------------------------------

@@ -103,7 +103,8 @@ int conv_fp32_launch(const float* in, const float* w, int rows, int cin, int cou
   Taps tap{};
   for (int t = 0; t < taps; ++t) tap.off[t] = tap_off_host[t];
   dim3 grid((rows + BM - 1) / BM, (cout + BN - 1) / BN);
-  conv_fp32_kernel<<<grid, 256, 0, stream>>>(in, w, rows, cin, cout, taps, tap, ep.residual, ep.raw_out,
+  conv_fp32_kernel<<<grid, 256, 0, stream>>>(in, w, rows, cin, cout, taps, tap, reinterpret_cast<const float*>(ep.residual),
+                                             reinterpret_cast<float*>(ep.raw_out),
                                              reinterpret_cast<float*>(ep.act_out), ep.scale, ep.shift, ep.act_mode);
   P3_CUDA(cudaGetLastError());
   return P3_OK;

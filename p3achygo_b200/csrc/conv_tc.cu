@@ -55,8 +55,10 @@ constexpr int kStageF32Bytes = kTileM * 32 * 4;   // 16 KB
 constexpr int kStageBf16Bytes = kTileM * 32 * 2;  // 8 KB
 constexpr int kNumResBuf = 4;
 constexpr int kNumOutBuf = 2;
-__host__ __device__ constexpr int staging_bytes(bool res, bool raw, bool act) {
-  return (res ? kNumResBuf * kStageF32Bytes : 0) + (raw ? kNumOutBuf * kStageF32Bytes : 0) + (act ? kNumOutBuf * kStageBf16Bytes : 0);
+// residual / raw tiles are fp32 (128 B rows, 128B swizzle) or, when the residual stream is fp16, 64 B rows (64B swizzle)
+__host__ __device__ constexpr int staging_bytes(bool res, bool raw, bool act, bool raw_f16) {
+  return (res ? kNumResBuf * (raw_f16 ? kStageBf16Bytes : kStageF32Bytes) : 0) +
+         (raw ? kNumOutBuf * (raw_f16 ? kStageBf16Bytes : kStageF32Bytes) : 0) + (act ? kNumOutBuf * kStageBf16Bytes : 0);
 }
 
 struct TcTaps {
@@ -84,6 +86,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// two floats -> packed IEEE fp16 pair, saturating to +-65504 (the residual stream never overflows to inf)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 template <int kMode>
 __device__ __forceinline__ float activate(float x, float sc, float sh) {
   if (kMode == kActMishBN) return mish_f32<false>(fmaf(x, sc, sh));
@@ -99,14 +108,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
-               const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace) {
+               const float* __restrict__ shift, int act_mode, int raw_f16, int debug, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int raw_tile_bytes = raw_f16 ? kStageBf16Bytes : kStageF32Bytes;
   uint8_t* st_res = smem;
-  uint8_t* st_raw = st_res + (has_res ? kNumResBuf * kStageF32Bytes : 0);
-  uint8_t* st_act = st_raw + (has_raw ? kNumOutBuf * kStageF32Bytes : 0);
-  uint8_t* ring = smem + staging_bytes(has_res, has_raw, has_act);
+  uint8_t* st_raw = st_res + (has_res ? kNumResBuf * raw_tile_bytes : 0);
+  uint8_t* st_act = st_raw + (has_raw ? kNumOutBuf * raw_tile_bytes : 0);
+  uint8_t* ring = smem + staging_bytes(has_res, has_raw, has_act, raw_f16);
   const int stage_bytes = kABytes + n_tile * kSlabK * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
@@ -234,8 +244,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // this thread's row inside a 128 B-row (fp32, 128B swizzle) / 64 B-row (bf16, 64B swizzle) staging tile
     const uint32_t f32_row = static_cast<uint32_t>(r) * 128u;
     const uint32_t bf_row = static_cast<uint32_t>(r) * 64u;
-    uint8_t* my_res = st_res + grp * (2 * kStageF32Bytes);   // 2-deep residual ring per group
-    uint8_t* my_raw = st_raw + grp * kStageF32Bytes;
+    uint8_t* my_res = st_res + grp * (2 * raw_tile_bytes);   // 2-deep residual ring per group
+    uint8_t* my_raw = st_raw + grp * raw_tile_bytes;
     uint8_t* my_act = st_act + grp * kStageBf16Bytes;
     uint64_t* my_res_full = res_full + 2 * grp;
 
@@ -246,8 +256,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ci = static_cast<int>(G % n_chunks);
       const int m0i = (tile_i / n_tiles) * kTileM, n0i = (tile_i % n_tiles) * n_tile;
       const uint32_t b = (G >> 1) & 1u;
-      ptx::mbar_arrive_expect_tx(&my_res_full[b], kStageF32Bytes);
-      ptx::tma_load_2d(my_res + b * kStageF32Bytes, &map_res, &my_res_full[b], n0i + ci * 32, m0i);
+      ptx::mbar_arrive_expect_tx(&my_res_full[b], static_cast<uint32_t>(raw_tile_bytes));
+      ptx::tma_load_2d(my_res + b * raw_tile_bytes, &map_res, &my_res_full[b], n0i + ci * 32, m0i);
     };
     if (leader && has_res) {  // prefetch this group's first two chunks
       issue_res(grp);
@@ -283,14 +293,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float x[16];
         if (has_res) {
           ptx::mbar_wait(&my_res_full[buf], (k >> 1) & 1u);
-          const uint32_t rp = ptx::smem_u32(my_res) + buf * kStageF32Bytes + f32_row;
+          if (raw_f16) {  // 16 halves = 2 chunks of the 64 B row (64B swizzle)
+            const uint32_t rp = ptx::smem_u32(my_res) + buf * raw_tile_bytes + bf_row;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t4 = ptx::lds_f4(rp + (((half * 4 + j) ^ (r & 7)) << 4));
-            x[4 * j] = t4.x;
-            x[4 * j + 1] = t4.y;
-            x[4 * j + 2] = t4.z;
-            x[4 * j + 3] = t4.w;
+            for (int j = 0; j < 2; ++j) {
+              const float4 t4 = ptx::lds_f4(rp + (((half * 2 + j) ^ ((r >> 1) & 3)) << 4));
+              const uint32_t u[4] = {__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w)};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u[q]));
+                x[8 * j + 2 * q] = f2.x;
+                x[8 * j + 2 * q + 1] = f2.y;
+              }
+            }
+          } else {
+            const uint32_t rp = ptx::smem_u32(my_res) + buf * raw_tile_bytes + f32_row;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = ptx::lds_f4(rp + (((half * 4 + j) ^ (r & 7)) << 4));
+              x[4 * j] = t4.x;
+              x[4 * j + 1] = t4.y;
+              x[4 * j + 2] = t4.z;
+              x[4 * j + 3] = t4.w;
+            }
           }
         } else {
 #pragma unroll
@@ -332,7 +357,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ptx::named_bar_sync(bar_a, kGrpThreads);
         if (tr) tc[5] = clock64();
         if (leader && has_res) issue_res(G + 4);  // refill the ring slot just consumed with this group's chunk k + 2
-        if (has_raw) {
+        if (has_raw && raw_f16) {
+          const uint32_t wp = ptx::smem_u32(my_raw) + bf_row;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            ptx::sts_u4(wp + (((half * 2 + j) ^ ((r >> 1) & 3)) << 4),
+                        make_uint4(pack_f16(x[8 * j], x[8 * j + 1]), pack_f16(x[8 * j + 2], x[8 * j + 3]),
+                                   pack_f16(x[8 * j + 4], x[8 * j + 5]), pack_f16(x[8 * j + 6], x[8 * j + 7])));
+        } else if (has_raw) {
           const uint32_t wp = ptx::smem_u32(my_raw) + f32_row;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -1047,7 +1079,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   } else {
     p->n_tile = pick_n_tile(cout);
     const int stage_bytes = kABytes + p->n_tile * kSlabK * 2;
-    const int staging = staging_bytes(ep.residual != nullptr, ep.raw_out != nullptr, ep.act_out != nullptr);
+    const int staging = staging_bytes(ep.residual != nullptr, ep.raw_out != nullptr, ep.act_out != nullptr, ep.raw_f16);
     p->stages = std::min(8, (kSmemBudget - 1024 - kBarBytes - staging) / stage_bytes);
     p->smem_bytes = static_cast<size_t>(p->stages) * stage_bytes + 1024 /*align slack*/ + kBarBytes + staging;
     int cols = 32;
@@ -1059,12 +1091,11 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
     if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_tile);
     // epilogue maps: fp32 [rows, cout] boxes of 128 rows x 32 cols (128 B rows, 128B swizzle);
     //                bf16 [rows, cout] boxes of 128 rows x 32 cols (64 B rows, 64B swizzle)
-    if (rc == P3_OK && ep.residual)
-      rc = make_map_2d(&p->map_res, ep.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, rows, 32, kTileM,
-                       CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc == P3_OK && ep.raw_out)
-      rc = make_map_2d(&p->map_raw, ep.raw_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, rows, 32, kTileM,
-                       CU_TENSOR_MAP_SWIZZLE_128B);
+    const CUtensorMapDataType raw_dt = ep.raw_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const int raw_es = ep.raw_f16 ? 2 : 4;
+    const CUtensorMapSwizzle raw_sw = ep.raw_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (rc == P3_OK && ep.residual) rc = make_map_2d(&p->map_res, ep.residual, raw_dt, raw_es, cout, rows, 32, kTileM, raw_sw);
+    if (rc == P3_OK && ep.raw_out) rc = make_map_2d(&p->map_raw, ep.raw_out, raw_dt, raw_es, cout, rows, 32, kTileM, raw_sw);
     if (rc == P3_OK && ep.act_out)
       rc = make_map_2d(&p->map_act, ep.act_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cout, rows, 32, kTileM,
                        CU_TENSOR_MAP_SWIZZLE_64B);
@@ -1117,7 +1148,7 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
         p->stages, p->tmem_cols, ep.residual != nullptr && !(p->debug & 32), ep.raw_out != nullptr, ep.act_out != nullptr,
-        ep.scale, ep.shift, ep.act_mode, p->debug >> 8, p->trace);
+        ep.scale, ep.shift, ep.act_mode, ep.raw_f16 ? 1 : 0, p->debug >> 8, p->trace);
   }
   P3_CUDA(cudaGetLastError());
   return P3_OK;

@@ -183,10 +183,10 @@ struct p3_engine {
   int run_init() {
     if (init_smem)
       return init_conv_smem_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
-                                   init_wt_bf16.as<__nv_bfloat16>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(),
+                                   init_wt_bf16.as<__nv_bfloat16>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<__half>(),
                                    actA.as<__nv_bfloat16>(), first_scale, first_shift, stream);
     return init_conv_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C, init_wt.as<float>(),
-                            gs_w.as<float>(), gs_b.as<float>(), xraw.as<float>(), actA.p, bf16, first_scale, first_shift, stream);
+                            gs_w.as<float>(), gs_b.as<float>(), xraw.p, actA.p, bf16, first_scale, first_shift, stream);
   }
 
   int run_broadcast(const Step& s) {
@@ -352,7 +352,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   if ((rc = e.d_masks.alloc(sizeof(uint16_t) * B * 361))) return rc;
   if ((rc = e.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
   if ((rc = e.d_aux.alloc(sizeof(p3_aux_result) * B))) return rc;
-  if ((rc = e.xraw.alloc(sizeof(float) * R * C))) return rc;
+  // residual stream: fp32, or IEEE fp16 in the bf16 engine (fp32 accumulation inside every block)
+  if ((rc = e.xraw.alloc((e.bf16 ? sizeof(__half) : sizeof(float)) * R * C))) return rc;
   if ((rc = e.actA.alloc(esz * R * C))) return rc;
   if ((rc = e.actB.alloc(esz * R * C))) return rc;
   if (btl) {
@@ -446,7 +447,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   void* other = e.actB.p;
   e.first_scale = blocks[0].convs[0]->in_scale.as<float>();
   e.first_shift = blocks[0].convs[0]->in_shift.as<float>();
-  auto add_conv = [&](ConvLayer* L, const void* in, const float* residual, float* raw, void* act, int mode,
+  auto add_conv = [&](ConvLayer* L, const void* in, const void* residual, void* raw, void* act, int mode,
                       const ConvLayer* next) -> int {
     Step s;
     s.kind = kStepConv;
@@ -454,6 +455,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.in = in;
     s.ep.residual = residual;
     s.ep.raw_out = raw;
+    s.ep.raw_f16 = e.bf16 && (residual != nullptr || raw != nullptr);
     s.ep.act_out = act;
     s.ep.act_mode = mode;
     if (mode == kActMishBN) {
@@ -471,6 +473,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   for (int i = 0; i < e.blocks; ++i) {
     BlockDesc& bk = blocks[i];
     const bool last_block = i == e.blocks - 1;
+    // bf16 engine: nothing reads the raw stream after the last block (the heads take the identity-activated copy)
+    void* raw_dst = (last_block && e.bf16) ? nullptr : e.xraw.p;
     const ConvLayer* next_first = last_block ? nullptr : blocks[i + 1].convs[0];
     // what the block's final conv writes besides the raw residual stream
     int end_mode = last_block ? (e.bf16 ? kActIdentity : kActNone) : kActMishBN;
@@ -492,7 +496,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
           return rc;
       }
       e.program.push_back(s);
-      if ((rc = add_conv(bk.convs[1], cur, e.xraw.as<float>(), e.xraw.as<float>(), end_act, end_mode, next_first))) return rc;
+      if ((rc = add_conv(bk.convs[1], cur, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
     } else if (btl) {  // BottleneckResidualConvBlock, model.py:372-412
       void* s0 = e.actS0.p;
       void* s1 = e.actS1.p;
@@ -502,11 +506,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
         if ((rc = add_conv(bk.convs[j], s0, nullptr, nullptr, s1, kActMishBN, bk.convs[j + 1]))) return rc;
         std::swap(s0, s1);
       }
-      if ((rc = add_conv(bk.convs[nc - 1], s0, e.xraw.as<float>(), e.xraw.as<float>(), end_act, end_mode, next_first))) return rc;
+      if ((rc = add_conv(bk.convs[nc - 1], s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
     } else {  // ClassicResidualBlock, model.py:330-354
       if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMishBN, bk.convs[1]))) return rc;
       // second conv reads `other`; `cur` is free again and becomes the block output
-      if ((rc = add_conv(bk.convs[1], other, e.xraw.as<float>(), e.xraw.as<float>(), last_block && !e.bf16 ? nullptr : cur,
+      if ((rc = add_conv(bk.convs[1], other, e.xraw.p, raw_dst, last_block && !e.bf16 ? nullptr : cur,
                          end_mode, next_first))) return rc;
       continue;  // output already in `cur`
     }

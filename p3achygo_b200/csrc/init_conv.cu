@@ -22,7 +22,7 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 init_conv_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ scalars, int nplanes, int nscalars,
                  int C, const float* __restrict__ wt, const float* __restrict__ gs_w, const float* __restrict__ gs_b,
-                 float* __restrict__ raw_out, void* __restrict__ act_out, const float* __restrict__ scale,
+                 void* __restrict__ raw_out, void* __restrict__ act_out, const float* __restrict__ scale,
                  const float* __restrict__ shift) {
   extern __shared__ float s_gs[];  // [C] game-state bias of this position
   __shared__ uint16_t s_mask[P3_NUM_BOARD_LOCS];
@@ -41,6 +41,8 @@ init_conv_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ s
   const size_t row0 = static_cast<size_t>(b) * kRowsPerPos;
   __nv_bfloat16* act_bf = reinterpret_cast<__nv_bfloat16*>(act_out);
   float* act_f = reinterpret_cast<float*>(act_out);
+  __half* raw_h = reinterpret_cast<__half*>(raw_out);  // bf16 mode: the residual stream is fp16
+  float* raw_f = reinterpret_cast<float*>(raw_out);
 
   for (int q = warp; q < kRowsPerPos; q += nwarps) {
     const size_t row = row0 + q;
@@ -48,7 +50,8 @@ init_conv_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ s
       for (int k = 0; k < per_lane; ++k) {
         const int c = lane + 32 * k;
         if (c < C) {
-          raw_out[row * C + c] = 0.0f;
+          if (kBf16) raw_h[row * C + c] = __float2half_rn(0.0f);
+          else raw_f[row * C + c] = 0.0f;
           if (kBf16) act_bf[row * C + c] = __float2bfloat16(0.0f);
           else act_f[row * C + c] = 0.0f;
         }
@@ -84,7 +87,8 @@ init_conv_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ s
       const int c = lane + 32 * k;
       if (k < per_lane && c < C) {
         const float x = acc[k] + s_gs[c];
-        raw_out[row * C + c] = x;
+        if (kBf16) raw_h[row * C + c] = __float2half_rn(x);
+        else raw_f[row * C + c] = x;
         const float a = mish_f32<!kBf16>(fmaf(x, scale[c], shift[c]));
         if (kBf16) act_bf[row * C + c] = __float2bfloat16(a);
         else act_f[row * C + c] = a;
@@ -102,7 +106,7 @@ constexpr int kIcThreads = 512;
 __global__ void __launch_bounds__(kIcThreads, 1)
 init_conv_smem_kernel(const uint16_t* __restrict__ masks, const float* __restrict__ scalars, int n, int nplanes,
                       int nscalars, int C, const __nv_bfloat16* __restrict__ wt_bf16, const float* __restrict__ gs_w,
-                      const float* __restrict__ gs_b, float* __restrict__ raw_out, __nv_bfloat16* __restrict__ act_out,
+                      const float* __restrict__ gs_b, __half* __restrict__ raw_out, __nv_bfloat16* __restrict__ act_out,
                       const float* __restrict__ scale, const float* __restrict__ shift) {
   extern __shared__ __align__(16) uint8_t ic_smem[];
   const int rows_w = 25 * nplanes;
@@ -136,11 +140,11 @@ init_conv_smem_kernel(const uint16_t* __restrict__ masks, const float* __restric
     const size_t row0 = static_cast<size_t>(b) * kRowsPerPos;
     for (int q = warp; q < kRowsPerPos; q += nwarps) {
       const size_t row = row0 + q;
-      float2* raw2 = reinterpret_cast<float2*>(raw_out + row * C);
+      __half2* raw2 = reinterpret_cast<__half2*>(raw_out + row * C);
       __nv_bfloat162* act2 = reinterpret_cast<__nv_bfloat162*>(act_out + row * C);
       if (!row_is_live(q)) {
         for (int k = 0; k < pairs; ++k) {
-          raw2[lane + 32 * k] = make_float2(0.0f, 0.0f);
+          raw2[lane + 32 * k] = __floats2half2_rn(0.0f, 0.0f);
           act2[lane + 32 * k] = __floats2bfloat162_rn(0.0f, 0.0f);
         }
         continue;
@@ -177,7 +181,7 @@ init_conv_smem_kernel(const uint16_t* __restrict__ masks, const float* __restric
         if (k < pairs) {
           const int c = 2 * (lane + 32 * k);
           const float x0 = acc[k].x + s_gs[c], x1 = acc[k].y + s_gs[c + 1];
-          raw2[lane + 32 * k] = make_float2(x0, x1);
+          raw2[lane + 32 * k] = __floats2half2_rn(x0, x1);
           act2[lane + 32 * k] = __floats2bfloat162_rn(mish_f32<false>(fmaf(x0, s_sc[c], s_sh[c])),
                                                       mish_f32<false>(fmaf(x1, s_sc[c + 1], s_sh[c + 1])));
         }
@@ -195,7 +199,7 @@ bool init_conv_smem_supported(int nplanes, int C) {
 }
 
 int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
-                          const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, float* raw_out,
+                          const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, __half* raw_out,
                           __nv_bfloat16* act_out, const float* scale, const float* shift, cudaStream_t stream) {
   const size_t smem = init_conv_smem_bytes(nplanes, C);
   cudaError_t e = cudaFuncSetAttribute(init_conv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -210,7 +214,7 @@ int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, in
 }
 
 int init_conv_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
-                     const float* wt, const float* gs_w, const float* gs_b, float* raw_out, void* act_out,
+                     const float* wt, const float* gs_w, const float* gs_b, void* raw_out, void* act_out,
                      bool act_bf16, const float* scale, const float* shift, cudaStream_t stream) {
   if (C > 32 * kMaxCPerLane) return fail(P3_ERR_UNSUPPORTED, "init_conv: C > 384");
   const size_t smem = sizeof(float) * C;
