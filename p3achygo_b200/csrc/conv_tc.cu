@@ -265,6 +265,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 
     int iter = 0;
+    const long long t_loop = (trace != nullptr && blockIdx.x == 3 && leader && grp == 0) ? clock64() : 0;
+    uint32_t tsum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // P3_TC_TRACE: per-phase cycle sums of this thread (registers)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int m0 = (tile / n_tiles) * kTileM, n0 = (tile % n_tiles) * n_tile;
       const int acc = iter & 1;
@@ -276,14 +278,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c = 0; c < ((debug & 1) ? 0 : n_chunks); ++c) {
         const uint32_t G = static_cast<uint32_t>(iter) * n_chunks + c;
         if ((G & 1u) != static_cast<uint32_t>(grp)) continue;
+        const bool tr = trace != nullptr && blockIdx.x == 3 && leader && grp == 0;
         if (!waited) {
+          const long long tw = tr ? clock64() : 0;
           ptx::mbar_wait(&tmem_full[acc], acc_phase);
           ptx::tc_fence_after_sync();
           waited = true;
+          if (tr) tsum[8] += static_cast<uint32_t>(clock64() - tw);
         }
         const uint32_t k = G >> 1;  // this group's chunk ordinal
         const uint32_t buf = k & 1u;
-        const bool tr = trace != nullptr && blockIdx.x == 3 && leader && grp == 0;
         long long tc[8];
         if (tr) tc[0] = clock64();
         uint32_t v[16];
@@ -386,10 +390,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (tr) {
           tc[7] = clock64();
           // phases: 0 res-wait  1 tmem ld wait  2 math  3 bulk_wait_read  4 barrier A  5 staging+fence  6 barrier B + TMA issue
-          for (int i = 0; i < 7; ++i) atomicAdd(&trace[i], static_cast<unsigned long long>(tc[i + 1] - tc[i]));
-          atomicAdd(&trace[7], 1ull);
-          if (trace[8] != 0) atomicAdd(&trace[9], static_cast<unsigned long long>(tc[0]) - trace[8]);  // gap since previous chunk end
-          trace[8] = static_cast<unsigned long long>(tc[7]);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) tsum[i] += static_cast<uint32_t>(tc[i + 1] - tc[i]);
+          ++tsum[7];
         }
       }
       if (!waited) {  // (only with the ablation that skips all chunks) still consume the accumulator
@@ -402,6 +405,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
     }
     if (leader) ptx::bulk_wait_all();
+    if (trace != nullptr && blockIdx.x == 3 && leader && grp == 0) {
+      atomicAdd(&trace[11], static_cast<unsigned long long>(clock64() - t_loop));
+      atomicAdd(&trace[12], 1ull);
+      for (int i = 0; i < 8; ++i) atomicAdd(&trace[i], static_cast<unsigned long long>(tsum[i]));
+      atomicAdd(&trace[10], static_cast<unsigned long long>(tsum[8]));
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -985,8 +994,8 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
   const char* env_res = std::getenv("P3_TC_RESIDENT");
   if (const char* dbg = std::getenv("P3_TC_DEBUG")) p->debug = std::atoi(dbg);
   if (std::getenv("P3_TC_TRACE")) {
-    cudaMalloc(&p->trace, 10 * sizeof(unsigned long long));
-    cudaMemset(p->trace, 0, 10 * sizeof(unsigned long long));
+    cudaMalloc(&p->trace, 16 * sizeof(unsigned long long));
+    cudaMemset(p->trace, 0, 16 * sizeof(unsigned long long));
   }
   const size_t res_smem =
       static_cast<size_t>(9) * (cin / kSlabK) * kResWSlabBytes + kResStages * kResABytes + 1024 + kBarBytes;
@@ -1117,7 +1126,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
 
 void tc_conv_plan_destroy(TcConvPlan* plan) {
   if (plan && plan->trace) {
-    unsigned long long h[10];
+    unsigned long long h[16];
     cudaMemcpy(h, plan->trace, sizeof h, cudaMemcpyDeviceToHost);
     if (plan->pair && h[0])
       std::fprintf(stderr, "[p3 trace] pair 3x3 cin=%d cout=%d launches=%llu ns/launch (CTA 0): gap-since-previous-kernel-end %llu  "
@@ -1125,9 +1134,10 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
                    plan->cin, plan->cout, h[0], h[1] / h[0], h[2] / h[0], h[3] / h[0], h[4] / h[0], h[5] / h[0]);
     else if (h[7])
       std::fprintf(stderr, "[p3 trace] cin=%d cout=%d taps=%d res=%d raw=%d act=%d chunks=%llu cycles/chunk: res_wait %llu  tmem_ld %llu  math %llu  "
-                           "bulk_wait %llu  barA %llu  stage+fence %llu  barB+tma %llu  | gap-between-chunks %llu\n",
+                           "bulk_wait %llu  barA %llu  stage+fence %llu  barB+tma %llu  | per launch: epilogue loop %llu cycles, of which waiting for accumulators %llu\n",
                    plan->cin, plan->cout, plan->taps, plan->ep.residual != nullptr, plan->ep.raw_out != nullptr, plan->ep.act_out != nullptr,
-                   h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7], h[9] / h[7]);
+                   h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7],
+                   h[12] ? h[11] / h[12] : 0ull, h[12] ? h[10] / h[12] : 0ull);
     cudaFree(plan->trace);
   }
   delete plan;

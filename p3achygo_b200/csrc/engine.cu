@@ -9,6 +9,7 @@
 // its TensorRT graph, trt_engine.cc:168-220).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -789,6 +790,15 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
     ms[cls[i]] += t;
     launches[cls[i]] += 1;
     flops[cls[i]] += fl[i];
+    if (std::getenv("P3_PROFILE_VERBOSE")) {  // per-launch listing (perf work)
+      const Step* st = (i >= 2 && i - 2 < e->program.size()) ? &e->program[i - 2] : nullptr;
+      if (st && st->kind == kStepConv)
+        std::fprintf(stderr, "[p3 profile] #%zu class %d conv taps=%d cin=%d cout=%d res=%d raw=%d act=%d: %.1f us\n", i, cls[i],
+                     st->layer->taps, st->layer->cin, st->layer->cout, st->ep.residual != nullptr, st->ep.raw_out != nullptr,
+                     st->ep.act_out != nullptr, t * 1e3f);
+      else
+        std::fprintf(stderr, "[p3 profile] #%zu class %d: %.1f us\n", i, cls[i], t * 1e3f);
+    }
   }
   for (auto& v : evs) cudaEventDestroy(v);
   return rc;
