@@ -1,0 +1,575 @@
+// Fused block boundary of the bottleneck tower on a CTA pair (tcgen05 cta_group::2):
+//
+//     x'  = x + W_expand * t                       (1x1, Cb -> C, + residual stream; python/model.py:404-412)
+//     u   = mish(BN_a(x'))                         (pre-activation of the NEXT block's first conv, model.py:276-281)
+//     out = act2( W_reduce * u )                   (1x1, C -> Cb of the next block; act2 = that block's next BN + mish)
+//
+// Unfused these are two HBM-bound launches that round-trip the C-wide activated copy `u` through HBM (write 2*C
+// bytes + read 2*C bytes per board row); here `u` only ever exists in shared memory as the A operand of the second
+// GEMM.  Per 128-row tile and CTA: read t (Cb bf16) + x (C fp16), write x' (C fp16) + out (N2 bf16).
+//
+// One persistent CTA pair per TPC, 576 threads per CTA:
+//   warp 0      TMA producer: this CTA's halves of W1 / W2 once (resident), then its own 128-row A1 tiles
+//   warp 1      MMA issuer (leader CTA only): GEMM1 (M=256, N=N1) into acc1, then GEMM2 (M=256, N=N2) into acc2, one
+//               64-wide K slab at a time as the epilogue warps publish the slabs of `u`
+//   warps 2-17  epilogue, 4 warps per TMEM lane quarter; a quarter (32 rows) works through 64-column slabs:
+//               tcgen05.ld -> + residual (TMA-prefetched box) -> x' box (TMA store) and the slab of `u` (swizzled K-major,
+//               straight into the A2 ring) ; then the same for acc2 -> out boxes.  Quarters are independent of each
+//               other (own named barrier, own staging, own bulk-store groups), so their phases interleave on the SM.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "math.cuh"
+#include "ptx.cuh"
+#include "tc_util.cuh"
+
+namespace p3 {
+
+constexpr int kChEpiWarps = 16;
+constexpr int kChThreads = (2 + kChEpiWarps + 4) * 32;  // 704: producer, MMA, 16 epilogue, 4 I/O (one per TMEM lane quarter)
+constexpr int kChSlabBytes = 128 * 128;   // 128 rows x 64 bf16 (one K slab of an A operand)
+constexpr int kChBoxBytes = 32 * 128;     // a quarter's 32 rows x 64 two-byte elements
+constexpr int kChResBufs = 2;
+constexpr int kChOutBufs = 3;
+constexpr int kChMaxN = 256;
+constexpr int kChSmemBudget = 227 * 1024;
+
+struct TcChainPlan {
+  CUtensorMap map_a1, map_w1, map_w2, map_res, map_raw, map_out2;
+  int rows = 0, k1 = 0, n1 = 0, n2 = 0, grid = 0, tmem_cols = 512, acc2_stages = 1;
+  size_t smem_bytes = 0;
+  const float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
+  int act2_mode = kActMishBN;
+  unsigned long long* trace = nullptr;  // P3_TC_TRACE
+};
+
+namespace {
+
+__host__ __device__ constexpr int chain_fixed_smem(int k1, int n1, int n2) {
+  return (k1 / 64) * (n1 / 2) * 128 + (n1 / 64) * (n2 / 2) * 128 + (k1 / 64) * kChSlabBytes + 2 * kChSlabBytes +
+         4 * (kChResBufs + kChOutBufs) * kChBoxBytes;
+}
+constexpr int kChBarRegion = 512;
+constexpr int kChBarBytes = kChBarRegion + 4 * kChMaxN * 4;
+
+// 16 activations: a[i] = mish(x[i] * scale[col0 + i] + shift[col0 + i]), scale / shift in shared memory
+__device__ __forceinline__ void bn_mish16(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 s4 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0 + 4 * i) * 4u);
+    const float4 h4 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0 + 4 * i) * 4u);
+    mish2_f32(fmaf(x[4 * i], s4.x, h4.x), fmaf(x[4 * i + 1], s4.y, h4.y), a[4 * i], a[4 * i + 1]);
+    mish2_f32(fmaf(x[4 * i + 2], s4.z, h4.z), fmaf(x[4 * i + 3], s4.w, h4.w), a[4 * i + 2], a[4 * i + 3]);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChThreads, 1)
+tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_w1,
+                     const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
+                     const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_out2, int rows, int k1,
+                     int n1, int n2, int acc2_stages, int tmem_cols, const float* __restrict__ scale1,
+                     const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
+                     int act2_mode, unsigned long long* trace) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int k1_slabs = k1 / 64, n1_slabs = n1 / 64, n2_slabs = n2 / 64;
+  const int w1_slab_bytes = (n1 / 2) * 128, w2_slab_bytes = (n2 / 2) * 128;
+  const int w1_bytes = k1_slabs * w1_slab_bytes, w2_bytes = n1_slabs * w2_slab_bytes;
+  uint8_t* smem_w1 = smem;
+  uint8_t* smem_w2 = smem_w1 + w1_bytes;
+  uint8_t* smem_a1 = smem_w2 + w2_bytes;
+  uint8_t* smem_a2 = smem_a1 + k1_slabs * kChSlabBytes;
+  uint8_t* smem_res = smem_a2 + 2 * kChSlabBytes;
+  uint8_t* smem_out = smem_res + 4 * kChResBufs * kChBoxBytes;
+  uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem_out + 4 * kChOutBufs * kChBoxBytes);
+  uint64_t* a1_empty = a1_full + 4;
+  uint64_t* acc1_full = a1_empty + 4;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* a2_full = acc1_empty + 1;
+  uint64_t* a2_empty = a2_full + 2;
+  uint64_t* acc2_full = a2_empty + 2;
+  uint64_t* acc2_empty = acc2_full + 2;
+  uint64_t* w_bar = acc2_empty + 2;
+  uint64_t* res_full = w_bar + 1;                      // [4 quarters][kChResBufs]  TMA load landed
+  uint64_t* res_empty = res_full + 4 * kChResBufs;     //                            the quarter's 4 warps have read it
+  uint64_t* out_full = res_empty + 4 * kChResBufs;     // [4 quarters][kChOutBufs]  the quarter's 4 warps have written it
+  uint64_t* out_empty = out_full + 4 * kChOutBufs;     //                            the TMA store has read it
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_empty + 4 * kChOutBufs);
+  float* s_scale1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a1_full) + kChBarRegion);
+  float* s_shift1 = s_scale1 + kChMaxN;
+  float* s_scale2 = s_shift1 + kChMaxN;
+  float* s_shift2 = s_scale2 + kChMaxN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (rows + 255) / 256;
+  const int n_it = pair < m_tiles ? (m_tiles - pair + n_pairs - 1) / n_pairs : 0;  // tiles of this pair
+  const int defer = acc2_stages >= 2 ? 1 : 0;  // epi2 runs one tile behind epi1 (needs the second acc2 stage)
+
+  for (int c = threadIdx.x; c < n1; c += blockDim.x) {
+    s_scale1[c] = scale1[c];
+    s_shift1[c] = shift1[c];
+  }
+  for (int c = threadIdx.x; c < n2; c += blockDim.x) {
+    s_scale2[c] = act2_mode == kActMishBN ? scale2[c] : 1.0f;
+    s_shift2[c] = act2_mode == kActMishBN ? shift2[c] : 0.0f;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a1);
+    ptx::prefetch_tensormap(&map_w1);
+    ptx::prefetch_tensormap(&map_w2);
+    ptx::prefetch_tensormap(&map_res);
+    ptx::prefetch_tensormap(&map_raw);
+    ptx::prefetch_tensormap(&map_out2);
+    for (int s = 0; s < 4; ++s) {
+      ptx::mbar_init(&a1_full[s], 1);   // leader's is live: one arrive.expect_tx for both CTAs' bytes
+      ptx::mbar_init(&a1_empty[s], 1);  // multicast commit
+    }
+    ptx::mbar_init(acc1_full, 1);
+    ptx::mbar_init(acc1_empty, 2 * kChEpiWarps);  // leader's: the epilogue warps of both CTAs
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&a2_full[s], 8);  // leader's: the 4 I/O warps of both CTAs
+      ptx::mbar_init(&a2_empty[s], 1);
+      ptx::mbar_init(&acc2_full[s], 1);
+      ptx::mbar_init(&acc2_empty[s], 2 * kChEpiWarps);
+    }
+    ptx::mbar_init(w_bar, 1);
+    for (int s = 0; s < 4 * kChResBufs; ++s) {
+      ptx::mbar_init(&res_full[s], 1);
+      ptx::mbar_init(&res_empty[s], 4);
+    }
+    for (int s = 0; s < 4 * kChOutBufs; ++s) {
+      ptx::mbar_init(&out_full[s], 4);
+      ptx::mbar_init(&out_empty[s], 1);
+    }
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, static_cast<uint32_t>(tmem_cols));
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): resident weight halves, then this CTA's A1 tiles =====
+    const uint32_t w_bar_leader = ptx::mapa_shared(ptx::smem_u32(w_bar), 0);
+    if (ptx::elect_one()) {
+      if (rank == 0) ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(2 * (w1_bytes + w2_bytes)));
+      for (int ks = 0; ks < k1_slabs; ++ks)
+        ptx::tma_load_2d_pair(smem_w1 + ks * w1_slab_bytes, &map_w1, w_bar_leader, ks * 64, static_cast<int>(rank) * (n1 / 2));
+      for (int j = 0; j < n1_slabs; ++j)
+        ptx::tma_load_2d_pair(smem_w2 + j * w2_slab_bytes, &map_w2, w_bar_leader, j * 64, static_cast<int>(rank) * (n2 / 2));
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = pair; mt < m_tiles; mt += n_pairs) {
+      const int m0 = mt * 256 + static_cast<int>(rank) * 128;
+      for (int ks = 0; ks < k1_slabs; ++ks) {
+        ptx::mbar_wait(&a1_empty[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&a1_full[stage], 2 * kChSlabBytes);
+          ptx::tma_load_2d_pair(smem_a1 + stage * kChSlabBytes, &map_a1, ptx::mapa_shared(ptx::smem_u32(&a1_full[stage]), 0),
+                                ks * 64, m0);
+        }
+        __syncwarp();
+        if (++stage == k1_slabs) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      const uint32_t idesc1 = ptx::make_idesc_bf16(256, n1), idesc2 = ptx::make_idesc_bf16(256, n2);
+      const uint32_t w1_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_w1)), w2_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_w2));
+      const uint32_t a1_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a1)), a2_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a2));
+      ptx::mbar_wait_cluster(w_bar, 0);
+      ptx::tc_fence_after_sync();
+      int stage = 0;
+      uint32_t phase = 0, g = 0;
+      int it = 0;
+      for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
+        // ---- GEMM1: acc1 = A1 * W1^T
+        ptx::mbar_wait_cluster(acc1_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
+        ptx::tc_fence_after_sync();
+        for (int ks = 0; ks < k1_slabs; ++ks) {
+          ptx::mbar_wait_cluster(&a1_full[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_lo = a1_lo + static_cast<uint32_t>(stage) * (kChSlabBytes / 16);
+          const uint32_t b_lo = w1_lo + static_cast<uint32_t>(ks) * static_cast<uint32_t>(w1_slab_bytes / 16);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16_pair_lohi(tmem_base, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 2 * k, ptx::desc_hi_sw128(), idesc1,
+                                      (ks > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit_pair(&a1_empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == k1_slabs) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(acc1_full);
+        __syncwarp();
+        // ---- GEMM2: acc2 = u * W2^T, one K slab of u at a time as the epilogue publishes it
+        const int as = it % acc2_stages;
+        ptx::mbar_wait_cluster(&acc2_empty[as], ((static_cast<uint32_t>(it / acc2_stages)) & 1u) ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t tmem_d2 = tmem_base + static_cast<uint32_t>(n1 + as * n2);
+        for (int j = 0; j < n1_slabs; ++j, ++g) {
+          const uint32_t slot = g & 1u;
+          ptx::mbar_wait_cluster(&a2_full[slot], (g >> 1) & 1u);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_lo = a2_lo + slot * (kChSlabBytes / 16);
+          const uint32_t b_lo = w2_lo + static_cast<uint32_t>(j) * static_cast<uint32_t>(w2_slab_bytes / 16);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16_pair_lohi(tmem_d2, a_lo + 2 * k, ptx::desc_hi_sw128(), b_lo + 2 * k, ptx::desc_hi_sw128(), idesc2,
+                                      (j > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit_pair(&a2_empty[slot]);
+          }
+          __syncwarp();
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(&acc2_full[as]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 2 + kChEpiWarps) {
+    // ===== I/O warp of quarter q (both CTAs): every TMA load / store of the quarter's staging boxes, so that the epilogue
+    // warps never issue TMA, never wait for a bulk group and never meet at a CTA barrier.  Per 64-column step of epi1:
+    //   residual box read by the 4 warps -> refill it 2 steps ahead ; x' box written -> TMA store, publish the A2 slab to
+    //   the leader's MMA warp ; the store issued one step earlier has read its box -> hand the box back.
+    const int q = warp - (2 + kChEpiWarps);
+    uint64_t* my_res_full = res_full + kChResBufs * q;
+    uint64_t* my_res_empty = res_empty + kChResBufs * q;
+    uint64_t* my_out_full = out_full + kChOutBufs * q;
+    uint64_t* my_out_empty = out_empty + kChOutBufs * q;
+    const uint32_t a2_full_l = ptx::mapa_shared(ptx::smem_u32(a2_full), 0);
+    uint8_t* my_res = smem_res + q * kChResBufs * kChBoxBytes;
+    const uint32_t my_out = ptx::smem_u32(smem_out) + static_cast<uint32_t>(q) * (kChOutBufs * kChBoxBytes);
+    const int q_row = static_cast<int>(rank) * 128 + q * 32;
+    // residual box of epi1 step s (s counts 64-column slabs over all of this pair's tiles)
+    auto issue_res = [&](uint32_t s) {
+      const int it_s = static_cast<int>(s / static_cast<uint32_t>(n1_slabs)), j_s = static_cast<int>(s % static_cast<uint32_t>(n1_slabs));
+      const int mt_s = pair + it_s * n_pairs;
+      if (mt_s >= m_tiles) return;
+      const uint32_t b = s & 1u;
+      ptx::mbar_arrive_expect_tx(&my_res_full[b], kChBoxBytes);
+      ptx::tma_load_2d(my_res + b * kChBoxBytes, &map_res, &my_res_full[b], j_s * 64, mt_s * 256 + q_row);
+    };
+    if (lane == 0) {
+      issue_res(0);
+      issue_res(1);
+    }
+    uint32_t so = 0, sr = 0, g = 0;
+    // step order per quarter (the epilogue warps follow the same one): epi1(0), [epi1(it), epi2(it - 1)]..., epi2(last)
+    // when acc2 is double-buffered (`defer`), else epi1(it), epi2(it)
+    for (int it = 0; it < n_it + defer; ++it) {
+      if (it < n_it) {
+        const int row0 = (pair + it * n_pairs) * 256 + q_row;
+        for (int j = 0; j < n1_slabs; ++j, ++sr, ++so, ++g) {
+          ptx::mbar_wait(&my_res_empty[sr & 1u], (sr >> 1) & 1u);
+          if (lane == 0) issue_res(sr + 2);
+          const uint32_t ob = so % kChOutBufs;
+          ptx::mbar_wait(&my_out_full[ob], (so / kChOutBufs) & 1u);
+          if (lane == 0) {
+            ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
+            ptx::tma_store_2d(&map_raw, nullptr, 0, 0, my_out + ob * kChBoxBytes, j * 64, row0);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<1>();
+            if (so > 0) ptx::mbar_arrive(&my_out_empty[(so - 1) % kChOutBufs]);
+          }
+          __syncwarp();
+        }
+      }
+      const int it2 = it - defer;
+      if (it2 >= 0 && it2 < n_it) {
+        const int row0 = (pair + it2 * n_pairs) * 256 + q_row;
+        for (int b = 0; b < n2_slabs; ++b, ++so) {
+          const uint32_t ob = so % kChOutBufs;
+          ptx::mbar_wait(&my_out_full[ob], (so / kChOutBufs) & 1u);
+          if (lane == 0) {
+            ptx::tma_store_2d(&map_out2, nullptr, 0, 0, my_out + ob * kChBoxBytes, b * 64, row0);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<1>();
+            ptx::mbar_arrive(&my_out_empty[(so - 1) % kChOutBufs]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) ptx::bulk_wait_all();
+  } else {
+    // ===== epilogue (both CTAs): 4 warps per TMEM lane quarter, thread = one row x 16 of a slab's 64 columns =====
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter of this warp
+    const int cg = ew >> 2;   // which 16 of a slab's 64 columns
+    // a thread's two 16-byte chunks inside a [rows x 128 B] 128B-swizzled box / K-major slab: row*128 + ((c ^ (row & 7)) << 4)
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const uint32_t ch0 = ((2u * cg) ^ sw) << 4, ch1 = ((2u * cg + 1u) ^ sw) << 4;
+    const uint32_t box_row = static_cast<uint32_t>(lane) * 128u;
+    const uint32_t slab_row = static_cast<uint32_t>(q * 32 + lane) * 128u;
+    const uint32_t res_base = ptx::smem_u32(smem_res) + static_cast<uint32_t>(q) * (kChResBufs * kChBoxBytes);
+    const uint32_t out_base = ptx::smem_u32(smem_out) + static_cast<uint32_t>(q) * (kChOutBufs * kChBoxBytes);
+    const uint32_t a2_base = ptx::smem_u32(smem_a2);
+    uint64_t* my_res_full = res_full + kChResBufs * q;
+    uint64_t* my_res_empty = res_empty + kChResBufs * q;
+    uint64_t* my_out_full = out_full + kChOutBufs * q;
+    uint64_t* my_out_empty = out_empty + kChOutBufs * q;
+    const uint32_t acc1_empty_l = ptx::mapa_shared(ptx::smem_u32(acc1_empty), 0);
+    const uint32_t acc2_empty_l = ptx::mapa_shared(ptx::smem_u32(acc2_empty), 0);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sc1 = ptx::smem_u32(s_scale1), sh1 = ptx::smem_u32(s_shift1);
+    const uint32_t sc2 = ptx::smem_u32(s_scale2), sh2 = ptx::smem_u32(s_shift2);
+
+    uint32_t so = 0, sr = 0, g = 0;  // output-box, residual-box and A2-slab ordinals of this quarter
+    int it = 0;
+    // P3_TC_TRACE: per-phase clock64 sums of one epilogue thread (perf experiments)
+    const bool tr = trace != nullptr && blockIdx.x == 3 && ew == 0 && lane == 0;
+    uint32_t ts[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_loop = tr ? clock64() : 0;
+    for (it = 0; it < n_it + defer; ++it) {
+      if (it < n_it) {
+        // ---- epi1: x' = acc1 + x ; u = mish(BN(x')).  Padding rows need no masking here: their A1 rows and residual rows
+        // are zeros (layout invariant), so x' = 0 exactly; their u rows only reach out rows that epi2 zeroes.
+        long long tc0 = tr ? clock64() : 0;
+        ptx::mbar_wait(acc1_full, static_cast<uint32_t>(it) & 1u);
+        ptx::tc_fence_after_sync();
+        if (tr) ts[8] += static_cast<uint32_t>(clock64() - tc0);
+        for (int j = 0; j < n1_slabs; ++j, ++sr, ++so, ++g) {
+          const int col = j * 64 + cg * 16;
+          uint32_t v[16];
+          long long t[8];
+          if (tr) t[0] = clock64();
+          ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(col), v);
+          const uint32_t rb = sr & 1u;
+          ptx::mbar_wait(&my_res_full[rb], (sr >> 1) & 1u);
+          if (tr) t[1] = clock64();
+          const uint32_t rp = res_base + rb * kChBoxBytes + box_row;
+          const float4 t0 = ptx::lds_f4(rp + ch0), t1 = ptx::lds_f4(rp + ch1);
+          float x[16];
+          {
+            const uint32_t u[8] = {__float_as_uint(t0.x), __float_as_uint(t0.y), __float_as_uint(t0.z), __float_as_uint(t0.w),
+                                   __float_as_uint(t1.x), __float_as_uint(t1.y), __float_as_uint(t1.z), __float_as_uint(t1.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+              x[2 * i] = f2.x;
+              x[2 * i + 1] = f2.y;
+            }
+          }
+          __syncwarp();  // the warp's residual values are in registers: hand the box back to the I/O warp
+          if (lane == 0) ptx::mbar_arrive(&my_res_empty[rb]);
+          ptx::tmem_ld_wait();
+          if (tr) t[2] = clock64();
+          if (j == n1_slabs - 1) {  // acc1 is in registers: hand it back to the MMA warp
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(acc1_empty_l);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] += __uint_as_float(v[i]);
+          const uint4 r0 = make_uint4(tc_pack_f16(x[0], x[1]), tc_pack_f16(x[2], x[3]), tc_pack_f16(x[4], x[5]), tc_pack_f16(x[6], x[7]));
+          const uint4 r1 = make_uint4(tc_pack_f16(x[8], x[9]), tc_pack_f16(x[10], x[11]), tc_pack_f16(x[12], x[13]), tc_pack_f16(x[14], x[15]));
+          float a[16];
+          bn_mish16(x, a, sc1, sh1, col);
+          const uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
+          const uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+          // A2 slot free: the MMAs that read its previous slab have completed; output box free: its previous store has read it
+          const uint32_t slot = g & 1u;
+          const uint32_t ob = so % kChOutBufs;
+          if (tr) t[3] = clock64() + (p0.x & 0);
+          ptx::mbar_wait(&a2_empty[slot], ((g >> 1) & 1u) ^ 1u);
+          if (tr) t[4] = clock64();
+          ptx::mbar_wait(&my_out_empty[ob], ((so / kChOutBufs) & 1u) ^ 1u);
+          if (tr) t[5] = clock64();
+          const uint32_t obuf = out_base + ob * kChBoxBytes + box_row;
+          ptx::sts_u4(obuf + ch0, r0);
+          ptx::sts_u4(obuf + ch1, r1);
+          const uint32_t ap = a2_base + slot * kChSlabBytes + slab_row;
+          ptx::sts_u4(ap + ch0, p0);
+          ptx::sts_u4(ap + ch1, p1);
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core / TMA engine
+          if (tr) t[6] = clock64();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&my_out_full[ob]);
+          if (tr) {
+            t[7] = clock64();
+            // 0 res wait  1 tmem ld wait  2 math  3 a2_empty wait  4 out_empty wait  5 sts + fence  6 arrive
+#pragma unroll
+            for (int i = 0; i < 7; ++i) ts[i] += static_cast<uint32_t>(t[i + 1] - t[i]);
+            ++ts[10];
+          }
+        }
+      }
+
+      // ---- epi2: out = act2(acc2) of tile it2 (one tile behind epi1 when acc2 is double-buffered, so GEMM2's tail and the
+      // commit latency are never waited for)
+      const int it2 = it - defer;
+      if (it2 >= 0 && it2 < n_it) {
+        const int m = (pair + it2 * n_pairs) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+        const bool live = m < rows && row_is_live(m % kRowsPerPos);
+        const int as = it2 % acc2_stages;
+        const long long tc0 = tr ? clock64() : 0;
+        ptx::mbar_wait(&acc2_full[as], static_cast<uint32_t>(it2 / acc2_stages) & 1u);
+        ptx::tc_fence_after_sync();
+        const long long tc1 = tr ? clock64() : 0;
+        if (tr) ts[9] += static_cast<uint32_t>(tc1 - tc0);
+        for (int b = 0; b < n2_slabs; ++b, ++so) {
+          const int col = b * 64 + cg * 16;
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(n1 + as * n2 + col), v);
+          ptx::tmem_ld_wait();
+          if (b == n2_slabs - 1) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(acc2_empty_l + 8u * static_cast<uint32_t>(as));
+          }
+          float x[16], a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+          if (act2_mode == kActIdentity) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = x[i];
+          } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
+            bn_mish16(x, a, sc2, sh2, col);
+          }
+          uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
+          uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+          if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
+          const uint32_t ob = so % kChOutBufs;
+          ptx::mbar_wait(&my_out_empty[ob], ((so / kChOutBufs) & 1u) ^ 1u);
+          const uint32_t obuf = out_base + ob * kChBoxBytes + box_row;
+          ptx::sts_u4(obuf + ch0, p0);
+          ptx::sts_u4(obuf + ch1, p1);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&my_out_full[ob]);
+        }
+        if (tr) {
+          ts[11] += static_cast<uint32_t>(clock64() - tc1);
+          ++ts[12];
+        }
+      }
+    }
+    if (tr) {
+      for (int i = 0; i < 13; ++i) atomicAdd(&trace[i], static_cast<unsigned long long>(ts[i]));
+      atomicAdd(&trace[13], static_cast<unsigned long long>(clock64() - t_loop));
+      atomicAdd(&trace[14], 1ull);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync_all();  // the peer's MMAs / TMEM traffic are complete before either CTA frees its columns
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(tmem_cols));
+  }
+}
+
+}  // namespace
+
+bool tc_chain_supported(int k1, int n1, int n2) {
+  if (k1 <= 0 || n1 <= 0 || n2 <= 0) return false;
+  if (k1 % 64 || n1 % 64 || n2 % 64) return false;
+  if (k1 > 256 || n1 > kChMaxN || n2 > kChMaxN || n1 + n2 > 512) return false;
+  return static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + 1024 + kChBarBytes <= static_cast<size_t>(kChSmemBudget);
+}
+
+int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
+                         int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out) {
+  if (!tc_chain_supported(k1, n1, n2)) return fail(P3_ERR_UNSUPPORTED, "tc_chain: shape not supported");
+  if (!in || !w1 || !w2 || !residual_f16 || !raw_f16 || !scale1 || !shift1 || !out2)
+    return fail(P3_ERR_INVALID_ARG, "tc_chain: null argument");
+  TcChainPlan* p = new TcChainPlan();
+  p->rows = rows;
+  p->k1 = k1;
+  p->n1 = n1;
+  p->n2 = n2;
+  p->scale1 = scale1;
+  p->shift1 = shift1;
+  p->scale2 = scale2;
+  p->shift2 = shift2;
+  p->act2_mode = act2_mode;
+  p->acc2_stages = (512 - n1) / n2 >= 2 ? 2 : 1;
+  p->tmem_cols = 512;
+  p->smem_bytes = static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + 1024 + kChBarBytes;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, hf = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc = tc_make_map_2d(&p->map_a1, in, bf, 2, k1, rows, 64, 128, sw);
+  if (rc == P3_OK) rc = tc_make_map_2d(&p->map_w1, w1, bf, 2, k1, n1, 64, n1 / 2, sw);
+  if (rc == P3_OK) rc = tc_make_map_2d(&p->map_w2, w2, bf, 2, n1, n2, 64, n2 / 2, sw);
+  if (rc == P3_OK) rc = tc_make_map_2d(&p->map_res, residual_f16, hf, 2, n1, rows, 64, 32, sw);
+  if (rc == P3_OK) rc = tc_make_map_2d(&p->map_raw, raw_f16, hf, 2, n1, rows, 64, 32, sw);
+  if (rc == P3_OK) rc = tc_make_map_2d(&p->map_out2, out2, bf, 2, n2, rows, 64, 32, sw);
+  if (rc == P3_OK) {
+    cudaError_t e = cudaFuncSetAttribute(tc_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBudget);
+    if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+  }
+  if (rc != P3_OK) {
+    delete p;
+    return rc;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int max_pairs = sms / 2;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+    cfg.blockDim = dim3(kChThreads);
+    cfg.dynamicSmemBytes = p->smem_bytes;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, tc_chain_pair_kernel, &cfg) == cudaSuccess && n_clusters > 0)
+      max_pairs = std::min(max_pairs, n_clusters);
+    else
+      cudaGetLastError();
+  }
+  const int m_tiles = (rows + 255) / 256;
+  p->grid = 2 * std::max(1, std::min(max_pairs, m_tiles));
+  if (std::getenv("P3_TC_TRACE")) {
+    cudaMalloc(&p->trace, 16 * sizeof(unsigned long long));
+    cudaMemset(p->trace, 0, 16 * sizeof(unsigned long long));
+  }
+  *out = p;
+  return P3_OK;
+}
+
+void tc_chain_plan_destroy(TcChainPlan* p) {
+  if (p && p->trace) {
+    unsigned long long h[16];
+    cudaMemcpy(h, p->trace, sizeof h, cudaMemcpyDeviceToHost);
+    if (h[10] && h[12] && h[14])
+      std::fprintf(stderr, "[p3 trace] chain %d->%d->%d epi1 cycles/step: res_wait %llu  tmem_ld %llu  math %llu  a2_empty %llu  out_empty %llu  "
+                           "sts+fence %llu  arrive %llu  (unused %llu) | per tile: acc1 wait %llu  acc2 wait %llu  epi2 %llu | "
+                           "per launch: loop %llu cycles, %llu tiles\n",
+                   p->k1, p->n1, p->n2, h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
+                   h[6] / h[10], h[7] / h[10], h[8] / h[12], h[9] / h[12], h[11] / h[12], h[13] / h[14], h[12] / h[14]);
+    cudaFree(p->trace);
+  }
+  delete p;
+}
+
+int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
+  tc_chain_pair_kernel<<<p->grid, kChThreads, p->smem_bytes, stream>>>(
+      p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw, p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages,
+      p->tmem_cols, p->scale1, p->shift1, p->scale2, p->shift2, p->act2_mode, p->trace);
+  P3_CUDA(cudaGetLastError());
+  return P3_OK;
+}
+
+}  // namespace p3

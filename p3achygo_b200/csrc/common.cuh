@@ -78,6 +78,16 @@ void tc_conv_plan_destroy(TcConvPlan* plan);
 int tc_conv_launch(const TcConvPlan* plan, cudaStream_t stream);
 bool tc_conv_supported(int cin, int cout);
 
+// fused block boundary (chain_tc.cu): x' = x + W1*in ; u = mish(BN1(x')) ; out2 = act2(W2*u), all on one CTA pair.
+// in [rows, k1] bf16, w1 [n1][k1] bf16, w2 [n2][n1] bf16, residual / raw [rows, n1] fp16 (may alias), out2 [rows, n2] bf16.
+struct TcChainPlan;
+bool tc_chain_supported(int k1, int n1, int n2);
+int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
+                         int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out);
+void tc_chain_plan_destroy(TcChainPlan* p);
+int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
+
 // ---- encode (encode.cu) --------------------------------------------------------------------------
 // feats: device copy of p3_go_features[n]. planes [n,361,P] fp32, scalars [n,S] fp32,
 // masks [n,361] uint16 (bit ch set <=> planes[...,ch] == 1).

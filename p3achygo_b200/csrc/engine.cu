@@ -101,7 +101,7 @@ struct ConvLayer {
   ~ConvLayer() { if (plan) tc_conv_plan_destroy(plan); }
 };
 
-enum StepKind { kStepConv, kStepBroadcast };
+enum StepKind { kStepConv, kStepBroadcast, kStepChain };
 struct Step {
   StepKind kind = kStepConv;
   ConvLayer* layer = nullptr;
@@ -114,6 +114,9 @@ struct Step {
   const float* b_scale = nullptr;
   const float* b_shift = nullptr;
   TcBcastPlan* bplan = nullptr;  // tcgen05 broadcast mix (bf16 mode)
+  // fused block boundary (bf16 mode): `layer` = the block's expand conv, `layer2` = the next block's reduce conv
+  ConvLayer* layer2 = nullptr;
+  TcChainPlan* cplan = nullptr;
 };
 
 }  // namespace
@@ -158,7 +161,10 @@ struct p3_engine {
   bool aux_host_valid = false;
 
   ~p3_engine() {
-    for (Step& s : program) if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
+    for (Step& s : program) {
+      if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
+      if (s.cplan) tc_chain_plan_destroy(s.cplan);
+    }
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -207,6 +213,7 @@ struct p3_engine {
     if (rc) return rc;
     for (const Step& s : program) {
       if (s.kind == kStepConv) rc = run_conv(s);
+      else if (s.kind == kStepChain) rc = tc_chain_launch(s.cplan, stream);
       else rc = run_broadcast(s);
       if (rc) return rc;
     }
@@ -471,6 +478,9 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     e.program.push_back(s);
     return P3_OK;
   };
+  void* chain_out = nullptr;  // set when the previous block ended with a fused boundary
+  const char* env_chain = std::getenv("P3_TC_CHAIN");
+  const bool chain_enabled = !(env_chain && std::atoi(env_chain) == 0);
   for (int i = 0; i < e.blocks; ++i) {
     BlockDesc& bk = blocks[i];
     const bool last_block = i == e.blocks - 1;
@@ -502,12 +512,37 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       void* s0 = e.actS0.p;
       void* s1 = e.actS1.p;
       const int nc = static_cast<int>(bk.convs.size());
-      if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, s0, kActMishBN, bk.convs[1]))) return rc;
+      if (chain_out) {  // the previous block's fused boundary already ran this block's reduce conv into chain_out
+        if (chain_out == s1) std::swap(s0, s1);
+        chain_out = nullptr;
+      } else if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, s0, kActMishBN, bk.convs[1]))) {
+        return rc;
+      }
       for (int j = 1; j < nc - 1; ++j) {
         if ((rc = add_conv(bk.convs[j], s0, nullptr, nullptr, s1, kActMishBN, bk.convs[j + 1]))) return rc;
         std::swap(s0, s1);
       }
-      if ((rc = add_conv(bk.convs[nc - 1], s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
+      // block boundary btl -> btl: expand + residual + next block's reduce as ONE launch (chain_tc.cu)
+      ConvLayer* ex = bk.convs[nc - 1];
+      ConvLayer* nr = (!last_block && !blocks[i + 1].bcast) ? blocks[i + 1].convs[0] : nullptr;
+      if (e.bf16 && chain_enabled && nr && blocks[i + 1].convs.size() >= 2 && ex->taps == 1 && nr->taps == 1 &&
+          tc_chain_supported(ex->cin, ex->cout, nr->cout)) {
+        Step s;
+        s.kind = kStepChain;
+        s.layer = ex;
+        s.layer2 = nr;
+        s.in = s0;
+        const ConvLayer* n2 = blocks[i + 1].convs[1];
+        if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(s0), ex->w_bf16.as<__nv_bfloat16>(),
+                                       nr->w_bf16.as<__nv_bfloat16>(), e.rows, ex->cin, ex->cout, nr->cout, e.xraw.p, e.xraw.p,
+                                       nr->in_scale.as<float>(), nr->in_shift.as<float>(), s1, n2->in_scale.as<float>(),
+                                       n2->in_shift.as<float>(), kActMishBN, &s.cplan)))
+          return rc;
+        e.program.push_back(s);
+        chain_out = s1;
+      } else if ((rc = add_conv(ex, s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) {
+        return rc;
+      }
     } else {  // ClassicResidualBlock, model.py:330-354
       if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMishBN, bk.convs[1]))) return rc;
       // second conv reads `other`; `cur` is free again and becomes the block output
@@ -770,6 +805,10 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
       rc = e->run_conv(s);
       cls.push_back(s.layer->taps == 1 ? 2 : 3);
       fl.push_back(2.0 * s.layer->taps * double(s.layer->cin) * s.layer->cout * Pn * B);
+    } else if (s.kind == kStepChain) {
+      rc = tc_chain_launch(s.cplan, e->stream);
+      cls.push_back(2);
+      fl.push_back(2.0 * (double(s.layer->cin) * s.layer->cout + double(s.layer2->cin) * s.layer2->cout) * Pn * B);
     } else {
       rc = e->run_broadcast(s);
       cls.push_back(4); fl.push_back(2.0 * e->C * Pn * Pn * B);
@@ -792,7 +831,10 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
     flops[cls[i]] += fl[i];
     if (std::getenv("P3_PROFILE_VERBOSE")) {  // per-launch listing (perf work)
       const Step* st = (i >= 2 && i - 2 < e->program.size()) ? &e->program[i - 2] : nullptr;
-      if (st && st->kind == kStepConv)
+      if (st && st->kind == kStepChain)
+        std::fprintf(stderr, "[p3 profile] #%zu class %d chain %d -> %d (+res) -> %d: %.1f us\n", i, cls[i], st->layer->cin,
+                     st->layer->cout, st->layer2->cout, t * 1e3f);
+      else if (st && st->kind == kStepConv)
         std::fprintf(stderr, "[p3 profile] #%zu class %d conv taps=%d cin=%d cout=%d res=%d raw=%d act=%d: %.1f us\n", i, cls[i],
                      st->layer->taps, st->layer->cin, st->layer->cout, st->ep.residual != nullptr, st->ep.raw_out != nullptr,
                      st->ep.act_out != nullptr, t * 1e3f);

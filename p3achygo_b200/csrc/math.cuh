@@ -34,6 +34,20 @@ __device__ __forceinline__ float mish_f32(float x) {
   }
 }
 
+// Two fast mishes sharing ONE reciprocal: 1/d1 = d2 / (d1 d2), 1/d2 = d1 / (d1 d2).  The SFU (16 lanes / clk / SM) is the
+// scarce unit in the conv epilogues (2 MUFU ops per element above); this form needs 1.5.  d = n + 2 is in [2, e^40 + 2],
+// so d1 * d2 <= 5.6e34 stays finite.
+// tanh(softplus(x)) = n / (n + 2) = 1 - 2 / d with d = e^x (e^x + 2) + 2, so mish(x) = x - 2 x / d (absolute error of the
+// 1 - 2/d cancellation is ~1e-7 |x|, irrelevant next to the bf16 rounding of the result).
+__device__ __forceinline__ void mish2_f32(float x1, float x2, float& y1, float& y2) {
+  const float e1 = ex2_approx_ftz(fminf(x1, 20.0f) * 1.4426950408889634f);
+  const float e2 = ex2_approx_ftz(fminf(x2, 20.0f) * 1.4426950408889634f);
+  const float d1 = fmaf(e1, e1 + 2.0f, 2.0f), d2 = fmaf(e2, e2 + 2.0f, 2.0f);
+  const float r = rcp_approx_ftz(d1 * d2);
+  y1 = fmaf(-2.0f * x1, d2 * r, x1);
+  y2 = fmaf(-2.0f * x2, d1 * r, x2);
+}
+
 __device__ __forceinline__ float softplus_f32(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f32(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -202,6 +202,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // arrive on a (possibly remote) barrier
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same, default semantics (release at CTA scope) on a shared::cluster address: what CUTLASS' ClusterBarrier::arrive(cta_id)
+// emits.  The .release.cluster form above compiles to MEMBAR.ALL.GPU + CGAERRBAR in front of the arrive; use this one when
+// the data being published was already made visible by other means (tcgen05 fences, fence.proxy.async + a local barrier).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // waits for remote arrivals too
   uint32_t done = 0;
   while (!done) {
