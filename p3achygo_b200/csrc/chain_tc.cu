@@ -33,8 +33,9 @@ constexpr int kChEpiWarps = 16;
 constexpr int kChThreads = (2 + kChEpiWarps + 4) * 32;  // 704: producer, MMA, 16 epilogue, 4 I/O (one per TMEM lane quarter)
 constexpr int kChSlabBytes = 128 * 128;   // 128 rows x 64 bf16 (one K slab of an A operand)
 constexpr int kChBoxBytes = 32 * 128;     // a quarter's 32 rows x 64 two-byte elements
-constexpr int kChResBufs = 2;
-constexpr int kChOutBufs = 3;
+// A quarter cycles through a pool of kChBoxes staging boxes: TMA load of the residual -> the quarter's 4 warps replace it IN
+// PLACE by x' (or write an epi2 output box) -> TMA store -> free.  Loads are issued kChBoxes - 1 steps ahead of their use.
+constexpr int kChBoxes = 5;
 constexpr int kChMaxN = 256;
 constexpr int kChSmemBudget = 227 * 1024;
 
@@ -51,22 +52,41 @@ namespace {
 
 __host__ __device__ constexpr int chain_fixed_smem(int k1, int n1, int n2) {
   return (k1 / 64) * (n1 / 2) * 128 + (n1 / 64) * (n2 / 2) * 128 + (k1 / 64) * kChSlabBytes + 2 * kChSlabBytes +
-         4 * (kChResBufs + kChOutBufs) * kChBoxBytes;
+         4 * kChBoxes * kChBoxBytes;
 }
 constexpr int kChBarRegion = 512;
 constexpr int kChBarBytes = kChBarRegion + 4 * kChMaxN * 4;
 
-// 16 activations: a[i] = mish(x[i] * scale[col0 + i] + shift[col0 + i]), scale / shift in shared memory
-__device__ __forceinline__ void bn_mish16(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
+// 8 activations a[i] = mish(t[i]), t = (x * scale + shift), with the constants pre-multiplied by log2(e): z = t log2(e) comes
+// straight out of the BN FFMA, e^t = ex2(z), and mish(t) = t (1 - 2/d) = z * (ln2 - 2 ln2 / d), d = e^t (e^t + 2) + 2.  Pairs
+// share one reciprocal (1/d0 = d1 / (d0 d1)).  Written phase by phase over the 8 values so that the 8 dependency chains are
+// interleaved (the SFU latency of one is covered by the others) instead of running back to back.
+__device__ __forceinline__ void bn_mish8(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
+  const float4 s0 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0) * 4u), s1 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0 + 4) * 4u);
+  const float4 h0 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0) * 4u), h1 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0 + 4) * 4u);
+  const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  float z[8], d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scv[i], shv[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = ex2_approx_ftz(fminf(z[i], 28.853900817779268f));  // e^t, t clamped to 20
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = fmaf(d[i], d[i] + 2.0f, 2.0f);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 s4 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0 + 4 * i) * 4u);
-    const float4 h4 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0 + 4 * i) * 4u);
-    mish2_f32(fmaf(x[4 * i], s4.x, h4.x), fmaf(x[4 * i + 1], s4.y, h4.y), a[4 * i], a[4 * i + 1]);
-    mish2_f32(fmaf(x[4 * i + 2], s4.z, h4.z), fmaf(x[4 * i + 3], s4.w, h4.w), a[4 * i + 2], a[4 * i + 3]);
+    const float r = rcp_approx_ftz(d[2 * i] * d[2 * i + 1]);
+    const float q0 = d[2 * i + 1] * r, q1 = d[2 * i] * r;  // 1/d0, 1/d1
+    a[2 * i] = z[2 * i] * fmaf(q0, -1.3862943611198906f, 0.6931471805599453f);
+    a[2 * i + 1] = z[2 * i + 1] * fmaf(q1, -1.3862943611198906f, 0.6931471805599453f);
   }
 }
+__device__ __forceinline__ void bn_mish16(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
+  bn_mish8(x, a, sc, sh, col0);
+  bn_mish8(x + 8, a + 8, sc, sh, col0 + 8);
+}
 
+template <bool kTrace>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChThreads, 1)
 tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_w1,
                      const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -83,9 +103,8 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   uint8_t* smem_w2 = smem_w1 + w1_bytes;
   uint8_t* smem_a1 = smem_w2 + w2_bytes;
   uint8_t* smem_a2 = smem_a1 + k1_slabs * kChSlabBytes;
-  uint8_t* smem_res = smem_a2 + 2 * kChSlabBytes;
-  uint8_t* smem_out = smem_res + 4 * kChResBufs * kChBoxBytes;
-  uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem_out + 4 * kChOutBufs * kChBoxBytes);
+  uint8_t* smem_box = smem_a2 + 2 * kChSlabBytes;  // [4 quarters][kChBoxes] staging boxes
+  uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem_box + 4 * kChBoxes * kChBoxBytes);
   uint64_t* a1_empty = a1_full + 4;
   uint64_t* acc1_full = a1_empty + 4;
   uint64_t* acc1_empty = acc1_full + 1;
@@ -94,11 +113,9 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   uint64_t* acc2_full = a2_empty + 2;
   uint64_t* acc2_empty = acc2_full + 2;
   uint64_t* w_bar = acc2_empty + 2;
-  uint64_t* res_full = w_bar + 1;                      // [4 quarters][kChResBufs]  TMA load landed
-  uint64_t* res_empty = res_full + 4 * kChResBufs;     //                            the quarter's 4 warps have read it
-  uint64_t* out_full = res_empty + 4 * kChResBufs;     // [4 quarters][kChOutBufs]  the quarter's 4 warps have written it
-  uint64_t* out_empty = out_full + 4 * kChOutBufs;     //                            the TMA store has read it
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_empty + 4 * kChOutBufs);
+  uint64_t* box_ready = w_bar + 1;                     // [4 quarters][kChBoxes] residual landed / box free for an epi2 output
+  uint64_t* box_written = box_ready + 4 * kChBoxes;    //                        the quarter's 4 warps have written the box
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(box_written + 4 * kChBoxes);
   float* s_scale1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a1_full) + kChBarRegion);
   float* s_shift1 = s_scale1 + kChMaxN;
   float* s_scale2 = s_shift1 + kChMaxN;
@@ -111,13 +128,14 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   const int n_it = pair < m_tiles ? (m_tiles - pair + n_pairs - 1) / n_pairs : 0;  // tiles of this pair
   const int defer = acc2_stages >= 2 ? 1 : 0;  // epi2 runs one tile behind epi1 (needs the second acc2 stage)
 
+  constexpr float kLog2e = 1.4426950408889634f;  // folded BN constants, pre-multiplied by log2(e) (see bn_mish8)
   for (int c = threadIdx.x; c < n1; c += blockDim.x) {
-    s_scale1[c] = scale1[c];
-    s_shift1[c] = shift1[c];
+    s_scale1[c] = scale1[c] * kLog2e;
+    s_shift1[c] = shift1[c] * kLog2e;
   }
   for (int c = threadIdx.x; c < n2; c += blockDim.x) {
-    s_scale2[c] = act2_mode == kActMishBN ? scale2[c] : 1.0f;
-    s_shift2[c] = act2_mode == kActMishBN ? shift2[c] : 0.0f;
+    s_scale2[c] = (act2_mode == kActMishBN ? scale2[c] : 1.0f) * kLog2e;
+    s_shift2[c] = (act2_mode == kActMishBN ? shift2[c] : 0.0f) * kLog2e;
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a1);
@@ -139,13 +157,9 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       ptx::mbar_init(&acc2_empty[s], 2 * kChEpiWarps);
     }
     ptx::mbar_init(w_bar, 1);
-    for (int s = 0; s < 4 * kChResBufs; ++s) {
-      ptx::mbar_init(&res_full[s], 1);
-      ptx::mbar_init(&res_empty[s], 4);
-    }
-    for (int s = 0; s < 4 * kChOutBufs; ++s) {
-      ptx::mbar_init(&out_full[s], 4);
-      ptx::mbar_init(&out_empty[s], 1);
+    for (int s = 0; s < 4 * kChBoxes; ++s) {
+      ptx::mbar_init(&box_ready[s], 1);
+      ptx::mbar_init(&box_written[s], 4);
     }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
@@ -197,10 +211,9 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       ptx::tc_fence_after_sync();
       int stage = 0;
       uint32_t phase = 0, g = 0;
-      int it = 0;
-      for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
-        // ---- GEMM1: acc1 = A1 * W1^T
-        ptx::mbar_wait_cluster(acc1_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);
+      // GEMM1 of tile `t`: acc1 = A1 * W1^T (acc1 must have been drained by epi1 of tile t - 1)
+      auto gemm1 = [&](int t) {
+        ptx::mbar_wait_cluster(acc1_empty, (static_cast<uint32_t>(t) & 1u) ^ 1u);
         ptx::tc_fence_after_sync();
         for (int ks = 0; ks < k1_slabs; ++ks) {
           ptx::mbar_wait_cluster(&a1_full[stage], phase);
@@ -222,12 +235,18 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         }
         if (ptx::elect_one()) ptx::umma_commit_pair(acc1_full);
         __syncwarp();
-        // ---- GEMM2: acc2 = u * W2^T, one K slab of u at a time as the epilogue publishes it
+      };
+      if (n_it > 0) gemm1(0);
+      for (int it = 0; it < n_it; ++it) {
+        // ---- GEMM2: acc2 = u * W2^T, one K slab of u at a time as the epilogue publishes it.  GEMM1 of the NEXT tile goes in
+        // front of the last slab: acc1 is free as soon as epi1 has loaded its last columns (start of its last step), so the next
+        // accumulator is ready before the epilogue gets to it.
         const int as = it % acc2_stages;
         ptx::mbar_wait_cluster(&acc2_empty[as], ((static_cast<uint32_t>(it / acc2_stages)) & 1u) ^ 1u);
         ptx::tc_fence_after_sync();
         const uint32_t tmem_d2 = tmem_base + static_cast<uint32_t>(n1 + as * n2);
         for (int j = 0; j < n1_slabs; ++j, ++g) {
+          if (j == n1_slabs - 1 && it + 1 < n_it) gemm1(it + 1);
           const uint32_t slot = g & 1u;
           ptx::mbar_wait_cluster(&a2_full[slot], (g >> 1) & 1u);
           ptx::tc_fence_after_sync();
@@ -252,63 +271,68 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     //   residual box read by the 4 warps -> refill it 2 steps ahead ; x' box written -> TMA store, publish the A2 slab to
     //   the leader's MMA warp ; the store issued one step earlier has read its box -> hand the box back.
     const int q = warp - (2 + kChEpiWarps);
-    uint64_t* my_res_full = res_full + kChResBufs * q;
-    uint64_t* my_res_empty = res_empty + kChResBufs * q;
-    uint64_t* my_out_full = out_full + kChOutBufs * q;
-    uint64_t* my_out_empty = out_empty + kChOutBufs * q;
+    uint64_t* my_ready = box_ready + kChBoxes * q;
+    uint64_t* my_written = box_written + kChBoxes * q;
     const uint32_t a2_full_l = ptx::mapa_shared(ptx::smem_u32(a2_full), 0);
-    uint8_t* my_res = smem_res + q * kChResBufs * kChBoxBytes;
-    const uint32_t my_out = ptx::smem_u32(smem_out) + static_cast<uint32_t>(q) * (kChOutBufs * kChBoxBytes);
+    uint8_t* my_box = smem_box + q * kChBoxes * kChBoxBytes;
     const int q_row = static_cast<int>(rank) * 128 + q * 32;
-    // residual box of epi1 step s (s counts 64-column slabs over all of this pair's tiles)
-    auto issue_res = [&](uint32_t s) {
-      const int it_s = static_cast<int>(s / static_cast<uint32_t>(n1_slabs)), j_s = static_cast<int>(s % static_cast<uint32_t>(n1_slabs));
-      const int mt_s = pair + it_s * n_pairs;
-      if (mt_s >= m_tiles) return;
-      const uint32_t b = s & 1u;
-      ptx::mbar_arrive_expect_tx(&my_res_full[b], kChBoxBytes);
-      ptx::tma_load_2d(my_res + b * kChBoxBytes, &map_res, &my_res_full[b], j_s * 64, mt_s * 256 + q_row);
+    // The quarter's step sequence (the epilogue warps walk the same one): per iteration `it`, the n1_slabs epi1 steps of
+    // tile it, then the n2_slabs epi2 steps of tile it - defer.  `ahead` runs kChBoxes - 1 steps in front of `cur`
+    // (the box of step cur - 1, just read by its store, serves step cur + kChBoxes - 1).
+    struct Cursor {
+      int it, idx;   // iteration, index within the iteration's steps
+      uint32_t s;    // step ordinal (box = s % kChBoxes)
     };
-    if (lane == 0) {
-      issue_res(0);
-      issue_res(1);
+    auto steps_in = [&](int it) { return (it < n_it ? n1_slabs : 0) + ((it - defer >= 0 && it - defer < n_it) ? n2_slabs : 0); };
+    auto advance = [&](Cursor& c) {
+      ++c.s;
+      if (++c.idx >= steps_in(c.it)) {
+        c.idx = 0;
+        ++c.it;
+      }
+    };
+    const int n_iter = n_it + defer;
+    // make box s % kChBoxes ready for step c: TMA-load the residual (epi1 step) or just hand the free box over (epi2 step)
+    auto prepare = [&](const Cursor& c) {
+      if (c.it >= n_iter) return;
+      const uint32_t b = c.s % kChBoxes;
+      const bool is_epi1 = c.it < n_it && c.idx < n1_slabs;
+      if (is_epi1) {
+        ptx::mbar_arrive_expect_tx(&my_ready[b], kChBoxBytes);
+        ptx::tma_load_2d(my_box + b * kChBoxBytes, &map_res, &my_ready[b], c.idx * 64, (pair + c.it * n_pairs) * 256 + q_row);
+      } else {
+        ptx::mbar_arrive(&my_ready[b]);
+      }
+    };
+    Cursor cur{0, 0, 0}, ahead{0, 0, 0};
+    if (n_it > 0) {
+      for (int i = 0; i < kChBoxes; ++i) {  // all boxes start out free
+        if (lane == 0) prepare(ahead);
+        advance(ahead);
+      }
     }
-    uint32_t so = 0, sr = 0, g = 0;
-    // step order per quarter (the epilogue warps follow the same one): epi1(0), [epi1(it), epi2(it - 1)]..., epi2(last)
-    // when acc2 is double-buffered (`defer`), else epi1(it), epi2(it)
-    for (int it = 0; it < n_it + defer; ++it) {
-      if (it < n_it) {
-        const int row0 = (pair + it * n_pairs) * 256 + q_row;
-        for (int j = 0; j < n1_slabs; ++j, ++sr, ++so, ++g) {
-          ptx::mbar_wait(&my_res_empty[sr & 1u], (sr >> 1) & 1u);
-          if (lane == 0) issue_res(sr + 2);
-          const uint32_t ob = so % kChOutBufs;
-          ptx::mbar_wait(&my_out_full[ob], (so / kChOutBufs) & 1u);
-          if (lane == 0) {
-            ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
-            ptx::tma_store_2d(&map_raw, nullptr, 0, 0, my_out + ob * kChBoxBytes, j * 64, row0);
-            ptx::bulk_commit();
-            ptx::bulk_wait_read<1>();
-            if (so > 0) ptx::mbar_arrive(&my_out_empty[(so - 1) % kChOutBufs]);
-          }
-          __syncwarp();
+    uint32_t g = 0;
+    while (cur.it < n_iter) {
+      const uint32_t b = cur.s % kChBoxes;
+      const bool is_epi1 = cur.it < n_it && cur.idx < n1_slabs;
+      ptx::mbar_wait(&my_written[b], (cur.s / kChBoxes) & 1u);
+      if (lane == 0) {
+        if (is_epi1) {
+          ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
+          ptx::tma_store_2d(&map_raw, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
+                            (pair + cur.it * n_pairs) * 256 + q_row);
+        } else {
+          ptx::tma_store_2d(&map_out2, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, (cur.idx - (cur.it < n_it ? n1_slabs : 0)) * 64,
+                            (pair + (cur.it - defer) * n_pairs) * 256 + q_row);
         }
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<1>();  // the previous step's store has read its box: that box serves the step kChBoxes - 1 ahead
+        if (cur.s > 0) prepare(ahead);
       }
-      const int it2 = it - defer;
-      if (it2 >= 0 && it2 < n_it) {
-        const int row0 = (pair + it2 * n_pairs) * 256 + q_row;
-        for (int b = 0; b < n2_slabs; ++b, ++so) {
-          const uint32_t ob = so % kChOutBufs;
-          ptx::mbar_wait(&my_out_full[ob], (so / kChOutBufs) & 1u);
-          if (lane == 0) {
-            ptx::tma_store_2d(&map_out2, nullptr, 0, 0, my_out + ob * kChBoxBytes, b * 64, row0);
-            ptx::bulk_commit();
-            ptx::bulk_wait_read<1>();
-            ptx::mbar_arrive(&my_out_empty[(so - 1) % kChOutBufs]);
-          }
-          __syncwarp();
-        }
-      }
+      if (is_epi1) ++g;
+      if (cur.s > 0) advance(ahead);
+      advance(cur);
+      __syncwarp();
     }
     if (lane == 0) ptx::bulk_wait_all();
   } else {
@@ -321,23 +345,21 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     const uint32_t ch0 = ((2u * cg) ^ sw) << 4, ch1 = ((2u * cg + 1u) ^ sw) << 4;
     const uint32_t box_row = static_cast<uint32_t>(lane) * 128u;
     const uint32_t slab_row = static_cast<uint32_t>(q * 32 + lane) * 128u;
-    const uint32_t res_base = ptx::smem_u32(smem_res) + static_cast<uint32_t>(q) * (kChResBufs * kChBoxBytes);
-    const uint32_t out_base = ptx::smem_u32(smem_out) + static_cast<uint32_t>(q) * (kChOutBufs * kChBoxBytes);
+    const uint32_t box_base = ptx::smem_u32(smem_box) + static_cast<uint32_t>(q) * (kChBoxes * kChBoxBytes) + box_row;
     const uint32_t a2_base = ptx::smem_u32(smem_a2);
-    uint64_t* my_res_full = res_full + kChResBufs * q;
-    uint64_t* my_res_empty = res_empty + kChResBufs * q;
-    uint64_t* my_out_full = out_full + kChOutBufs * q;
-    uint64_t* my_out_empty = out_empty + kChOutBufs * q;
+    uint64_t* my_ready = box_ready + kChBoxes * q;
+    uint64_t* my_written = box_written + kChBoxes * q;
     const uint32_t acc1_empty_l = ptx::mapa_shared(ptx::smem_u32(acc1_empty), 0);
     const uint32_t acc2_empty_l = ptx::mapa_shared(ptx::smem_u32(acc2_empty), 0);
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sc1 = ptx::smem_u32(s_scale1), sh1 = ptx::smem_u32(s_shift1);
     const uint32_t sc2 = ptx::smem_u32(s_scale2), sh2 = ptx::smem_u32(s_shift2);
 
-    uint32_t so = 0, sr = 0, g = 0;  // output-box, residual-box and A2-slab ordinals of this quarter
+    uint32_t so = 0, g = 0;  // step (staging box) and A2-slab ordinals of this quarter
     int it = 0;
+
     // P3_TC_TRACE: per-phase clock64 sums of one epilogue thread (perf experiments)
-    const bool tr = trace != nullptr && blockIdx.x == 3 && ew == 0 && lane == 0;
+    const bool tr = kTrace && trace != nullptr && blockIdx.x == 3 && ew == 0 && lane == 0;
     uint32_t ts[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_loop = tr ? clock64() : 0;
     for (it = 0; it < n_it + defer; ++it) {
@@ -348,17 +370,17 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::mbar_wait(acc1_full, static_cast<uint32_t>(it) & 1u);
         ptx::tc_fence_after_sync();
         if (tr) ts[8] += static_cast<uint32_t>(clock64() - tc0);
-        for (int j = 0; j < n1_slabs; ++j, ++sr, ++so, ++g) {
+        for (int j = 0; j < n1_slabs; ++j, ++so, ++g) {
           const int col = j * 64 + cg * 16;
           uint32_t v[16];
           long long t[8];
           if (tr) t[0] = clock64();
           ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(col), v);
-          const uint32_t rb = sr & 1u;
-          ptx::mbar_wait(&my_res_full[rb], (sr >> 1) & 1u);
+          const uint32_t ob = so % kChBoxes;
+          ptx::mbar_wait(&my_ready[ob], (so / kChBoxes) & 1u);
           if (tr) t[1] = clock64();
-          const uint32_t rp = res_base + rb * kChBoxBytes + box_row;
-          const float4 t0 = ptx::lds_f4(rp + ch0), t1 = ptx::lds_f4(rp + ch1);
+          const uint32_t obuf = box_base + ob * kChBoxBytes;
+          const float4 t0 = ptx::lds_f4(obuf + ch0), t1 = ptx::lds_f4(obuf + ch1);
           float x[16];
           {
             const uint32_t u[8] = {__float_as_uint(t0.x), __float_as_uint(t0.y), __float_as_uint(t0.z), __float_as_uint(t0.w),
@@ -370,8 +392,6 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
               x[2 * i + 1] = f2.y;
             }
           }
-          __syncwarp();  // the warp's residual values are in registers: hand the box back to the I/O warp
-          if (lane == 0) ptx::mbar_arrive(&my_res_empty[rb]);
           ptx::tmem_ld_wait();
           if (tr) t[2] = clock64();
           if (j == n1_slabs - 1) {  // acc1 is in registers: hand it back to the MMA warp
@@ -387,15 +407,11 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           bn_mish16(x, a, sc1, sh1, col);
           const uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
           const uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
-          // A2 slot free: the MMAs that read its previous slab have completed; output box free: its previous store has read it
+          // A2 slot free: the MMAs that read its previous slab have completed.  x' replaces the residual in place.
           const uint32_t slot = g & 1u;
-          const uint32_t ob = so % kChOutBufs;
           if (tr) t[3] = clock64() + (p0.x & 0);
           ptx::mbar_wait(&a2_empty[slot], ((g >> 1) & 1u) ^ 1u);
-          if (tr) t[4] = clock64();
-          ptx::mbar_wait(&my_out_empty[ob], ((so / kChOutBufs) & 1u) ^ 1u);
-          if (tr) t[5] = clock64();
-          const uint32_t obuf = out_base + ob * kChBoxBytes + box_row;
+          if (tr) t[4] = t[5] = clock64();
           ptx::sts_u4(obuf + ch0, r0);
           ptx::sts_u4(obuf + ch1, r1);
           const uint32_t ap = a2_base + slot * kChSlabBytes + slab_row;
@@ -404,10 +420,10 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core / TMA engine
           if (tr) t[6] = clock64();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&my_out_full[ob]);
+          if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
           if (tr) {
             t[7] = clock64();
-            // 0 res wait  1 tmem ld wait  2 math  3 a2_empty wait  4 out_empty wait  5 sts + fence  6 arrive
+            // 0 box ready wait  1 tmem ld wait  2 math  3 a2_empty wait  4 -  5 sts + fence  6 arrive
 #pragma unroll
             for (int i = 0; i < 7; ++i) ts[i] += static_cast<uint32_t>(t[i + 1] - t[i]);
             ++ts[10];
@@ -449,14 +465,14 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
           uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
           if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
-          const uint32_t ob = so % kChOutBufs;
-          ptx::mbar_wait(&my_out_empty[ob], ((so / kChOutBufs) & 1u) ^ 1u);
-          const uint32_t obuf = out_base + ob * kChBoxBytes + box_row;
+          const uint32_t ob = so % kChBoxes;
+          ptx::mbar_wait(&my_ready[ob], (so / kChBoxes) & 1u);
+          const uint32_t obuf = box_base + ob * kChBoxBytes;
           ptx::sts_u4(obuf + ch0, p0);
           ptx::sts_u4(obuf + ch1, p1);
           ptx::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&my_out_full[ob]);
+          if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
         }
         if (tr) {
           ts[11] += static_cast<uint32_t>(clock64() - tc1);
@@ -517,7 +533,8 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
   if (rc == P3_OK) rc = tc_make_map_2d(&p->map_raw, raw_f16, hf, 2, n1, rows, 64, 32, sw);
   if (rc == P3_OK) rc = tc_make_map_2d(&p->map_out2, out2, bf, 2, n2, rows, 64, 32, sw);
   if (rc == P3_OK) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(tc_chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBudget);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBudget);
     if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
   }
   if (rc != P3_OK) {
@@ -534,7 +551,7 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
     cfg.blockDim = dim3(kChThreads);
     cfg.dynamicSmemBytes = p->smem_bytes;
     int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, tc_chain_pair_kernel, &cfg) == cudaSuccess && n_clusters > 0)
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, tc_chain_pair_kernel<false>, &cfg) == cudaSuccess && n_clusters > 0)
       max_pairs = std::min(max_pairs, n_clusters);
     else
       cudaGetLastError();
@@ -554,8 +571,8 @@ void tc_chain_plan_destroy(TcChainPlan* p) {
     unsigned long long h[16];
     cudaMemcpy(h, p->trace, sizeof h, cudaMemcpyDeviceToHost);
     if (h[10] && h[12] && h[14])
-      std::fprintf(stderr, "[p3 trace] chain %d->%d->%d epi1 cycles/step: res_wait %llu  tmem_ld %llu  math %llu  a2_empty %llu  out_empty %llu  "
-                           "sts+fence %llu  arrive %llu  (unused %llu) | per tile: acc1 wait %llu  acc2 wait %llu  epi2 %llu | "
+      std::fprintf(stderr, "[p3 trace] chain %d->%d->%d epi1 cycles/step: box_ready %llu  tmem_ld %llu  math %llu  a2_empty %llu  (-) %llu  "
+                           "sts+fence %llu  arrive %llu  (-) %llu | per tile: acc1 wait %llu  acc2 wait %llu  epi2 %llu | "
                            "per launch: loop %llu cycles, %llu tiles\n",
                    p->k1, p->n1, p->n2, h[0] / h[10], h[1] / h[10], h[2] / h[10], h[3] / h[10], h[4] / h[10], h[5] / h[10],
                    h[6] / h[10], h[7] / h[10], h[8] / h[12], h[9] / h[12], h[11] / h[12], h[13] / h[14], h[12] / h[14]);
@@ -565,7 +582,8 @@ void tc_chain_plan_destroy(TcChainPlan* p) {
 }
 
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
-  tc_chain_pair_kernel<<<p->grid, kChThreads, p->smem_bytes, stream>>>(
+  auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
+  kern<<<p->grid, kChThreads, p->smem_bytes, stream>>>(
       p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw, p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages,
       p->tmem_cols, p->scale1, p->shift1, p->scale2, p->shift2, p->act2_mode, p->trace);
   P3_CUDA(cudaGetLastError());

@@ -845,7 +845,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (last) {
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(empty_leader + 8u * static_cast<uint32_t>(acc));
+          if (lane == 0) ptx::mbar_arrive_remote(empty_leader + 8u * static_cast<uint32_t>(acc));
         }
         if (debug & 1) return;  // ablation: no epilogue math / stores
         uint4 pk[kW / 8];
