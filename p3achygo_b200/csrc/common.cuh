@@ -91,8 +91,18 @@ int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
 // ---- encode (encode.cu) --------------------------------------------------------------------------
 // feats: device copy of p3_go_features[n]. planes [n,361,P] fp32, scalars [n,S] fp32,
 // masks [n,361] uint16 (bit ch set <=> planes[...,ch] == 1).
+// Optional extra outputs for the tensor-core first layer (init_tc.cu): the plane masks in a zero-bordered 23 x 24 grid per
+// position (point (r, c) at (r + 2) * 24 + c + 2, so a 5x5 neighbourhood needs no bounds checks) and the game-state bias.
+constexpr int kMaskPadW = 24, kMaskPadH = 23, kMaskPadElems = kMaskPadW * kMaskPadH;  // 552 uint16 = 1104 B (16-byte multiple)
+struct EncodeExtra {
+  uint16_t* masks_padded = nullptr;  // [n][kMaskPadElems], borders pre-zeroed
+  const float* gs_w = nullptr;       // [S][C]
+  const float* gs_b = nullptr;       // [C]
+  int C = 0;
+  float* gs_out = nullptr;           // [n][C]
+};
 int encode_launch(const p3_go_features* feats, int n, int version, float* planes, float* scalars,
-                  uint16_t* masks, cudaStream_t stream);
+                  uint16_t* masks, cudaStream_t stream, const EncodeExtra* extra = nullptr);
 int liberties_launch(const int8_t* boards, int n, int8_t* out, cudaStream_t stream);
 int legal_mask_launch(const int8_t* boards, const int8_t* colors, const int8_t* forbidden, int n,
                       uint8_t* out, cudaStream_t stream);
@@ -109,6 +119,14 @@ bool init_conv_smem_supported(int nplanes, int C);
 int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, int nplanes, int nscalars, int C,
                           const __nv_bfloat16* wt_bf16, const float* gs_w, const float* gs_b, __half* raw_out,
                           __nv_bfloat16* act_out, const float* scale, const float* shift, cudaStream_t stream);
+
+// bf16-mode tensor-core variant (init_tc.cu): implicit GEMM over the plane masks, weights repacked by init_tc_pack_weights.
+bool init_tc_supported(int nplanes, int nscalars, int C);
+struct InitTcPlan;
+int init_tc_plan_create(const uint16_t* masks_padded, const float* gs, int n, int C, const __nv_bfloat16* w_packed,
+                        __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTcPlan** out);
+void init_tc_plan_destroy(InitTcPlan* p);
+int init_tc_launch(const InitTcPlan* p, cudaStream_t stream);
 
 // ---- broadcast mix (broadcast.cu) -------------------------------------------------------------------
 // y[b,q,c] = sum_p W[p,q] * x[b,p,c] + bias[q], then act = mish(BN(y)); x, act in the operand type.

@@ -20,9 +20,10 @@ static_assert(sizeof(p3_infer_result) == 7568, "p3_infer_result must mirror nn::
 
 __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __restrict__ feats, int n, int version,
                                                      float* __restrict__ planes, float* __restrict__ scalars,
-                                                     uint16_t* __restrict__ masks) {
+                                                     uint16_t* __restrict__ masks, EncodeExtra ex) {
   __shared__ uint32_t s_raw[kFeatWords];
   __shared__ uint16_t s_mask[P3_NUM_BOARD_LOCS];
+  __shared__ float s_scal[P3_NUM_SCALARS_V1];
   const int b = blockIdx.x;
   if (b >= n) return;
   const int np = version == 0 ? P3_NUM_PLANES_V0 : P3_NUM_PLANES_V1;
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __res
     }
     s_mask[p] = static_cast<uint16_t>(m);
     if (masks) masks[static_cast<size_t>(b) * P3_NUM_BOARD_LOCS + p] = static_cast<uint16_t>(m);
+    if (ex.masks_padded)  // zero-bordered 23 x 24 grid (the borders are zeroed once by the owner of the buffer)
+      ex.masks_padded[static_cast<size_t>(b) * kMaskPadElems + (i + 2) * kMaskPadW + (j + 2)] = static_cast<uint16_t>(m);
   }
   __syncthreads();
 
@@ -83,6 +86,15 @@ __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __res
       v = __fdiv_rn(__fmul_rn(color == P3_BLACK ? -1.0f : 1.0f, f.komi), 15.0f);
     }
     scalars[static_cast<size_t>(b) * ns + s] = v;
+    s_scal[s] = v;
+  }
+  if (ex.gs_out) {  // game-state dense of the tower's first layer (python/model.py:1234-1237): [C] bias of this position
+    __syncthreads();
+    for (int c = threadIdx.x; c < ex.C; c += blockDim.x) {
+      float acc = ex.gs_b[c];
+      for (int s = 0; s < ns; ++s) acc = fmaf(s_scal[s], ex.gs_w[s * ex.C + c], acc);
+      ex.gs_out[static_cast<size_t>(b) * ex.C + c] = acc;
+    }
   }
 }
 
@@ -200,9 +212,9 @@ __global__ void __launch_bounds__(384) legal_kernel(const int8_t* __restrict__ b
 }  // namespace
 
 int encode_launch(const p3_go_features* feats, int n, int version, float* planes, float* scalars, uint16_t* masks,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const EncodeExtra* extra) {
   if (n <= 0) return P3_OK;
-  encode_kernel<<<n, 256, 0, stream>>>(feats, n, version, planes, scalars, masks);
+  encode_kernel<<<n, 256, 0, stream>>>(feats, n, version, planes, scalars, masks, extra ? *extra : EncodeExtra());
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

@@ -20,6 +20,7 @@
 #include "weights_file.h"
 
 namespace p3 {
+int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out);  // init_tc.cu
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -144,6 +145,10 @@ struct p3_engine {
   // weights
   DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
   bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
+  bool init_tc = false;    // init conv as a tcgen05 implicit GEMM over the plane masks (init_tc.cu)
+  DevBuf init_wt_tc, d_masks_pad, d_gs;
+  InitTcPlan* init_plan = nullptr;
+  EncodeExtra enc_extra;
   std::vector<std::unique_ptr<ConvLayer>> layers;
   std::vector<DevBuf*> owned;
   std::vector<std::unique_ptr<DevBuf>> misc;
@@ -165,6 +170,7 @@ struct p3_engine {
       if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
       if (s.cplan) tc_chain_plan_destroy(s.cplan);
     }
+    if (init_plan) init_tc_plan_destroy(init_plan);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -188,6 +194,7 @@ struct p3_engine {
   }
 
   int run_init() {
+    if (init_tc) return init_tc_launch(init_plan, stream);
     if (init_smem)
       return init_conv_smem_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
                                    init_wt_bf16.as<__nv_bfloat16>(), gs_w.as<float>(), gs_b.as<float>(), xraw.as<__half>(),
@@ -206,7 +213,7 @@ struct p3_engine {
     int rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[0], stream));
     rc = encode_launch(d_feats.as<p3_go_features>(), batch, version, d_planes.as<float>(), d_scalars.as<float>(),
-                       d_masks.as<uint16_t>(), stream);
+                       d_masks.as<uint16_t>(), stream, init_tc ? &enc_extra : nullptr);
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[1], stream));
     rc = run_init();
@@ -392,6 +399,20 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     const char* env_ic = std::getenv("P3_INIT_SMEM");
     e.init_smem = e.bf16 && init_conv_smem_supported(P, C) && !(env_ic && std::atoi(env_ic) == 0);
     if (e.init_smem && (rc = upload_bf16(e.init_wt_bf16, wt))) return rc;
+    const char* env_it = std::getenv("P3_INIT_TC");
+    e.init_tc = e.bf16 && init_tc_supported(P, e.nscalars, C) && !(env_it && std::atoi(env_it) == 0);
+    if (e.init_tc) {
+      std::vector<__nv_bfloat16> packed;
+      init_tc_pack_weights(wt.data(), P, C, packed);
+      if ((rc = upload(e.init_wt_tc, packed.data(), packed.size() * sizeof(__nv_bfloat16)))) return rc;
+      if ((rc = e.d_masks_pad.alloc(sizeof(uint16_t) * B * kMaskPadElems)) || (rc = e.d_gs.alloc(sizeof(float) * B * C))) return rc;
+      P3_CUDA(cudaMemset(e.d_masks_pad.p, 0, e.d_masks_pad.bytes));  // the grid borders stay zero for the engine's lifetime
+      e.enc_extra.masks_padded = e.d_masks_pad.as<uint16_t>();
+      e.enc_extra.gs_w = e.gs_w.as<float>();
+      e.enc_extra.gs_b = e.gs_b.as<float>();
+      e.enc_extra.C = C;
+      e.enc_extra.gs_out = e.d_gs.as<float>();
+    }
   }
   {
     std::vector<float> ones(std::max(C, 3 * Ch), 1.0f), zeros(std::max(C, 3 * Ch), 0.0f);
@@ -455,6 +476,10 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   void* other = e.actB.p;
   e.first_scale = blocks[0].convs[0]->in_scale.as<float>();
   e.first_shift = blocks[0].convs[0]->in_shift.as<float>();
+  if (e.init_tc && (rc = init_tc_plan_create(e.d_masks_pad.as<uint16_t>(), e.d_gs.as<float>(), B, C,
+                                             e.init_wt_tc.as<__nv_bfloat16>(), e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(),
+                                             e.first_scale, e.first_shift, &e.init_plan)))
+    return rc;
   auto add_conv = [&](ConvLayer* L, const void* in, const void* residual, void* raw, void* act, int mode,
                       const ConvLayer* next) -> int {
     Step s;
@@ -793,7 +818,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   auto rec = [&]() { return cudaEventRecord(evs[idx++], e->stream); };
   P3_CUDA(rec());
   rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
-                     e->d_masks.as<uint16_t>(), e->stream);
+                     e->d_masks.as<uint16_t>(), e->stream, e->init_tc ? &e->enc_extra : nullptr);
   cls.push_back(0); fl.push_back(0.0);
   P3_CUDA(rec());
   if (!rc) rc = e->run_init();
