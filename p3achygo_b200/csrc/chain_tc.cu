@@ -57,30 +57,6 @@ __host__ __device__ constexpr int chain_fixed_smem(int k1, int n1, int n2) {
 constexpr int kChBarRegion = 512;
 constexpr int kChBarBytes = kChBarRegion + 4 * kChMaxN * 4;
 
-// 8 activations a[i] = mish(t[i]), t = (x * scale + shift), with the constants pre-multiplied by log2(e): z = t log2(e) comes
-// straight out of the BN FFMA, e^t = ex2(z), and mish(t) = t (1 - 2/d) = z * (ln2 - 2 ln2 / d), d = e^t (e^t + 2) + 2.  Pairs
-// share one reciprocal (1/d0 = d1 / (d0 d1)).  Written phase by phase over the 8 values so that the 8 dependency chains are
-// interleaved (the SFU latency of one is covered by the others) instead of running back to back.
-__device__ __forceinline__ void bn_mish8(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
-  const float4 s0 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0) * 4u), s1 = ptx::lds_f4_const(sc + static_cast<uint32_t>(col0 + 4) * 4u);
-  const float4 h0 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0) * 4u), h1 = ptx::lds_f4_const(sh + static_cast<uint32_t>(col0 + 4) * 4u);
-  const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-  const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-  float z[8], d[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scv[i], shv[i]);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = ex2_approx_ftz(fminf(z[i], 28.853900817779268f));  // e^t, t clamped to 20
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = fmaf(d[i], d[i] + 2.0f, 2.0f);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float r = rcp_approx_ftz(d[2 * i] * d[2 * i + 1]);
-    const float q0 = d[2 * i + 1] * r, q1 = d[2 * i] * r;  // 1/d0, 1/d1
-    a[2 * i] = z[2 * i] * fmaf(q0, -1.3862943611198906f, 0.6931471805599453f);
-    a[2 * i + 1] = z[2 * i + 1] * fmaf(q1, -1.3862943611198906f, 0.6931471805599453f);
-  }
-}
 __device__ __forceinline__ void bn_mish16(const float* x, float* a, uint32_t sc, uint32_t sh, int col0) {
   bn_mish8(x, a, sc, sh, col0);
   bn_mish8(x + 8, a + 8, sc, sh, col0 + 8);
