@@ -88,6 +88,15 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
 void tc_chain_plan_destroy(TcChainPlan* p);
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
 
+// stand-alone 1x1 trunk layers of the bf16 engine (pw_tc.cu): CTA-pair GEMM with resident weights, in-place residual boxes,
+// per-quarter I/O warps.  ep.residual / ep.raw_out must be the fp16 stream (ep.raw_f16), ep.act_out bf16.
+struct TcPwPlan;
+bool tc_pw_supported(int k1, int n1);
+int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int k1, int n1, const ConvEpilogue& ep,
+                      TcPwPlan** out);
+void tc_pw_plan_destroy(TcPwPlan* p);
+int tc_pw_launch(const TcPwPlan* p, cudaStream_t stream);
+
 // ---- encode (encode.cu) --------------------------------------------------------------------------
 // feats: device copy of p3_go_features[n]. planes [n,361,P] fp32, scalars [n,S] fp32,
 // masks [n,361] uint16 (bit ch set <=> planes[...,ch] == 1).
@@ -162,7 +171,7 @@ struct HeadWeights {
 };
 // pgv [n*400, 3*Ch] fp32 (p | g | v); results/aux device arrays of n.
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream);
+                 cudaStream_t stream, bool accurate = true);
 
 // ---- gumbel (gumbel.cu) --------------------------------------------------------------------------------------
 int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,

@@ -118,6 +118,7 @@ struct Step {
   // fused block boundary (bf16 mode): `layer` = the block's expand conv, `layer2` = the next block's reduce conv
   ConvLayer* layer2 = nullptr;
   TcChainPlan* cplan = nullptr;
+  TcPwPlan* pplan = nullptr;  // stand-alone 1x1 layer on the CTA-pair kernel (pw_tc.cu) instead of layer->plan
 };
 
 }  // namespace
@@ -169,6 +170,7 @@ struct p3_engine {
     for (Step& s : program) {
       if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
       if (s.cplan) tc_chain_plan_destroy(s.cplan);
+      if (s.pplan) tc_pw_plan_destroy(s.pplan);
     }
     if (init_plan) init_tc_plan_destroy(init_plan);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -187,6 +189,7 @@ struct p3_engine {
 
   int run_conv(const Step& s) {
     ConvLayer& L = *s.layer;
+    if (s.pplan) return tc_pw_launch(s.pplan, stream);
     if (bf16)
       return tc_conv_launch(L.plan, stream);
     return conv_fp32_launch(reinterpret_cast<const float*>(s.in), L.w_f32.as<float>(), rows, L.cin, L.cout, L.taps,
@@ -227,7 +230,7 @@ struct p3_engine {
     if (with_events) P3_CUDA(cudaEventRecord(ev[2], stream));
     rc = run_conv(head_step);
     if (rc) return rc;
-    rc = heads_launch(pgv.as<float>(), batch, hw, d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(), stream);
+    rc = heads_launch(pgv.as<float>(), batch, hw, d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(), stream, !bf16);
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
     return P3_OK;
@@ -480,6 +483,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
                                              e.init_wt_tc.as<__nv_bfloat16>(), e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(),
                                              e.first_scale, e.first_shift, &e.init_plan)))
     return rc;
+  const char* env_pw = std::getenv("P3_TC_PW");
+  const bool pw_enabled = !(env_pw && std::atoi(env_pw) == 0);
   auto add_conv = [&](ConvLayer* L, const void* in, const void* residual, void* raw, void* act, int mode,
                       const ConvLayer* next) -> int {
     Step s;
@@ -495,7 +500,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       s.ep.scale = next->in_scale.as<float>();
       s.ep.shift = next->in_shift.as<float>();
     }
-    if (e.bf16) {
+    if (e.bf16 && pw_enabled && L->taps == 1 && tc_pw_supported(L->cin, L->cout) && (act != nullptr || raw != nullptr)) {
+      int r = tc_pw_plan_create(reinterpret_cast<const __nv_bfloat16*>(in), L->w_bf16.as<__nv_bfloat16>(), e.rows, L->cin,
+                                L->cout, s.ep, &s.pplan);
+      if (r) return r;
+    } else if (e.bf16) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(in), L->w_bf16.as<__nv_bfloat16>(), e.rows,
                                   L->cin, L->cout, L->taps, L->tap_off.data(), s.ep, &L->plan);
       if (r) return r;
@@ -843,7 +852,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   if (!rc) rc = e->run_conv(e->head_step);
   cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
   P3_CUDA(rec());
-  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream);
+  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16);
   cls.push_back(6); fl.push_back(0.0);
   P3_CUDA(rec());
   P3_CUDA(cudaStreamSynchronize(e->stream));

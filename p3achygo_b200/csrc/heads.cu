@@ -42,6 +42,9 @@ __device__ void block_softmax(const float* s_in, int n, float* out, float* out2,
   }
 }
 
+// kAccurate: libm-grade mish / exp (the fp32 parity engine).  The bf16 engine uses the ex2 / rcp forms (rel. err ~1e-6,
+// far below the bf16 rounding of its inputs): the 800 x Cv mish evaluations of the score head dominate this kernel.
+template <bool kAccurate>
 __global__ void __launch_bounds__(kThreads)
 heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __restrict__ results,
              p3_aux_result* __restrict__ auxs) {
@@ -70,7 +73,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
       const float sc = is_g ? hw.gp_scale[col] : 1.0f, sh = is_g ? hw.gp_shift[col] : 0.0f;
       for (int p = grp; p < P3_NUM_BOARD_LOCS; p += groups) {
         float x = base[static_cast<size_t>(board_row(p)) * W3 + Ch + col];
-        if (is_g) x = mish_f32<true>(fmaf(x, sc, sh));
+        if (is_g) x = mish_f32<kAccurate>(fmaf(x, sc, sh));
         sum += x;
         mx = fmaxf(mx, x);
       }
@@ -117,8 +120,8 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
       g2 = fmaf(v, hw.gamma_pre_w[i * Cv + j], g2);
       sb = fmaf(v, hw.score_pre_w[i * Cv + j], sb);
     }
-    s_e[j] = mish_f32<true>(e);
-    s_g2[j] = mish_f32<true>(g2);
+    s_e[j] = mish_f32<kAccurate>(e);
+    s_g2[j] = mish_f32<kAccurate>(g2);
     s_base[j] = sb;                               // W_v . v_pooled + b : the per-position part of score_pre
     s_ws[j] = hw.score_pre_w[2 * Ch * Cv + j];    // weight of the score-bin input
   }
@@ -144,7 +147,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
     const float* row = base + static_cast<size_t>(board_row(p)) * W3;
     float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f, own = 0.0f;
     for (int c = 0; c < Ch; ++c) {
-      const float a = mish_f32<true>(row[c] + s_pbias[c]);
+      const float a = mish_f32<kAccurate>(row[c] + s_pbias[c]);
       l0 = fmaf(a, hw.moves_w[c], l0);
       l1 = fmaf(a, hw.moves_w[Ch + c], l1);
       l2 = fmaf(a, hw.moves_w[2 * Ch + c], l2);
@@ -163,7 +166,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
   for (int i = tid; i < P3_NUM_SCORE_LOGITS; i += kThreads) {
     const float si = hw.scores[i];
     float a = hw.score_b[0];
-    for (int j = 0; j < Cv; ++j) a = fmaf(mish_f32<true>(fmaf(s_ws[j], si, s_base[j])), hw.score_w[j], a);
+    for (int j = 0; j < Cv; ++j) a = fmaf(mish_f32<kAccurate>(fmaf(s_ws[j], si, s_base[j])), hw.score_w[j], a);
     s_score[i] = s_gamma_mult * a;
   }
   __syncthreads();
@@ -227,10 +230,11 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
 }  // namespace
 
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, bool accurate) {
   if (hw.Ch > kMaxCh || hw.Cv > kMaxCv || 2 * hw.Ch > kThreads)
     return fail(P3_ERR_UNSUPPORTED, "heads: head channels / c_val too large");
-  heads_kernel<<<n, kThreads, 0, stream>>>(pgv, hw, results, aux);
+  if (accurate) heads_kernel<true><<<n, kThreads, 0, stream>>>(pgv, hw, results, aux);
+  else heads_kernel<false><<<n, kThreads, 0, stream>>>(pgv, hw, results, aux);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }
