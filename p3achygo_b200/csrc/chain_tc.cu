@@ -147,6 +147,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) ptx::griddep_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): resident weight halves, then this CTA's A1 tiles =====
@@ -159,6 +160,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::tma_load_2d_pair(smem_w2 + j * w2_slab_bytes, &map_w2, w_bar_leader, j * 64, static_cast<int>(rank) * (n2 / 2));
     }
     __syncwarp();
+    ptx::griddep_wait();  // the weights above do not depend on the previous kernel; the activations do
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair; mt < m_tiles; mt += n_pairs) {
@@ -281,6 +283,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       }
     };
     Cursor cur{0, 0, 0}, ahead{0, 0, 0};
+    ptx::griddep_wait();  // residual loads / output stores touch buffers of the previous kernel
     if (n_it > 0) {
       for (int i = 0; i < kChBoxes; ++i) {  // all boxes start out free
         if (lane == 0) prepare(ahead);
@@ -559,10 +562,9 @@ void tc_chain_plan_destroy(TcChainPlan* p) {
 
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
-  kern<<<p->grid, kChThreads, p->smem_bytes, stream>>>(
-      p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw, p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages,
-      p->tmem_cols, p->scale1, p->shift1, p->scale2, p->shift2, p->act2_mode, p->trace);
-  P3_CUDA(cudaGetLastError());
+  P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
+                        p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->tmem_cols, p->scale1, p->shift1, p->scale2,
+                        p->shift2, p->act2_mode, p->trace));
   return P3_OK;
 }
 

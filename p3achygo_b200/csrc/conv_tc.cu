@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "math.cuh"
 #include "ptx.cuh"
+#include "tc_util.cuh"
 
 namespace p3 {
 
@@ -725,6 +726,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   if (tr && threadIdx.x == 0) atomicAdd(&trace[2], global_timer() - t_start);
+  if (threadIdx.x == 0) ptx::griddep_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -737,6 +739,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                                 t * cout + n0 + static_cast<int>(rank) * n_half);
     }
     __syncwarp();
+    ptx::griddep_wait();  // (PDL) the resident weights above do not depend on the previous kernel; the activations do
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice) {
@@ -1146,10 +1149,9 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
   if (p->pair) {
-    pair_kernel_for(p->n_tile)<<<p->grid, kPairThreads, p->smem_bytes, stream>>>(
-        p->map_a, p->map_w, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0,
-        p->tmem_cols, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff,
-        p->trace);
+    P3_CUDA(tc_launch_pdl(pair_kernel_for(p->n_tile), p->grid, kPairThreads, p->smem_bytes, stream, p->map_a, p->map_w, p->map_raw,
+                          p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0, p->tmem_cols, p->tap,
+                          reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff, p->trace));
   } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,

@@ -52,6 +52,16 @@ __device__ __forceinline__ void stg_u8(void* gptr, uint4 a, uint4 b) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still draining (its CTAs become resident as the predecessor's CTAs exit).  Everything that does not depend on the
+// predecessor (barrier init, TMEM allocation, weight loads) runs ahead; a thread calls griddep_wait() before it first
+// touches global memory the predecessor reads or writes.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the dependent grid be scheduled once every CTA of this grid has executed it (or exited); the dependent's CTAs then become
+// resident as this grid's CTAs leave their SMs and run their own prologue up to griddep_wait().
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

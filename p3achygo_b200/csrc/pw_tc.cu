@@ -117,6 +117,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   ptx::cluster_sync_all();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) ptx::griddep_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -127,6 +128,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         ptx::tma_load_2d_pair(smem_w + ks * w_slab_bytes, &map_w1, w_bar_leader, ks * 64, n0 + static_cast<int>(rank) * (n_tile / 2));
     }
     __syncwarp();
+    ptx::griddep_wait();  // the weights above do not depend on the previous kernel; the activations do
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < n_it; ++it) {
@@ -204,6 +206,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         ptx::mbar_arrive(&my_ready[b]);
       }
     };
+    ptx::griddep_wait();  // residual loads / output stores touch buffers of the previous kernel
     if (lane == 0)
       for (uint32_t s = 0; s < static_cast<uint32_t>(n_boxes); ++s) prepare(s);  // all boxes start out free
     for (uint32_t s = 0; s < total_steps; ++s) {
@@ -407,10 +410,9 @@ int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows,
 void tc_pw_plan_destroy(TcPwPlan* p) { delete p; }
 
 int tc_pw_launch(const TcPwPlan* p, cudaStream_t stream) {
-  tc_pw_pair_kernel<<<p->grid, kPwThreads, p->smem_bytes, stream>>>(
-      p->map_a1, p->map_w1, p->map_res, p->map_raw, p->map_act, p->rows, p->k1, p->n1, p->n_tile, p->a1_stages, p->n_boxes,
-      p->has_res, p->has_raw, p->has_act, p->act_mode, p->scale, p->shift);
-  P3_CUDA(cudaGetLastError());
+  P3_CUDA(tc_launch_pdl(tc_pw_pair_kernel, p->grid, kPwThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_res, p->map_raw,
+                        p->map_act, p->rows, p->k1, p->n1, p->n_tile, p->a1_stages, p->n_boxes, p->has_res, p->has_raw, p->has_act,
+                        p->act_mode, p->scale, p->shift));
   return P3_OK;
 }
 

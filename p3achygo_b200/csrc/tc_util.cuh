@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -40,6 +41,26 @@ inline int tc_make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataTyp
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(P3_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(r));
   return P3_OK;
+}
+
+// Launch `kern` with programmatic stream serialization (see ptx::griddep_wait); P3_PDL=0 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t tc_launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("P3_PDL");
+    return !(e && std::atoi(e) == 0);
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ uint32_t tc_pack_bf16(float a, float b) {
