@@ -247,7 +247,17 @@ def main():
             a[0] += ms / n_prof
     peaks = measured_peaks()
     dom = prof["conv3x3"] if prof["conv3x3"][1] > 0 else prof["conv1x1"]
-    dom_name = "tc_conv_kernel (3x3 layers)" if prof["conv3x3"][1] > 0 else "tc_conv_kernel (1x1 layers)"
+    dom_name = "tc_conv3x3_pair_kernel (3x3 layers)" if prof["conv3x3"][1] > 0 else "1x1 layers"
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    traffic, traffic_src, ncu_share, ncu_tensor = None, None, None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v11.json")
+    if os.path.exists(tpath) and args.config == CONFIG and B == BATCH and prof["conv3x3"][1] > 0:
+        with open(tpath) as f:
+            tj = json.load(f)
+        k = tj["kernels"].get("tc_conv3x3_pair_kernel")
+        if k:
+            traffic, traffic_src = k["dram_bytes"], tj["source"]
+            ncu_share, ncu_tensor = k.get("share_of_step_in_launch_list"), k.get("tensor_pipe_active_pct")
     achieved = dom[2] / (dom[0] * 1e-3) / 1e12 if dom[0] > 0 else 0.0
     all_conv_ms = prof["conv1x1"][0] + prof["conv3x3"][0] + prof["head_conv"][0]
     all_conv_fl = prof["conv1x1"][2] + prof["conv3x3"][2] + prof["head_conv"][2]
@@ -255,7 +265,10 @@ def main():
     roofline = {
         "bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-        "traffic": None, "launches_per_step": dom[1], "avg_launch_ms": dom[0] / max(dom[1], 1),
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)", "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": 2.0 * 400 * cfg.bottleneck_channels * 2 * B if hasattr(cfg, "bottleneck_channels") else None,
+        "ncu_share_of_step": ncu_share, "ncu_tensor_pipe_active_pct": ncu_tensor,
+        "launches_per_step": dom[1], "avg_launch_ms": dom[0] / max(dom[1], 1),
         "share_of_step": dom[0] / step_ms if step_ms else None,
         "all_conv_tflops": all_conv_fl / (all_conv_ms * 1e-3) / 1e12 if all_conv_ms else None,
         "whole_step_tflops": cfg.flops_per_position() * B / (np.mean(ms_steps) * 1e-3) / 1e12,

@@ -211,6 +211,17 @@ int p3_conv_test(int device, int precision, const float* x, const float* w, int 
  * x [n,361,C] fp32 (HOST, already activated), w [361,361] (in, out), bias [361]; y [n,361,C] = mish(W^T x + bias). */
 int p3_broadcast_test(int device, int precision, const float* x, const float* w, const float* bias, int n, int C, float* y);
 
+/* The boundary between two bottleneck blocks of the bf16 engine (python/model.py:372-427), for kernel unit tests:
+ *   x'  = x + W1 t                    (expand 1x1, k1 -> n1, plus the residual stream x)
+ *   u   = mish(x' * scale1 + shift1)  (folded BN of the next block's first conv)
+ *   out = mish((W2 u) * scale2 + shift2)   (reduce 1x1, n1 -> n2, and the following conv's folded BN)
+ * t [n,361,k1], x [n,361,n1] fp32 NHWC (HOST; rounded to bf16 / fp16 on upload), w1 [n1,k1], w2 [n2,n1] fp32,
+ * scale / shift fp32 vectors; xprime [n,361,n1] (the fp16 stream) and out [n,361,n2] (bf16) come back as fp32.
+ * fused != 0 runs the single fused launch (chain_tc.cu), fused == 0 the two stand-alone 1x1 launches (pw_tc.cu). */
+int p3_block_boundary_test(int device, int fused, const float* t, const float* x, const float* w1, const float* w2,
+                           const float* scale1, const float* shift1, const float* scale2, const float* shift2, int n,
+                           int k1, int n1, int n2, float* xprime, float* out);
+
 const char* p3_last_error(void);
 const char* p3_version(void);
 

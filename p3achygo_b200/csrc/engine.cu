@@ -1011,6 +1011,85 @@ int p3_broadcast_test(int device, int precision, const float* x, const float* w,
   return P3_OK;
 }
 
+int p3_block_boundary_test(int device, int fused, const float* t, const float* x, const float* w1, const float* w2,
+                           const float* scale1, const float* shift1, const float* scale2, const float* shift2, int n, int k1,
+                           int n1, int n2, float* xprime, float* out) {
+  if (!t || !x || !w1 || !w2 || !scale1 || !shift1 || !scale2 || !shift2 || !xprime || !out || n <= 0)
+    return fail(P3_ERR_INVALID_ARG, "block_boundary_test: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (fused ? !tc_chain_supported(k1, n1, n2) : !(tc_pw_supported(k1, n1) && tc_pw_supported(n1, n2)))
+    return fail(P3_ERR_UNSUPPORTED, "block_boundary_test: shape not supported");
+  const size_t R = static_cast<size_t>(n) * kRowsPerPos;
+  auto pad = [&](const float* src, int C) {  // [n,361,C] -> padded board-row layout [n*400, C]
+    std::vector<float> v(R * C, 0.0f);
+    for (int b = 0; b < n; ++b)
+      for (int p = 0; p < 361; ++p)
+        std::memcpy(&v[(static_cast<size_t>(b) * kRowsPerPos + board_row(p)) * C], &src[(static_cast<size_t>(b) * 361 + p) * C], sizeof(float) * C);
+    return v;
+  };
+  const std::vector<float> tp = pad(t, k1), xp = pad(x, n1);
+  std::vector<__half> xh(xp.size());
+  for (size_t i = 0; i < xp.size(); ++i) xh[i] = __float2half_rn(xp[i]);
+  DevBuf dt, dx, dw1, dw2, ds1, dh1, ds2, dh2, du, dout;
+  if ((rc = upload_bf16(dt, tp)) || (rc = upload(dx, xh.data(), xh.size() * sizeof(__half))) ||
+      (rc = upload_bf16(dw1, std::vector<float>(w1, w1 + static_cast<size_t>(n1) * k1))) ||
+      (rc = upload_bf16(dw2, std::vector<float>(w2, w2 + static_cast<size_t>(n2) * n1))) ||
+      (rc = upload_f32(ds1, std::vector<float>(scale1, scale1 + n1))) || (rc = upload_f32(dh1, std::vector<float>(shift1, shift1 + n1))) ||
+      (rc = upload_f32(ds2, std::vector<float>(scale2, scale2 + n2))) || (rc = upload_f32(dh2, std::vector<float>(shift2, shift2 + n2))) ||
+      (rc = du.alloc(R * n1 * 2)) || (rc = dout.alloc(R * n2 * 2)))
+    return rc;
+  P3_CUDA(cudaMemset(dout.p, 0xff, dout.bytes));  // padding rows must come back as zeros
+  if (fused) {
+    TcChainPlan* plan = nullptr;
+    if ((rc = tc_chain_plan_create(dt.as<__nv_bfloat16>(), dw1.as<__nv_bfloat16>(), dw2.as<__nv_bfloat16>(), static_cast<int>(R), k1, n1,
+                                   n2, dx.p, dx.p, ds1.as<float>(), dh1.as<float>(), dout.p, ds2.as<float>(), dh2.as<float>(),
+                                   kActMishBN, &plan)))
+      return rc;
+    rc = tc_chain_launch(plan, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    tc_chain_plan_destroy(plan);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(P3_ERR_CUDA, std::string("tc_chain kernel: ") + cudaGetErrorString(se));
+  } else {
+    ConvEpilogue e1, e2;
+    e1.residual = dx.p; e1.raw_out = dx.p; e1.raw_f16 = true; e1.act_out = du.p; e1.act_mode = kActMishBN;
+    e1.scale = ds1.as<float>(); e1.shift = dh1.as<float>();
+    e2.act_out = dout.p; e2.act_mode = kActMishBN; e2.scale = ds2.as<float>(); e2.shift = dh2.as<float>();
+    TcPwPlan *p1 = nullptr, *p2 = nullptr;
+    if ((rc = tc_pw_plan_create(dt.as<__nv_bfloat16>(), dw1.as<__nv_bfloat16>(), static_cast<int>(R), k1, n1, e1, &p1))) return rc;
+    if ((rc = tc_pw_plan_create(du.as<__nv_bfloat16>(), dw2.as<__nv_bfloat16>(), static_cast<int>(R), n1, n2, e2, &p2))) {
+      tc_pw_plan_destroy(p1);
+      return rc;
+    }
+    rc = tc_pw_launch(p1, 0);
+    if (!rc) rc = tc_pw_launch(p2, 0);
+    cudaError_t se = cudaDeviceSynchronize();
+    tc_pw_plan_destroy(p1);
+    tc_pw_plan_destroy(p2);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(P3_ERR_CUDA, std::string("tc_pw kernel: ") + cudaGetErrorString(se));
+  }
+  std::vector<__half> hx(R * n1);
+  std::vector<__nv_bfloat16> ho(R * n2);
+  P3_CUDA(cudaMemcpy(hx.data(), dx.p, dx.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(ho.data(), dout.p, dout.bytes, cudaMemcpyDeviceToHost));
+  for (size_t row = 0; row < R; ++row)
+    if (!row_is_live(static_cast<int>(row % kRowsPerPos))) {
+      for (int c = 0; c < n2; ++c)
+        if (__bfloat162float(ho[row * n2 + c]) != 0.0f) return fail(P3_ERR_CUDA, "block_boundary_test: padding row of out not zero");
+      for (int c = 0; c < n1; ++c)
+        if (__half2float(hx[row * n1 + c]) != 0.0f) return fail(P3_ERR_CUDA, "block_boundary_test: padding row of x' not zero");
+    }
+  for (int b = 0; b < n; ++b)
+    for (int p = 0; p < 361; ++p) {
+      const size_t row = static_cast<size_t>(b) * kRowsPerPos + board_row(p);
+      for (int c = 0; c < n1; ++c) xprime[(static_cast<size_t>(b) * 361 + p) * n1 + c] = __half2float(hx[row * n1 + c]);
+      for (int c = 0; c < n2; ++c) out[(static_cast<size_t>(b) * 361 + p) * n2 + c] = __bfloat162float(ho[row * n2 + c]);
+    }
+  return P3_OK;
+}
+
 int p3_conv_test(int device, int precision, const float* x, const float* w, int n, int cin, int cout, int ksize, float* y) {
   if (!x || !w || !y || n <= 0 || (ksize != 1 && ksize != 3)) return fail(P3_ERR_INVALID_ARG, "conv_test: bad argument");
   int rc = check_device(device);

@@ -244,3 +244,22 @@ def broadcast_test(x: np.ndarray, w: np.ndarray, bias: np.ndarray, precision: in
     y = np.zeros((n, NUM_LOCS, C), dtype=np.float32)
     check(lib.p3_broadcast_test(device, precision, ptr(x), ptr(w), ptr(bias), n, C, ptr(y)))
     return y
+
+
+def block_boundary_test(t: np.ndarray, x: np.ndarray, w1: np.ndarray, w2: np.ndarray, scale1, shift1, scale2, shift2,
+                        fused: bool, device: int = 0):
+    """Expand 1x1 + residual -> BN/mish -> reduce 1x1 -> BN/mish of the bf16 engine (p3_block_boundary_test).
+    t [n,361,k1], x [n,361,n1], w1 [n1,k1], w2 [n2,n1]; returns (x' [n,361,n1], out [n,361,n2])."""
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w1 = np.ascontiguousarray(w1, dtype=np.float32)
+    w2 = np.ascontiguousarray(w2, dtype=np.float32)
+    vecs = [np.ascontiguousarray(v, dtype=np.float32) for v in (scale1, shift1, scale2, shift2)]
+    n, _, k1 = t.shape
+    n1, n2 = w1.shape[0], w2.shape[0]
+    xprime = np.empty((n, 361, n1), dtype=np.float32)
+    out = np.empty((n, 361, n2), dtype=np.float32)
+    check(lib.p3_block_boundary_test(device, 1 if fused else 0, ptr(t), ptr(x), ptr(w1), ptr(w2), ptr(vecs[0]), ptr(vecs[1]),
+                                     ptr(vecs[2]), ptr(vecs[3]), n, k1, n1, n2, ptr(xprime), ptr(out)))
+    return xprime, out
+

@@ -81,3 +81,54 @@ def test_broadcast_mix(C, n, prec):
         assert np.abs(y - ref).max() < 2e-5
     else:
         assert np.all(np.abs(y - ref) <= np.abs(ref) * 2.0 ** -8 + 2e-4), f"max abs err {np.abs(y - ref).max()}"
+
+
+def _f16_round(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("k1,n1,n2,n", [(128, 256, 128, 3), (64, 128, 64, 5), (128, 256, 128, 41), (64, 128, 128, 2)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_block_boundary(k1, n1, n2, n, fused):
+    """Expand 1x1 + residual -> BN/mish -> reduce 1x1 -> BN/mish (python/model.py:372-427, 276-281) on the fused CTA-pair
+    kernel (chain_tc.cu) and on the two stand-alone 1x1 launches (pw_tc.cu), against numpy in fp64 on the SAME bf16 / fp16
+    rounded operands.  x' is exact up to its fp16 store; `out` additionally sees the bf16 rounding of u and of itself."""
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(k1 + 7 * n1 + 13 * n2 + n)
+    t = _bf16_round(rng.standard_normal((n, 361, k1)).astype(np.float32))
+    x = _f16_round(rng.standard_normal((n, 361, n1)).astype(np.float32) * 2.0)
+    w1 = _bf16_round((rng.standard_normal((n1, k1)) / np.sqrt(k1)).astype(np.float32))
+    w2 = _bf16_round((rng.standard_normal((n2, n1)) / np.sqrt(n1)).astype(np.float32))
+    s1 = rng.uniform(0.5, 1.5, n1).astype(np.float32)
+    h1 = rng.uniform(-0.5, 0.5, n1).astype(np.float32)
+    s2 = rng.uniform(0.5, 1.5, n2).astype(np.float32)
+    h2 = rng.uniform(-0.5, 0.5, n2).astype(np.float32)
+    xp, out = E.block_boundary_test(t, x, w1, w2, s1, h1, s2, h2, fused)
+    ref_x = x.astype(np.float64) + t.astype(np.float64) @ w1.astype(np.float64).T
+    # x' is stored as fp16: half an ulp of fp16 (2^-11 relative) plus fp32 accumulation noise
+    assert np.all(np.abs(xp - ref_x) <= np.abs(ref_x) * 2.0 ** -11 + 2e-4), f"x' max abs err {np.abs(xp - ref_x).max()}"
+    u = _bf16_round(_mish(ref_x * s1 + h1).astype(np.float32)).astype(np.float64)
+    ref_out = _mish((u @ w2.astype(np.float64).T) * s2 + h2)
+    # u is rounded to bf16 before the second GEMM (a value on a rounding boundary may flip: n1 terms of 2^-9 relative,
+    # averaged down by the sum) and `out` is rounded to bf16
+    err = np.abs(out - ref_out)
+    assert np.all(err <= np.abs(ref_out) * 2.0 ** -8 + 6e-3), f"out max abs err {err.max()}"
+    assert err.mean() < 1e-3
+
+
+def test_block_boundary_fused_equals_unfused():
+    """The fused launch and the two stand-alone launches compute the same function with the same roundings: bit-identical
+    x', and identical `out` (same operands, same MMA shapes along K)."""
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(5)
+    n, k1, n1, n2 = 6, 128, 256, 128
+    t = _bf16_round(rng.standard_normal((n, 361, k1)).astype(np.float32))
+    x = _f16_round(rng.standard_normal((n, 361, n1)).astype(np.float32))
+    w1 = _bf16_round((rng.standard_normal((n1, k1)) / np.sqrt(k1)).astype(np.float32))
+    w2 = _bf16_round((rng.standard_normal((n2, n1)) / np.sqrt(n1)).astype(np.float32))
+    s1, h1 = np.ones(n1, np.float32), np.zeros(n1, np.float32)
+    s2, h2 = np.ones(n2, np.float32), np.zeros(n2, np.float32)
+    xa, oa = E.block_boundary_test(t, x, w1, w2, s1, h1, s2, h2, True)
+    xb, ob = E.block_boundary_test(t, x, w1, w2, s1, h1, s2, h2, False)
+    assert np.array_equal(xa, xb)
+    assert np.abs(oa - ob).max() <= 2.0 ** -7 * max(1.0, float(np.abs(ob).max()))  # at most one bf16 ulp apart
