@@ -113,7 +113,7 @@ def test_block_boundary(k1, n1, n2, n, fused):
     # averaged down by the sum) and `out` is rounded to bf16
     err = np.abs(out - ref_out)
     assert np.all(err <= np.abs(ref_out) * 2.0 ** -8 + 6e-3), f"out max abs err {err.max()}"
-    assert err.mean() < 1e-3
+    assert err.mean() < 2.5e-3  # ~a quarter ulp of bf16 at |out| ~ 1
 
 
 def test_block_boundary_fused_equals_unfused():
