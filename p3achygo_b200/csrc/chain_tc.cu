@@ -33,15 +33,15 @@ constexpr int kChEpiWarps = 16;
 constexpr int kChThreads = (2 + kChEpiWarps + 4) * 32;  // 704: producer, MMA, 16 epilogue, 4 I/O (one per TMEM lane quarter)
 constexpr int kChSlabBytes = 128 * 128;   // 128 rows x 64 bf16 (one K slab of an A operand)
 constexpr int kChBoxBytes = 32 * 128;     // a quarter's 32 rows x 64 two-byte elements
-// A quarter cycles through a pool of kChBoxes staging boxes: TMA load of the residual -> the quarter's 4 warps replace it IN
-// PLACE by x' (or write an epi2 output box) -> TMA store -> free.  Loads are issued kChBoxes - 1 steps ahead of their use.
-constexpr int kChBoxes = 5;
+// A quarter cycles through a pool of n_boxes (3..5) staging boxes: TMA load of the residual -> the quarter's 4 warps replace
+// it IN PLACE by x' (or write an epi2 output box) -> TMA store -> free.  Loads are issued n_boxes - 1 steps ahead of their use.
+constexpr int kChMaxBoxes = 5;
 constexpr int kChMaxN = 256;
 constexpr int kChSmemBudget = 227 * 1024;
 
 struct TcChainPlan {
   CUtensorMap map_a1, map_w1, map_w2, map_res, map_raw, map_out2;
-  int rows = 0, k1 = 0, n1 = 0, n2 = 0, grid = 0, tmem_cols = 512, acc2_stages = 1;
+  int rows = 0, k1 = 0, n1 = 0, n2 = 0, grid = 0, tmem_cols = 512, acc2_stages = 1, a1_stages = 2, n_boxes = 3;
   size_t smem_bytes = 0;
   const float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
   int act2_mode = kActMishBN;
@@ -50,9 +50,9 @@ struct TcChainPlan {
 
 namespace {
 
+// resident weight halves + the A2 ring; the A1 ring (a1_stages slabs) and the box pool (n_boxes per quarter) share the rest
 __host__ __device__ constexpr int chain_fixed_smem(int k1, int n1, int n2) {
-  return (k1 / 64) * (n1 / 2) * 128 + (n1 / 64) * (n2 / 2) * 128 + (k1 / 64) * kChSlabBytes + 2 * kChSlabBytes +
-         4 * kChBoxes * kChBoxBytes;
+  return (k1 / 64) * (n1 / 2) * 128 + (n1 / 64) * (n2 / 2) * 128 + 2 * kChSlabBytes;
 }
 constexpr int kChBarRegion = 512;
 constexpr int kChBarBytes = kChBarRegion + 4 * kChMaxN * 4;
@@ -67,7 +67,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChThreads, 1)
 tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_w1,
                      const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
                      const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_out2, int rows, int k1,
-                     int n1, int n2, int acc2_stages, int tmem_cols, const float* __restrict__ scale1,
+                     int n1, int n2, int acc2_stages, int a1_stages, int n_boxes, int tmem_cols, const float* __restrict__ scale1,
                      const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
                      int act2_mode, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -78,9 +78,9 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   uint8_t* smem_w1 = smem;
   uint8_t* smem_w2 = smem_w1 + w1_bytes;
   uint8_t* smem_a1 = smem_w2 + w2_bytes;
-  uint8_t* smem_a2 = smem_a1 + k1_slabs * kChSlabBytes;
-  uint8_t* smem_box = smem_a2 + 2 * kChSlabBytes;  // [4 quarters][kChBoxes] staging boxes
-  uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem_box + 4 * kChBoxes * kChBoxBytes);
+  uint8_t* smem_a2 = smem_a1 + a1_stages * kChSlabBytes;
+  uint8_t* smem_box = smem_a2 + 2 * kChSlabBytes;  // [4 quarters][n_boxes] staging boxes
+  uint64_t* a1_full = reinterpret_cast<uint64_t*>(smem_box + 4 * n_boxes * kChBoxBytes);
   uint64_t* a1_empty = a1_full + 4;
   uint64_t* acc1_full = a1_empty + 4;
   uint64_t* acc1_empty = acc1_full + 1;
@@ -89,9 +89,9 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   uint64_t* acc2_full = a2_empty + 2;
   uint64_t* acc2_empty = acc2_full + 2;
   uint64_t* w_bar = acc2_empty + 2;
-  uint64_t* box_ready = w_bar + 1;                     // [4 quarters][kChBoxes] residual landed / box free for an epi2 output
-  uint64_t* box_written = box_ready + 4 * kChBoxes;    //                        the quarter's 4 warps have written the box
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(box_written + 4 * kChBoxes);
+  uint64_t* box_ready = w_bar + 1;                     // [4 quarters][kChMaxBoxes] residual landed / box free for an epi2 output
+  uint64_t* box_written = box_ready + 4 * kChMaxBoxes;    //                        the quarter's 4 warps have written the box
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(box_written + 4 * kChMaxBoxes);
   float* s_scale1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a1_full) + kChBarRegion);
   float* s_shift1 = s_scale1 + kChMaxN;
   float* s_scale2 = s_shift1 + kChMaxN;
@@ -133,7 +133,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       ptx::mbar_init(&acc2_empty[s], 2 * kChEpiWarps);
     }
     ptx::mbar_init(w_bar, 1);
-    for (int s = 0; s < 4 * kChBoxes; ++s) {
+    for (int s = 0; s < 4 * kChMaxBoxes; ++s) {
       ptx::mbar_init(&box_ready[s], 1);
       ptx::mbar_init(&box_written[s], 4);
     }
@@ -173,7 +173,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                                 ks * 64, m0);
         }
         __syncwarp();
-        if (++stage == k1_slabs) {
+        if (++stage == a1_stages) {
           stage = 0;
           phase ^= 1;
         }
@@ -206,7 +206,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
             ptx::umma_commit_pair(&a1_empty[stage]);
           }
           __syncwarp();
-          if (++stage == k1_slabs) {
+          if (++stage == a1_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -249,31 +249,37 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     //   residual box read by the 4 warps -> refill it 2 steps ahead ; x' box written -> TMA store, publish the A2 slab to
     //   the leader's MMA warp ; the store issued one step earlier has read its box -> hand the box back.
     const int q = warp - (2 + kChEpiWarps);
-    uint64_t* my_ready = box_ready + kChBoxes * q;
-    uint64_t* my_written = box_written + kChBoxes * q;
+    uint64_t* my_ready = box_ready + kChMaxBoxes * q;
+    uint64_t* my_written = box_written + kChMaxBoxes * q;
     const uint32_t a2_full_l = ptx::mapa_shared(ptx::smem_u32(a2_full), 0);
-    uint8_t* my_box = smem_box + q * kChBoxes * kChBoxBytes;
+    uint8_t* my_box = smem_box + q * n_boxes * kChBoxBytes;
     const int q_row = static_cast<int>(rank) * 128 + q * 32;
     // The quarter's step sequence (the epilogue warps walk the same one): per iteration `it`, the n1_slabs epi1 steps of
-    // tile it, then the n2_slabs epi2 steps of tile it - defer.  `ahead` runs kChBoxes - 1 steps in front of `cur`
-    // (the box of step cur - 1, just read by its store, serves step cur + kChBoxes - 1).
+    // tile it, then the n2_slabs epi2 steps of tile it - defer.  `ahead` runs n_boxes - 1 steps in front of `cur`
+    // (the box of step cur - 1, just read by its store, serves step cur + n_boxes - 1).
     struct Cursor {
       int it, idx;   // iteration, index within the iteration's steps
-      uint32_t s;    // step ordinal (box = s % kChBoxes)
+      uint32_t s;    // step ordinal
+      uint32_t b;    // box of the step: s mod n_boxes
+      uint32_t ph;   // use parity of that box: (s / n_boxes) & 1
     };
     auto steps_in = [&](int it) { return (it < n_it ? n1_slabs : 0) + ((it - defer >= 0 && it - defer < n_it) ? n2_slabs : 0); };
     auto advance = [&](Cursor& c) {
       ++c.s;
+      if (++c.b == static_cast<uint32_t>(n_boxes)) {
+        c.b = 0;
+        c.ph ^= 1u;
+      }
       if (++c.idx >= steps_in(c.it)) {
         c.idx = 0;
         ++c.it;
       }
     };
     const int n_iter = n_it + defer;
-    // make box s % kChBoxes ready for step c: TMA-load the residual (epi1 step) or just hand the free box over (epi2 step)
+    // make box s % n_boxes ready for step c: TMA-load the residual (epi1 step) or just hand the free box over (epi2 step)
     auto prepare = [&](const Cursor& c) {
       if (c.it >= n_iter) return;
-      const uint32_t b = c.s % kChBoxes;
+      const uint32_t b = c.b;
       const bool is_epi1 = c.it < n_it && c.idx < n1_slabs;
       if (is_epi1) {
         ptx::mbar_arrive_expect_tx(&my_ready[b], kChBoxBytes);
@@ -282,19 +288,19 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::mbar_arrive(&my_ready[b]);
       }
     };
-    Cursor cur{0, 0, 0}, ahead{0, 0, 0};
+    Cursor cur{0, 0, 0, 0, 0}, ahead{0, 0, 0, 0, 0};
     ptx::griddep_wait();  // residual loads / output stores touch buffers of the previous kernel
     if (n_it > 0) {
-      for (int i = 0; i < kChBoxes; ++i) {  // all boxes start out free
+      for (int i = 0; i < n_boxes; ++i) {  // all boxes start out free
         if (lane == 0) prepare(ahead);
         advance(ahead);
       }
     }
     uint32_t g = 0;
     while (cur.it < n_iter) {
-      const uint32_t b = cur.s % kChBoxes;
+      const uint32_t b = cur.b;
       const bool is_epi1 = cur.it < n_it && cur.idx < n1_slabs;
-      ptx::mbar_wait(&my_written[b], (cur.s / kChBoxes) & 1u);
+      ptx::mbar_wait(&my_written[b], cur.ph);
       if (lane == 0) {
         if (is_epi1) {
           ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
@@ -305,7 +311,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                             (pair + (cur.it - defer) * n_pairs) * 256 + q_row);
         }
         ptx::bulk_commit();
-        ptx::bulk_wait_read<1>();  // the previous step's store has read its box: that box serves the step kChBoxes - 1 ahead
+        ptx::bulk_wait_read<1>();  // the previous step's store has read its box: that box serves the step n_boxes - 1 ahead
         if (cur.s > 0) prepare(ahead);
       }
       if (is_epi1) ++g;
@@ -324,17 +330,18 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     const uint32_t ch0 = ((2u * cg) ^ sw) << 4, ch1 = ((2u * cg + 1u) ^ sw) << 4;
     const uint32_t box_row = static_cast<uint32_t>(lane) * 128u;
     const uint32_t slab_row = static_cast<uint32_t>(q * 32 + lane) * 128u;
-    const uint32_t box_base = ptx::smem_u32(smem_box) + static_cast<uint32_t>(q) * (kChBoxes * kChBoxBytes) + box_row;
+    const uint32_t box_base = ptx::smem_u32(smem_box) + static_cast<uint32_t>(q * n_boxes) * kChBoxBytes + box_row;
     const uint32_t a2_base = ptx::smem_u32(smem_a2);
-    uint64_t* my_ready = box_ready + kChBoxes * q;
-    uint64_t* my_written = box_written + kChBoxes * q;
+    uint64_t* my_ready = box_ready + kChMaxBoxes * q;
+    uint64_t* my_written = box_written + kChMaxBoxes * q;
     const uint32_t acc1_empty_l = ptx::mapa_shared(ptx::smem_u32(acc1_empty), 0);
     const uint32_t acc2_empty_l = ptx::mapa_shared(ptx::smem_u32(acc2_empty), 0);
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sc1 = ptx::smem_u32(s_scale1), sh1 = ptx::smem_u32(s_shift1);
     const uint32_t sc2 = ptx::smem_u32(s_scale2), sh2 = ptx::smem_u32(s_shift2);
 
-    uint32_t so = 0, g = 0;  // step (staging box) and A2-slab ordinals of this quarter
+    uint32_t g = 0;                 // A2-slab ordinal of this quarter
+    uint32_t ob = 0, ob_phase = 0;  // staging box of the current step (step ordinal mod n_boxes) and its use parity
     int it = 0;
 
     // P3_TC_TRACE: per-phase clock64 sums of one epilogue thread (perf experiments)
@@ -349,14 +356,13 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::mbar_wait(acc1_full, static_cast<uint32_t>(it) & 1u);
         ptx::tc_fence_after_sync();
         if (tr) ts[8] += static_cast<uint32_t>(clock64() - tc0);
-        for (int j = 0; j < n1_slabs; ++j, ++so, ++g) {
+        for (int j = 0; j < n1_slabs; ++j, ++g) {
           const int col = j * 64 + cg * 16;
           uint32_t v[16];
           long long t[8];
           if (tr) t[0] = clock64();
           ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(col), v);
-          const uint32_t ob = so % kChBoxes;
-          ptx::mbar_wait(&my_ready[ob], (so / kChBoxes) & 1u);
+          ptx::mbar_wait(&my_ready[ob], ob_phase);
           if (tr) t[1] = clock64();
           const uint32_t obuf = box_base + ob * kChBoxBytes;
           const float4 t0 = ptx::lds_f4(obuf + ch0), t1 = ptx::lds_f4(obuf + ch1);
@@ -400,6 +406,10 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           if (tr) t[6] = clock64();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
+          if (++ob == static_cast<uint32_t>(n_boxes)) {
+            ob = 0;
+            ob_phase ^= 1u;
+          }
           if (tr) {
             t[7] = clock64();
             // 0 box ready wait  1 tmem ld wait  2 math  3 a2_empty wait  4 -  5 sts + fence  6 arrive
@@ -422,7 +432,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::tc_fence_after_sync();
         const long long tc1 = tr ? clock64() : 0;
         if (tr) ts[9] += static_cast<uint32_t>(tc1 - tc0);
-        for (int b = 0; b < n2_slabs; ++b, ++so) {
+        for (int b = 0; b < n2_slabs; ++b) {
           const int col = b * 64 + cg * 16;
           uint32_t v[16];
           ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(n1 + as * n2 + col), v);
@@ -444,14 +454,17 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
           uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
           if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
-          const uint32_t ob = so % kChBoxes;
-          ptx::mbar_wait(&my_ready[ob], (so / kChBoxes) & 1u);
+          ptx::mbar_wait(&my_ready[ob], ob_phase);
           const uint32_t obuf = box_base + ob * kChBoxBytes;
           ptx::sts_u4(obuf + ch0, p0);
           ptx::sts_u4(obuf + ch1, p1);
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
+          if (++ob == static_cast<uint32_t>(n_boxes)) {
+            ob = 0;
+            ob_phase ^= 1u;
+          }
         }
         if (tr) {
           ts[11] += static_cast<uint32_t>(clock64() - tc1);
@@ -481,7 +494,9 @@ bool tc_chain_supported(int k1, int n1, int n2) {
   if (k1 <= 0 || n1 <= 0 || n2 <= 0) return false;
   if (k1 % 64 || n1 % 64 || n2 % 64) return false;
   if (k1 > 256 || n1 > kChMaxN || n2 > kChMaxN || n1 + n2 > 512) return false;
-  return static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + 1024 + kChBarBytes <= static_cast<size_t>(kChSmemBudget);
+  // at least a 2-slab A1 ring (one slab if K1 = 64) and 3 boxes per quarter
+  return static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + std::min(2, k1 / 64) * kChSlabBytes + 4 * 3 * kChBoxBytes + 1024 + kChBarBytes <=
+         static_cast<size_t>(kChSmemBudget);
 }
 
 int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
@@ -502,7 +517,26 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
   p->act2_mode = act2_mode;
   p->acc2_stages = (512 - n1) / n2 >= 2 ? 2 : 1;
   p->tmem_cols = 512;
-  p->smem_bytes = static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + 1024 + kChBarBytes;
+  {  // split what is left of shared memory between the A1 ring (up to one tile) and the box pool (up to 5 per quarter)
+    const size_t left = static_cast<size_t>(kChSmemBudget) - 1024 - kChBarBytes - chain_fixed_smem(k1, n1, n2);
+    int stages = std::min(2, k1 / 64), boxes = 3;
+    while (true) {
+      bool grew = false;
+      if (boxes < kChMaxBoxes && static_cast<size_t>(stages) * kChSlabBytes + static_cast<size_t>(4 * (boxes + 1)) * kChBoxBytes <= left) {
+        ++boxes;
+        grew = true;
+      }
+      if (stages < std::min(4, k1 / 64) && static_cast<size_t>(stages + 1) * kChSlabBytes + static_cast<size_t>(4 * boxes) * kChBoxBytes <= left) {
+        ++stages;
+        grew = true;
+      }
+      if (!grew) break;
+    }
+    p->a1_stages = stages;
+    p->n_boxes = boxes;
+    p->smem_bytes = static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + static_cast<size_t>(stages) * kChSlabBytes +
+                    static_cast<size_t>(4 * boxes) * kChBoxBytes + 1024 + kChBarBytes;
+  }
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, hf = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   int rc = tc_make_map_2d(&p->map_a1, in, bf, 2, k1, rows, 64, 128, sw);
@@ -563,7 +597,7 @@ void tc_chain_plan_destroy(TcChainPlan* p) {
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
   P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
-                        p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->tmem_cols, p->scale1, p->shift1, p->scale2,
+                        p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->a1_stages, p->n_boxes, p->tmem_cols, p->scale1, p->shift1, p->scale2,
                         p->shift2, p->act2_mode, p->trace));
   return P3_OK;
 }

@@ -513,8 +513,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     return P3_OK;
   };
   void* chain_out = nullptr;  // set when the previous block ended with a fused boundary
+  bool bcast_conv0_done = false;  // the previous btl block's fused boundary ran the broadcast block's first conv
   const char* env_chain = std::getenv("P3_TC_CHAIN");
   const bool chain_enabled = !(env_chain && std::atoi(env_chain) == 0);
+  const char* env_cb = std::getenv("P3_TC_CHAIN_BCAST");
+  const bool chain_bcast = !(env_cb && std::atoi(env_cb) == 0);
   for (int i = 0; i < e.blocks; ++i) {
     BlockDesc& bk = blocks[i];
     const bool last_block = i == e.blocks - 1;
@@ -522,26 +525,58 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     void* raw_dst = (last_block && e.bf16) ? nullptr : e.xraw.p;
     const ConvLayer* next_first = last_block ? nullptr : blocks[i + 1].convs[0];
     // what the block's final conv writes besides the raw residual stream
-    int end_mode = last_block ? (e.bf16 ? kActIdentity : kActNone) : kActMishBN;
+    const int end_mode = last_block ? (e.bf16 ? kActIdentity : kActNone) : kActMishBN;
     void* end_act = (last_block && !e.bf16) ? nullptr : other;
     if (bk.bcast) {  // BroadcastResidualBlock, model.py:583-607
-      if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMish, nullptr))) return rc;
+      // buffers: t0 = output of the first conv (input of the mix), t1 = output of the mix, both C-wide
+      void* t0 = other;
+      void* t1 = cur;
+      if (bcast_conv0_done) {  // the previous block's fused boundary already ran this block's first conv into `cur`
+        t0 = cur;
+        t1 = other;
+        bcast_conv0_done = false;
+      } else if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, t0, kActMish, nullptr))) {
+        return rc;
+      }
       Step s;
       s.kind = kStepBroadcast;
-      s.in = other;
+      s.in = t0;
       s.bw = bk.bw;
       s.bb = bk.bb;
-      s.b_out = cur;
+      s.b_out = t1;
       s.b_scale = bk.convs[1]->in_scale.as<float>();
       s.b_shift = bk.convs[1]->in_shift.as<float>();
       const char* env_tb = std::getenv("P3_TC_BROADCAST");
       if (e.bf16 && tc_broadcast_supported(C) && !(env_tb && std::atoi(env_tb) == 0)) {
-        if ((rc = tc_broadcast_plan_create(bk.bw_host->data.data(), bk.bb_host->data.data(), other, cur, B, C, s.b_scale,
+        if ((rc = tc_broadcast_plan_create(bk.bw_host->data.data(), bk.bb_host->data.data(), t0, t1, B, C, s.b_scale,
                                            s.b_shift, &s.bplan)))
           return rc;
       }
       e.program.push_back(s);
-      if ((rc = add_conv(bk.convs[1], cur, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
+      // block boundary broadcast -> btl: second conv + residual + next block's reduce as ONE launch (chain_tc.cu)
+      ConvLayer* c2 = bk.convs[1];
+      ConvLayer* nr = (!last_block && !blocks[i + 1].bcast && btl) ? blocks[i + 1].convs[0] : nullptr;
+      if (e.bf16 && chain_enabled && chain_bcast && nr && blocks[i + 1].convs.size() >= 2 && nr->taps == 1 &&
+          tc_chain_supported(c2->cin, c2->cout, nr->cout)) {
+        Step cs;
+        cs.kind = kStepChain;
+        cs.layer = c2;
+        cs.layer2 = nr;
+        cs.in = t1;
+        const ConvLayer* n2 = blocks[i + 1].convs[1];
+        if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(t1), c2->w_bf16.as<__nv_bfloat16>(),
+                                       nr->w_bf16.as<__nv_bfloat16>(), e.rows, c2->cin, c2->cout, nr->cout, e.xraw.p, e.xraw.p,
+                                       nr->in_scale.as<float>(), nr->in_shift.as<float>(), e.actS0.p, n2->in_scale.as<float>(),
+                                       n2->in_shift.as<float>(), kActMishBN, &cs.cplan)))
+          return rc;
+        e.program.push_back(cs);
+        chain_out = e.actS0.p;
+      } else {
+        // the block's activated output goes to the buffer that is not the mix output; make it `other` (swapped below)
+        if (t1 == other) std::swap(cur, other);
+        end_act = (last_block && !e.bf16) ? nullptr : other;
+        if ((rc = add_conv(c2, cur, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
+      }
     } else if (btl) {  // BottleneckResidualConvBlock, model.py:372-412
       void* s0 = e.actS0.p;
       void* s1 = e.actS1.p;
@@ -574,6 +609,22 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
           return rc;
         e.program.push_back(s);
         chain_out = s1;
+      } else if (e.bf16 && chain_enabled && chain_bcast && !last_block && blocks[i + 1].bcast && ex->taps == 1 &&
+                 tc_chain_supported(ex->cin, ex->cout, blocks[i + 1].convs[0]->cout)) {
+        // block boundary btl -> broadcast: expand + residual + the broadcast block's first conv (act = mish, no BN: model.py:574)
+        ConvLayer* c0 = blocks[i + 1].convs[0];
+        Step cs;
+        cs.kind = kStepChain;
+        cs.layer = ex;
+        cs.layer2 = c0;
+        cs.in = s0;
+        if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(s0), ex->w_bf16.as<__nv_bfloat16>(),
+                                       c0->w_bf16.as<__nv_bfloat16>(), e.rows, ex->cin, ex->cout, c0->cout, e.xraw.p, e.xraw.p,
+                                       c0->in_scale.as<float>(), c0->in_shift.as<float>(), other, nullptr, nullptr, kActMish,
+                                       &cs.cplan)))
+          return rc;
+        e.program.push_back(cs);
+        bcast_conv0_done = true;  // its output is in `other`, which becomes `cur` below
       } else if ((rc = add_conv(ex, s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) {
         return rc;
       }

@@ -87,7 +87,8 @@ def _f16_round(a):
     return a.astype(np.float16).astype(np.float32)
 
 
-@pytest.mark.parametrize("k1,n1,n2,n", [(128, 256, 128, 3), (64, 128, 64, 5), (128, 256, 128, 41), (64, 128, 128, 2)])
+@pytest.mark.parametrize("k1,n1,n2,n", [(128, 256, 128, 3), (64, 128, 64, 5), (128, 256, 128, 41), (64, 128, 128, 2),
+                                        (128, 256, 256, 4), (256, 256, 128, 4), (128, 128, 128, 37)])
 @pytest.mark.parametrize("fused", [True, False])
 def test_block_boundary(k1, n1, n2, n, fused):
     """Expand 1x1 + residual -> BN/mish -> reduce 1x1 -> BN/mish (python/model.py:372-427, 276-281) on the fused CTA-pair
@@ -110,9 +111,9 @@ def test_block_boundary(k1, n1, n2, n, fused):
     u = _bf16_round(_mish(ref_x * s1 + h1).astype(np.float32)).astype(np.float64)
     ref_out = _mish((u @ w2.astype(np.float64).T) * s2 + h2)
     # u is rounded to bf16 before the second GEMM (a value on a rounding boundary may flip: n1 terms of 2^-9 relative,
-    # averaged down by the sum) and `out` is rounded to bf16
+    # averaged down by the sum) and `out` is rounded to bf16: a pre-rounding difference can move it by one whole bf16 ulp
     err = np.abs(out - ref_out)
-    assert np.all(err <= np.abs(ref_out) * 2.0 ** -8 + 6e-3), f"out max abs err {err.max()}"
+    assert np.all(err <= np.abs(ref_out) * 2.0 ** -7 + 6e-3), f"out max abs err {err.max()}"
     assert err.mean() < 2.5e-3  # ~a quarter ulp of bf16 at |out| ~ 1
 
 
