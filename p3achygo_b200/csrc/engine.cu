@@ -162,6 +162,8 @@ struct p3_engine {
 
   bool use_graph = true;
   cudaGraphExec_t graph_exec = nullptr;
+  cudaGraphExec_t graph_exec_host = nullptr;  // same step with the heads kernel writing NNInferResult straight to pinned host memory
+  bool results_to_host = true;                // RunInference: no separate D2H copy (P3_RESULTS_TO_HOST=0 restores it)
   float stage_ms[3] = {0, 0, 0};
   int launches = 0;
   bool aux_host_valid = false;
@@ -174,6 +176,7 @@ struct p3_engine {
     }
     if (init_plan) init_tc_plan_destroy(init_plan);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph_exec_host) cudaGraphExecDestroy(graph_exec_host);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (h_feats) cudaFreeHost(h_feats);
@@ -212,7 +215,9 @@ struct p3_engine {
   }
 
   // encode -> init conv -> tower -> head conv -> heads, all on `stream`; optional stage events
-  int enqueue_device(bool with_events) {
+  // to_host: the heads kernel stores the results through the mapped pinned buffer (posted PCIe writes that overlap the
+  // kernel) instead of HBM + a D2H copy after the step
+  int enqueue_device(bool with_events, bool to_host = false) {
     int rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[0], stream));
     rc = encode_launch(d_feats.as<p3_go_features>(), batch, version, d_planes.as<float>(), d_scalars.as<float>(),
@@ -230,17 +235,19 @@ struct p3_engine {
     if (with_events) P3_CUDA(cudaEventRecord(ev[2], stream));
     rc = run_conv(head_step);
     if (rc) return rc;
-    rc = heads_launch(pgv.as<float>(), batch, hw, d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(), stream, !bf16);
+    rc = heads_launch(pgv.as<float>(), batch, hw, to_host ? h_results : d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(),
+                      stream, !bf16);
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
     return P3_OK;
   }
 
-  int ensure_graph() {
+  int ensure_graph(bool to_host = false) {
+    cudaGraphExec_t& graph_exec = to_host ? this->graph_exec_host : this->graph_exec;
     if (graph_exec || !use_graph) return P3_OK;
     cudaGraph_t graph = nullptr;
     P3_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_device(false);
+    int rc = enqueue_device(false, to_host);
     cudaError_t e = cudaStreamEndCapture(stream, &graph);
     if (rc) {
       if (graph) cudaGraphDestroy(graph);
@@ -253,14 +260,14 @@ struct p3_engine {
     return P3_OK;
   }
 
-  int enqueue_device_maybe_graph() {
+  int enqueue_device_maybe_graph(bool to_host = false) {
     if (use_graph) {
-      int rc = ensure_graph();
+      int rc = ensure_graph(to_host);
       if (rc) return rc;
-      P3_CUDA(cudaGraphLaunch(graph_exec, stream));
+      P3_CUDA(cudaGraphLaunch(to_host ? graph_exec_host : graph_exec, stream));
       return P3_OK;
     }
-    return enqueue_device(false);
+    return enqueue_device(false, to_host);
   }
 };
 
@@ -769,6 +776,7 @@ int p3_engine_create(const char* weights_path, int device, int batch_size, int f
   e->precision = precision;
   e->bf16 = precision == P3_PRECISION_BF16;
   if (const char* g = std::getenv("P3_CUDA_GRAPH")) e->use_graph = std::atoi(g) != 0;
+  if (const char* g = std::getenv("P3_RESULTS_TO_HOST")) e->results_to_host = std::atoi(g) != 0;
   P3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) P3_CUDA(cudaEventCreate(&ev));
   rc = build_engine(*e, wf);
@@ -801,9 +809,10 @@ int p3_engine_run_inference(p3_engine* e) {
   if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
-  int rc = e->enqueue_device_maybe_graph();
+  int rc = e->enqueue_device_maybe_graph(e->results_to_host);
   if (rc) return rc;
-  P3_CUDA(cudaMemcpyAsync(e->h_results, e->d_results.p, sizeof(p3_infer_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
+  if (!e->results_to_host)
+    P3_CUDA(cudaMemcpyAsync(e->h_results, e->d_results.p, sizeof(p3_infer_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
   P3_CUDA(cudaStreamSynchronize(e->stream));
   return P3_OK;
 }

@@ -278,9 +278,10 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
       // outcome = softmax(o[0:2]) (model.py:1266); [0] = loss, [1] = win (leaf_evaluator.cc:92-93)
       const float m = fmaxf(s_o[0], s_o[1]);
       const float e0 = expf(s_o[0] - m), e1 = expf(s_o[1] - m);
-      res.value_probs[0] = e0 / (e0 + e1);
-      res.value_probs[1] = e1 / (e0 + e1);
-      aux.value = res.value_probs[1] - res.value_probs[0];
+      const float p_loss = e0 / (e0 + e1), p_win = e1 / (e0 + e1);  // (`res` may be mapped host memory: never read it back)
+      res.value_probs[0] = p_loss;
+      res.value_probs[1] = p_win;
+      aux.value = p_win - p_loss;
       aux.outcome_logits[0] = s_o[0];
       aux.outcome_logits[1] = s_o[1];
       aux.gamma = s_misc[1];
@@ -290,7 +291,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
         aux.q_score[k] = s_o[8 + k];
         aux.q_score_err[k] = fabsf(s_o[11 + k]);            // model.py:961-963
       }
-      res.err2_outcome = aux.q_err[0];                      // 12:q6_err (trt_names.h:19)
+      res.err2_outcome = 4.0f * sigmoid_f32(s_o[5]);        // 12:q6_err (trt_names.h:19)
     }
     group_sync(g);  // the group's shared arrays are reused by its next position
   }

@@ -5,7 +5,9 @@
 // LoadBatch / GetBatch calls spread over `threads` host threads the way NNInterface's workers issue them
 // (cc/nn/nn_interface.cc:245-277, cc/nn/nn_interface.h:251-290).
 #include <chrono>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -16,18 +18,67 @@ namespace {
 using Clock = std::chrono::steady_clock;
 double us_since(Clock::time_point t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); }
 
-void parallel_for(int n, int threads, const std::function<void(int)>& fn) {
-  if (threads <= 1) {
-    for (int i = 0; i < n; ++i) fn(i);
-    return;
+// Persistent worker threads, as the search threads that call NNInterface::LoadBatch / GetBatch are
+// (cc/nn/nn_interface.cc:245-277): run(n, fn) hands out indices i = t, t + threads, ... and returns when all are done.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int threads) : threads_(threads < 1 ? 1 : threads) {
+    for (int t = 1; t < threads_; ++t) pool_.emplace_back([this, t]() { Loop(t); });
   }
-  std::vector<std::thread> pool;
-  for (int t = 0; t < threads; ++t)
-    pool.emplace_back([=, &fn]() {
-      for (int i = t; i < n; i += threads) fn(i);
-    });
-  for (auto& th : pool) th.join();
-}
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++generation_;
+    }
+    cv_.notify_all();
+    for (auto& th : pool_) th.join();
+  }
+  void run(int n, const std::function<void(int)>& fn) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      n_ = n;
+      pending_ = threads_ - 1;
+      ++generation_;
+    }
+    cv_.notify_all();
+    for (int i = 0; i < n; i += threads_) fn(i);  // the caller is worker 0
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this]() { return pending_ == 0; });
+  }
+
+ private:
+  void Loop(int t) {
+    unsigned long long seen = 0;
+    while (true) {
+      const std::function<void(int)>* fn;
+      int n;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return generation_ != seen; });
+        seen = generation_;
+        if (stop_) return;
+        fn = fn_;
+        n = n_;
+      }
+      for (int i = t; i < n; i += threads_) (*fn)(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --pending_;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  const int threads_;
+  std::vector<std::thread> pool_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_ = 0, pending_ = 0;
+  unsigned long long generation_ = 0;
+  bool stop_ = false;
+};
 }  // namespace
 
 extern "C" {
@@ -40,6 +91,7 @@ int p3_host_benchmark(const char* weights_path, int device, int batch, int versi
                       const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
   auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
   std::vector<nn::NNInferResult> results(batch);
+  WorkerPool pool(threads);
   double t_run = 0, t_load = 0, t_get = 0, t_cycle = 0, checksum = 0;
   int cursor = 0;
   for (int it = 0; it < warmup + steps; ++it) {
@@ -47,13 +99,13 @@ int p3_host_benchmark(const char* weights_path, int device, int batch, int versi
     const int base = cursor;
     cursor = (cursor + batch) % n_positions;
     auto c0 = Clock::now();
-    parallel_for(batch, threads, [&](int b) { engine->LoadBatch(b, positions[(base + b) % n_positions]); });
+    pool.run(batch, [&](int b) { engine->LoadBatch(b, positions[(base + b) % n_positions]); });
     const double load_us = us_since(c0);
     auto r0 = Clock::now();
     engine->RunInference();
     const double run_us = us_since(r0);
     auto g0 = Clock::now();
-    parallel_for(batch, threads, [&](int b) { engine->GetBatch(b, results[b]); });
+    pool.run(batch, [&](int b) { engine->GetBatch(b, results[b]); });
     const double get_us = us_since(g0);
     const double cycle_us = us_since(c0);
     if (timed) {
