@@ -6,10 +6,14 @@ in third-party modules that are absent here — TensorFlow 2.16.2 / Keras 3 (``r
 Conv2D, BatchNormalization, Dense, mish, softmax, softplus, tanh, sigmoid) and TensorRT 10 — so
 their published definitions are restated and each function cites the reference call site.
 
-PARITY UNPINNED for floating point: the reference holds no golden numeric vectors for the net
-(its model tests check shapes / normalisation only, ``python/test/model_v1_test.py:74-279``) and
-TensorFlow cannot be imported here, so this restatement is anchored on the reference's call sites
-only.  (Integer features / masks / PRNG are pinned separately: oracle/features_oracle.c.)
+PARITY PINNED against the reference's own model code: tests/golden/model_golden.npz holds the outputs of the UNMODIFIED
+``python/model.py`` (``P3achyGoModel.create(...)`` + ``call``) run in this container in float64 on ``oracle/tf_shim`` (a
+restatement of the TensorFlow / Keras calls model.py makes, since those libraries cannot be installed here), with this repo's
+seeded weights on committed golden positions (generator: tests/golden/make_model_golden.py).  tests/test_model_golden.py
+checks this restatement against that fixture to 1e-9 on all 25 outputs for every BASELINE config.  What stays unpinned is
+only TensorFlow's own kernel arithmetic (conv / matmul rounding order), which no restatement can pin without TensorFlow; the
+reference's own tests hold no numeric vectors for it (``python/test/model_v1_test.py:74-279`` checks shapes / ranges).
+(Integer features / masks / PRNG are pinned separately: oracle/features_oracle.c.)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 """

@@ -188,3 +188,44 @@ def test_full_size_properties(weight_dir, golden_positions):
             assert np.abs(np.asarray(r32["value_probs"]) - np.asarray(big_res[b]["value_probs"])).max() < BF16_TOL["value"]
     small.close()
     ref32.close()
+
+
+# ---- the engine against the reference's own model code (tests/golden/model_golden.npz, see tests/test_model_golden.py)
+_GOLDEN_MAP = [("move_logits", "res", "pi_logits"), ("move_probs", "res", "pi"), ("value_probs", "res", "outcome"),
+               ("score_probs", "res", "score_probs"), ("pi_logits_aux", "aux", "pi_logits_aux"),
+               ("pi_logits_soft", "aux", "pi_logits_soft"), ("pi_logits_optimistic", "aux", "pi_logits_optimistic"),
+               ("outcome_logits", "aux", "outcome_logits"), ("score_logits", "aux", "score_logits"), ("gamma", "aux", "gamma"),
+               ("mcts_dist_probs", "aux", "mcts_dist_probs"), ("ownership", "aux", "own")]
+
+
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("config", ["tiny", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic"])
+def test_engine_matches_reference_model_golden(config, precision_name, weight_dir, golden_positions):
+    """The CUDA engine on the positions / weights of the fixture produced by the reference's unmodified python/model.py
+    (float64, on oracle/tf_shim).  fp32 engine: max-abs 1e-3 (north star); bf16 engine: the documented bound."""
+    import os
+    from p3achygo_b200 import engine as E
+    if config == "tiny" and precision_name == "bf16":
+        pytest.skip("tiny (C=16) is below the tensor-core tile sizes; bf16 engine reports UNSUPPORTED (tested above)")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_golden.npz"))
+    first, n = (int(v) for v in z[f"{config}/first"])
+    path, cfg, tensors = weight_dir(config)
+    feats = golden_positions["feats"][first:first + n]
+    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    eng, res, aux = _run_engine(path, feats, prec)
+    tl, tp, tv = (FP32_TOL, FP32_TOL, FP32_TOL) if precision_name == "fp32" else (BF16_TOL["logits"], BF16_TOL["probs"], BF16_TOL["value"])
+    tol_of = {"move_logits": tl, "pi_logits_aux": tl, "pi_logits_soft": tl, "pi_logits_optimistic": tl, "outcome_logits": tl,
+              "score_logits": 4 * tl, "gamma": tl, "move_probs": tp, "score_probs": tp, "mcts_dist_probs": tp, "value_probs": tv,
+              "ownership": tv}
+    worst = {}
+    for field, src, gname in _GOLDEN_MAP:
+        got = np.stack([np.asarray((res if src == "res" else aux)[b][field], dtype=np.float64) for b in range(n)]).reshape(n, -1)
+        ref = z[f"{config}/{gname}"].reshape(n, -1)
+        worst[field] = (float(np.abs(got - ref).max()), tol_of[field])
+    bad = {k: v for k, v in worst.items() if not v[0] <= v[1]}
+    assert not bad, f"out of tolerance vs the reference model code: {bad}\nall: {worst}"
+    q = np.stack([np.asarray(aux[b]["q"], dtype=np.float64) for b in range(n)])
+    for k, nm in enumerate(("q6", "q16", "q50")):
+        assert np.abs(q[:, k] - z[f"{config}/{nm}"].reshape(n)).max() <= tv
+    print(config, precision_name, "worst vs reference model code:", {k: f"{v[0]:.2e}" for k, v in worst.items()})
+    eng.close()
