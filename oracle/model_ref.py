@@ -86,6 +86,11 @@ class RefModel:
             y = self.conv_pre_act(convs[0][0], y)
             y = self.broadcast(f"{block_tag(self.cfg, i)}/01:broadcast", y)
             y = self.conv_pre_act(convs[1][0], y)
+        elif self.cfg.trunk_block_type == "nbt":  # NbtResidualBlock (model.py:431-470): two nested classic blocks at Cb
+            t = self.conv_pre_act(convs[0][0], y)
+            t = t + self.conv_pre_act(convs[2][0], self.conv_pre_act(convs[1][0], t))
+            t = t + self.conv_pre_act(convs[4][0], self.conv_pre_act(convs[3][0], t))
+            y = self.conv_pre_act(convs[5][0], t)
         else:  # Bottleneck (model.py:372-412) / Classic (model.py:330-354)
             for tag, _, _, _ in convs:
                 y = self.conv_pre_act(tag, y)

@@ -142,7 +142,7 @@ struct p3_engine {
   // device IO
   DevBuf d_feats, d_planes, d_scalars, d_masks, d_results, d_aux;
   // activations
-  DevBuf xraw, actA, actB, actS0, actS1, pgv;
+  DevBuf xraw, actA, actB, actS0, actS1, rawB, pgv;
   // weights
   DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
   bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
@@ -325,9 +325,9 @@ struct Builder {
   }
 };
 
-std::string block_tag(int i, bool bcast, bool btl) {
+std::string block_tag(int i, bool bcast, bool btl, bool nbt = false) {
   char buf[64];
-  std::snprintf(buf, sizeof buf, "model/trunk/%02d:%s", i, bcast ? "broadcast_res" : (btl ? "bottleneck_res" : "classic_res"));
+  std::snprintf(buf, sizeof buf, "model/trunk/%02d:%s", i, bcast ? "broadcast_res" : (btl ? "bottleneck_res" : (nbt ? "nbt_res" : "classic_res")));
   return buf;
 }
 std::string sub_tag(const std::string& base, int j, const char* kind) {
@@ -350,13 +350,14 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   const int ksz = wf.meta_or("conv_size", 3);
   const int bint = wf.meta_or("broadcast_interval", 1 << 30);
   const bool btl = wf.meta_or("trunk_block_type", 0) == 0;
+  const bool nbt = wf.meta_or("trunk_block_type", 0) == 2;  // NbtResidualBlock, python/model.py:431-470
   if (wf.meta_or("board_len", 19) != 19) return fail(P3_ERR_UNSUPPORTED, "only 19x19 boards are supported");
   if (C <= 0 || e.blocks <= 0 || Ch <= 0 || Cv <= 0) return fail(P3_ERR_IO, "weight file metadata incomplete");
   if (e.version == 1 && (P != 15 || e.nscalars != 8)) return fail(P3_ERR_UNSUPPORTED, "feature version 1 needs 15 planes / 8 scalars");
   if (e.version == 0 && (P != 13 || e.nscalars != 7)) return fail(P3_ERR_UNSUPPORTED, "feature version 0 needs 13 planes / 7 scalars");
   if (e.bf16) {
     bool ok = tc_conv_supported(C, C) && tc_conv_supported(C, 3 * Ch);
-    if (btl) ok = ok && tc_conv_supported(C, Cb) && tc_conv_supported(Cb, Cb) && tc_conv_supported(Cb, C);
+    if (btl || nbt) ok = ok && tc_conv_supported(C, Cb) && tc_conv_supported(Cb, Cb) && tc_conv_supported(Cb, C);
     if (!ok) return fail(P3_ERR_UNSUPPORTED, "P3_PRECISION_BF16 needs channel counts that are multiples of 64 "
                                              "(and 3*head_channels a multiple of 32); use P3_PRECISION_FP32 for this net");
   }
@@ -381,7 +382,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   if ((rc = e.xraw.alloc((e.bf16 ? sizeof(__half) : sizeof(float)) * R * C))) return rc;
   if ((rc = e.actA.alloc(esz * R * C))) return rc;
   if ((rc = e.actB.alloc(esz * R * C))) return rc;
-  if (btl) {
+  if (nbt) {  // Cb-wide raw stream of the nested classic blocks (fp16 in the bf16 engine, like the trunk stream)
+    if ((rc = e.rawB.alloc((e.bf16 ? sizeof(__half) : sizeof(float)) * R * Cb))) return rc;
+    P3_CUDA(cudaMemset(e.rawB.p, 0, e.rawB.bytes));
+  }
+  if (btl || nbt) {
     if ((rc = e.actS0.alloc(esz * R * Cb))) return rc;
     if ((rc = e.actS1.alloc(esz * R * Cb))) return rc;
     P3_CUDA(cudaMemset(e.actS0.p, 0, e.actS0.bytes));
@@ -442,10 +447,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   for (int i = 0; i < e.blocks; ++i) {
     const bool bcast = (i % bint) == bint - 1;  // model.py:1003
     blocks[i].bcast = bcast;
-    const std::string bt = block_tag(i, bcast, btl);
+    const std::string bt = block_tag(i, bcast, btl, nbt);
     std::vector<int> idx;
     if (bcast) idx = {0, 2};
     else if (btl) for (int j = 0; j < nbtl + 2; ++j) idx.push_back(j);
+    else if (nbt) idx = {0, 1, 2, 3, 4, 5};
     else idx = {0, 1};
     for (int j : idx) {
       const std::string tag = sub_tag(bt, j, "conv_block");
@@ -635,6 +641,16 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       } else if ((rc = add_conv(ex, s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) {
         return rc;
       }
+    } else if (nbt) {  // NbtResidualBlock, model.py:431-470: 1x1 reduce, two classic blocks at Cb (inner residuals), 1x1 expand
+      void* s0 = e.actS0.p;
+      void* s1 = e.actS1.p;
+      void* tb = e.rawB.p;
+      if ((rc = add_conv(bk.convs[0], cur, nullptr, tb, s0, kActMishBN, bk.convs[1]))) return rc;   // t, mish(BN(t))
+      if ((rc = add_conv(bk.convs[1], s0, nullptr, nullptr, s1, kActMishBN, bk.convs[2]))) return rc;
+      if ((rc = add_conv(bk.convs[2], s1, tb, tb, s0, kActMishBN, bk.convs[3]))) return rc;          // t += nbt_res0(t)
+      if ((rc = add_conv(bk.convs[3], s0, nullptr, nullptr, s1, kActMishBN, bk.convs[4]))) return rc;
+      if ((rc = add_conv(bk.convs[4], s1, tb, nullptr, s0, kActMishBN, bk.convs[5]))) return rc;     // t += nbt_res1(t), only its activation is needed
+      if ((rc = add_conv(bk.convs[5], s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) return rc;
     } else {  // ClassicResidualBlock, model.py:330-354
       if ((rc = add_conv(bk.convs[0], cur, nullptr, nullptr, other, kActMishBN, bk.convs[1]))) return rc;
       // second conv reads `other`; `cur` is free again and becomes the block output
@@ -735,6 +751,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     for (int i = 0; i < e.blocks; ++i) {
       if (blocks[i].bcast) mac += 2.0 * C * C * Pn + C * Pn * Pn;
       else if (btl) mac += (2.0 * C * Cb + nbtl * 9.0 * Cb * Cb) * Pn;
+      else if (nbt) mac += (2.0 * C * Cb + 4 * 9.0 * Cb * Cb) * Pn;
       else mac += 18.0 * C * C * Pn;
     }
     mac += 2.0 * C * Ch * Pn + 4.0 * Ch * Pn + 2.0 * Ch * (Ch + 4);

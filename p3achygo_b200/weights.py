@@ -33,7 +33,7 @@ import numpy as np
 MAGIC = b"P3ACHYW1"
 BOARD_LEN = 19
 NUM_LOCS = 361
-TRUNK_BTL, TRUNK_CLASSIC = 0, 1
+TRUNK_BTL, TRUNK_CLASSIC, TRUNK_NBT = 0, 1, 2
 
 
 @dataclasses.dataclass(frozen=True)
@@ -67,6 +67,8 @@ class ModelConfig:
                 mac += 2 * C * C * P + C * P * P
             elif self.trunk_block_type == "btl":
                 mac += (2 * C * Cb + self.inner_bottleneck_layers * k * k * Cb * Cb) * P
+            elif self.trunk_block_type == "nbt":  # NbtResidualBlock: 1x1, two classic blocks of two convs at Cb, 1x1
+                mac += (2 * C * Cb + 4 * k * k * Cb * Cb) * P
             else:
                 mac += 2 * k * k * C * C * P
         mac += 2 * C * Ch * P + 4 * Ch * P + 2 * Ch * (Ch + 4)
@@ -82,6 +84,8 @@ class ModelConfig:
                 mac += 2 * C * C * P + C * P * P
             elif self.trunk_block_type == "btl":
                 mac += (2 * C * Cb + self.inner_bottleneck_layers * k * k * Cb * Cb) * P
+            elif self.trunk_block_type == "nbt":
+                mac += (2 * C * Cb + 4 * k * k * Cb * Cb) * P
             else:
                 mac += 2 * k * k * C * C * P
         return 2.0 * mac
@@ -102,6 +106,13 @@ CONFIGS: Dict[str, ModelConfig] = {
                                channels=384, bottleneck_channels=192, head_channels=32, c_val=80),
     "b15c192_classic": ModelConfig("b15c192_classic", blocks=15, broadcast_interval=6, channels=192,
                                    head_channels=32, c_val=80, trunk_block_type="classic"),
+    # nested-bottleneck nets (python/model_config.py:131-163, NbtResidualBlock python/model.py:431-470)
+    "b8c128nbt": ModelConfig("b8c128nbt", blocks=8, broadcast_interval=3, channels=128, bottleneck_channels=64,
+                             head_channels=32, trunk_block_type="nbt"),
+    "b12c256nbt": ModelConfig("b12c256nbt", blocks=12, broadcast_interval=3, channels=256, bottleneck_channels=128,
+                              head_channels=32, c_val=80, trunk_block_type="nbt"),
+    "b10c384nbt": ModelConfig("b10c384nbt", blocks=10, broadcast_interval=4, channels=384, bottleneck_channels=192,
+                              head_channels=32, c_val=80, trunk_block_type="nbt"),
 }
 
 
@@ -120,6 +131,8 @@ def block_tag(cfg: ModelConfig, i: int) -> str:
         return f"model/trunk/{i:02d}:broadcast_res"
     if cfg.trunk_block_type == "btl":
         return f"model/trunk/{i:02d}:bottleneck_res"
+    if cfg.trunk_block_type == "nbt":
+        return f"model/trunk/{i:02d}:nbt_res"
     return f"model/trunk/{i:02d}:classic_res"
 
 
@@ -136,6 +149,10 @@ def block_convs(cfg: ModelConfig, i: int):
             out.append((f"{t}/{j + 1:02d}:conv_block", Cb, Cb, k))
         out.append((f"{t}/{cfg.inner_bottleneck_layers + 1:02d}:conv_block", Cb, C, 1))
         return out
+    if cfg.trunk_block_type == "nbt":
+        # reduce 1x1, nbt_res0 = two convs, nbt_res1 = two convs (each with its own inner residual), expand 1x1; flattened 0..5
+        return ([(f"{t}/00:conv_block", C, Cb, 1)] + [(f"{t}/{j:02d}:conv_block", Cb, Cb, k) for j in range(1, 5)] +
+                [(f"{t}/05:conv_block", Cb, C, 1)])
     return [(f"{t}/00:conv_block", C, C, k), (f"{t}/01:conv_block", C, C, k)]
 
 
@@ -203,7 +220,7 @@ def config_meta(cfg: ModelConfig) -> Dict[str, int]:
         "board_len": BOARD_LEN,
         "conv_size": cfg.conv_size,
         "broadcast_interval": cfg.broadcast_interval,
-        "trunk_block_type": TRUNK_BTL if cfg.trunk_block_type == "btl" else TRUNK_CLASSIC,
+        "trunk_block_type": {"btl": TRUNK_BTL, "classic": TRUNK_CLASSIC, "nbt": TRUNK_NBT}[cfg.trunk_block_type],
     }
 
 
@@ -213,7 +230,7 @@ def config_from_meta(meta: Dict[str, int], name: str = "from_file") -> ModelConf
         broadcast_interval=meta["broadcast_interval"], inner_bottleneck_layers=meta["nbtl"],
         channels=meta["nchannels"], bottleneck_channels=meta["nbtl_channels"],
         head_channels=meta["nhead_channels"], c_val=meta["nval_channels"],
-        trunk_block_type="btl" if meta["trunk_block_type"] == TRUNK_BTL else "classic",
+        trunk_block_type={TRUNK_BTL: "btl", TRUNK_CLASSIC: "classic", TRUNK_NBT: "nbt"}[meta["trunk_block_type"]],
         num_input_planes=meta["ninput_planes"], num_input_features=meta["ninput_features"])
 
 
@@ -237,7 +254,7 @@ def synthetic_weights(cfg: ModelConfig, seed: int = 0) -> Dict[str, np.ndarray]:
             if "/trunk/" in name and "conv_block" in name:
                 last = int(name.split("/")[3].split(":")[0])
                 n_convs = len(block_convs(cfg, int(name.split("/")[2].split(":")[0])))
-                is_last = last == (2 if "broadcast_res" in name else n_convs - 1)
+                is_last = last == (2 if "broadcast_res" in name else n_convs - 1) or ("nbt_res" in name and last in (2, 4))
                 gain = 0.1 if is_last else 1.5
             elif "broadcast/dense" in name:
                 gain = 0.5

@@ -73,7 +73,7 @@ def _compare(res, aux, o, tol_logits, tol_probs, tol_value, tol_smean):
     return worst
 
 
-@pytest.mark.parametrize("config,n", [("tiny", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b15c192_classic", 3)])
+@pytest.mark.parametrize("config,n", [("tiny", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b15c192_classic", 3), ("b8c128nbt", 4)])
 def test_fp32_engine_matches_oracle(config, n, weight_dir, golden_positions):
     from p3achygo_b200 import engine as E
     path, cfg, tensors = weight_dir(config)
@@ -92,7 +92,8 @@ def test_fp32_engine_matches_oracle(config, n, weight_dir, golden_positions):
     eng.close()
 
 
-@pytest.mark.parametrize("config,n", [("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2), ("b15c192_classic", 3)])
+@pytest.mark.parametrize("config,n", [("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2), ("b15c192_classic", 3), ("b8c128nbt", 4),
+                                      ("b12c256nbt", 2)])
 def test_bf16_engine_within_documented_bound(config, n, weight_dir, golden_positions):
     from p3achygo_b200 import engine as E
     path, cfg, tensors = weight_dir(config)
@@ -199,7 +200,7 @@ _GOLDEN_MAP = [("move_logits", "res", "pi_logits"), ("move_probs", "res", "pi"),
 
 
 @pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("config", ["tiny", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic"])
+@pytest.mark.parametrize("config", ["tiny", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic", "b8c128nbt"])
 def test_engine_matches_reference_model_golden(config, precision_name, weight_dir, golden_positions):
     """The CUDA engine on the positions / weights of the fixture produced by the reference's unmodified python/model.py
     (float64, on oracle/tf_shim).  fp32 engine: max-abs 1e-3 (north star); bf16 engine: the documented bound."""
