@@ -131,6 +131,13 @@ void p3_engine_destroy(p3_engine* e);
  * (cc/nn/nn_interface.cc:276). Copies the 1860-byte game state into pinned staging. */
 int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* features);
 
+/* NNInterface::LoadBatch + GetBatch symmetry handling moved onto the GPU (cc/nn/nn_interface.cc:245-277,
+ * cc/nn/nn_interface.h:263-287): `features` are in the game's own (identity) orientation and `sym` is the
+ * game::Symmetry (0..7, cc/game/symmetry.h) the caller would have applied.  The encode kernel applies it to the board,
+ * the derived grids and the last moves (passes / no-ops untouched); the heads kernel un-applies it on the 361 board
+ * entries of move_logits, move_probs and opt_move_probs, so GetBatch returns what NNInterface::GetBatch would. */
+int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* features, int sym);
+
 /* nn::Engine::RunInference, cc/nn/engine/engine.h:36 (cc/nn/engine/trt_engine.cc:238-304).
  * H2D(game state) -> encode -> tower -> heads -> D2H(results) -> stream sync. Always the full batch. */
 int p3_engine_run_inference(p3_engine* e);

@@ -109,7 +109,27 @@ struct EncodeExtra {
   const float* gs_b = nullptr;       // [C]
   int C = 0;
   float* gs_out = nullptr;           // [n][C]
+  const int8_t* sym = nullptr;       // [n] game::Symmetry to apply to each slot's (identity-orientation) features, or null
 };
+
+// Dihedral-8 index maps of cc/game/symmetry.cc:11-80 on the 19x19 grid (0 identity, 1-3 rot90/180/270, 4 flip, 5-7 flip then rot).
+__host__ __device__ inline int sym_rot(int idx, int r) {  // r: 0 = 90, 1 = 180, 2 = 270 (symmetry.cc:20-34)
+  const int i = idx / 19, j = idx % 19;
+  return r == 0 ? j * 19 + (18 - i) : r == 1 ? (18 - i) * 19 + (18 - j) : (18 - j) * 19 + i;
+}
+__host__ __device__ inline int sym_flip(int idx) { return (idx / 19) * 19 + (18 - idx % 19); }
+__host__ __device__ inline int sym_transform_index(int sym, int idx) {  // TransformIndex, symmetry.cc:36-57
+  if (sym == 0) return idx;
+  if (sym <= 3) return sym_rot(idx, sym - 1);
+  if (sym == 4) return sym_flip(idx);
+  return sym_rot(sym_flip(idx), sym - 5);
+}
+__host__ __device__ inline int sym_transform_inv(int sym, int idx) {  // TransformInv, symmetry.cc:59-80
+  if (sym == 0) return idx;
+  if (sym <= 3) return sym_rot(idx, 3 - sym);
+  if (sym == 4) return sym_flip(idx);
+  return sym_flip(sym_rot(idx, 7 - sym));
+}
 int encode_launch(const p3_go_features* feats, int n, int version, float* planes, float* scalars,
                   uint16_t* masks, cudaStream_t stream, const EncodeExtra* extra = nullptr);
 int liberties_launch(const int8_t* boards, int n, int8_t* out, cudaStream_t stream);
@@ -170,8 +190,10 @@ struct HeadWeights {
   const float* scores;                         // [800]
 };
 // pgv [n*400, 3*Ch] fp32 (p | g | v); results/aux device arrays of n.
+// sym (optional, [n]): the symmetry each slot's input was rotated by; move_logits / move_probs / opt_move_probs come back
+// un-rotated (ApplyInverse, cc/nn/nn_interface.h:263-287), the pass entry untouched.
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream, bool accurate = true);
+                 cudaStream_t stream, bool accurate = true, const int8_t* sym = nullptr);
 
 // ---- gumbel (gumbel.cu) --------------------------------------------------------------------------------------
 int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,

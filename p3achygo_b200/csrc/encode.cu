@@ -35,13 +35,17 @@ __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __res
   const p3_go_features& f = *reinterpret_cast<const p3_go_features*>(s_raw);
   const int bsize = f.bsize;
   const int8_t color = f.color;
+  // ApplySymmetry (cc/game/symmetry.h:42-51): sym_grid[T(i)] = grid[i], i.e. output point p reads source point Tinv(p);
+  // the caller hands over identity-orientation features when it gives a symmetry (NNInterface::LoadBatch, nn_interface.cc:245-277)
+  const int sym = ex.sym ? ex.sym[b] : 0;
 
   // plane bits per point: FillPlanePair (buf_utils.h:57-76) reads grid[i*bsize + j] for i, j < bsize
   for (int p = threadIdx.x; p < P3_NUM_BOARD_LOCS; p += blockDim.x) {
     const int i = p / P3_BOARD_LEN, j = p % P3_BOARD_LEN;
+    const int sp = sym_transform_inv(sym, p), si = sp / P3_BOARD_LEN, sj = sp % P3_BOARD_LEN;
     uint32_t m = 0;
-    if (i < bsize && j < bsize) {
-      const int src_idx = i * bsize + j;
+    if (si < bsize && sj < bsize) {
+      const int src_idx = si * bsize + sj;
       auto pair = [&](const int8_t* grid, int ours, int theirs) {
         const int8_t c = grid[src_idx];
         if (c == color) m |= 1u << ours;
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __res
 #pragma unroll
     for (int k = 0; k < P3_NUM_LAST_MOVES; ++k) {  // :27-36, skips noop {-1,-1} and pass {19,0}
       const p3_loc lm = f.last_moves[k];
-      if (lm.i >= 0 && lm.i < P3_BOARD_LEN && lm.j >= 0 && lm.j < P3_BOARD_LEN && lm.i * P3_BOARD_LEN + lm.j == p)
+      if (lm.i >= 0 && lm.i < P3_BOARD_LEN && lm.j >= 0 && lm.j < P3_BOARD_LEN && lm.i * P3_BOARD_LEN + lm.j == sp)
         m |= 1u << (k + 2);
     }
     s_mask[p] = static_cast<uint16_t>(m);

@@ -139,6 +139,7 @@ struct p3_engine {
   // host staging (pinned)
   p3_go_features* h_feats = nullptr;
   p3_infer_result* h_results = nullptr;
+  int8_t* h_sym = nullptr;  // per-slot game::Symmetry of p3_engine_load_batch_sym (0 = features already oriented by the caller)
   // device IO
   DevBuf d_feats, d_planes, d_scalars, d_masks, d_results, d_aux;
   // activations
@@ -147,7 +148,7 @@ struct p3_engine {
   DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
   bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
   bool init_tc = false;    // init conv as a tcgen05 implicit GEMM over the plane masks (init_tc.cu)
-  DevBuf init_wt_tc, d_masks_pad, d_gs;
+  DevBuf init_wt_tc, d_masks_pad, d_gs, d_sym;
   InitTcPlan* init_plan = nullptr;
   EncodeExtra enc_extra;
   std::vector<std::unique_ptr<ConvLayer>> layers;
@@ -181,6 +182,7 @@ struct p3_engine {
     if (stream) cudaStreamDestroy(stream);
     if (h_feats) cudaFreeHost(h_feats);
     if (h_results) cudaFreeHost(h_results);
+    if (h_sym) cudaFreeHost(h_sym);
   }
 
   const float* dev_vec(const std::vector<float>& v, int* rc) {
@@ -221,7 +223,7 @@ struct p3_engine {
     int rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[0], stream));
     rc = encode_launch(d_feats.as<p3_go_features>(), batch, version, d_planes.as<float>(), d_scalars.as<float>(),
-                       d_masks.as<uint16_t>(), stream, init_tc ? &enc_extra : nullptr);
+                       d_masks.as<uint16_t>(), stream, &enc_extra);
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[1], stream));
     rc = run_init();
@@ -236,7 +238,7 @@ struct p3_engine {
     rc = run_conv(head_step);
     if (rc) return rc;
     rc = heads_launch(pgv.as<float>(), batch, hw, to_host ? h_results : d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(),
-                      stream, !bf16);
+                      stream, !bf16, d_sym.as<int8_t>());
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
     return P3_OK;
@@ -371,6 +373,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   std::memset(e.h_feats, 0, sizeof(p3_go_features) * B);
   for (int b = 0; b < B; ++b) { e.h_feats[b].bsize = 19; e.h_feats[b].color = P3_BLACK; }
   std::memset(e.h_results, 0, sizeof(p3_infer_result) * B);
+  P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e.h_sym), B));
+  std::memset(e.h_sym, 0, B);
+  if ((rc = e.d_sym.alloc(B))) return rc;
+  P3_CUDA(cudaMemset(e.d_sym.p, 0, B));
+  e.enc_extra.sym = e.d_sym.as<int8_t>();
   if ((rc = e.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
   P3_CUDA(cudaMemcpy(e.d_feats.p, e.h_feats, sizeof(p3_go_features) * B, cudaMemcpyHostToDevice));
   if ((rc = e.d_planes.alloc(sizeof(float) * B * 361 * P))) return rc;
@@ -819,6 +826,15 @@ void p3_engine_destroy(p3_engine* e) {
 int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* features) {
   if (!e || !features || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "load_batch: bad argument");
   std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
+  e->h_sym[batch_id] = 0;
+  return P3_OK;
+}
+
+int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* features, int sym) {
+  if (!e || !features || batch_id < 0 || batch_id >= e->batch || sym < 0 || sym > 7)
+    return fail(P3_ERR_INVALID_ARG, "load_batch_sym: bad argument");
+  std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
+  e->h_sym[batch_id] = static_cast<int8_t>(sym);
   return P3_OK;
 }
 
@@ -826,6 +842,7 @@ int p3_engine_run_inference(p3_engine* e) {
   if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
+  P3_CUDA(cudaMemcpyAsync(e->d_sym.p, e->h_sym, e->batch, cudaMemcpyHostToDevice, e->stream));
   int rc = e->enqueue_device_maybe_graph(e->results_to_host);
   if (rc) return rc;
   if (!e->results_to_host)
@@ -886,6 +903,7 @@ int p3_engine_upload(p3_engine* e) {
   if (!e) return fail(P3_ERR_INVALID_ARG, "upload: null engine");
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
+  P3_CUDA(cudaMemcpyAsync(e->d_sym.p, e->h_sym, e->batch, cudaMemcpyHostToDevice, e->stream));
   P3_CUDA(cudaStreamSynchronize(e->stream));
   return P3_OK;
 }
@@ -904,7 +922,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   auto rec = [&]() { return cudaEventRecord(evs[idx++], e->stream); };
   P3_CUDA(rec());
   rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
-                     e->d_masks.as<uint16_t>(), e->stream, e->init_tc ? &e->enc_extra : nullptr);
+                     e->d_masks.as<uint16_t>(), e->stream, &e->enc_extra);
   cls.push_back(0); fl.push_back(0.0);
   P3_CUDA(rec());
   if (!rc) rc = e->run_init();
@@ -929,7 +947,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   if (!rc) rc = e->run_conv(e->head_step);
   cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
   P3_CUDA(rec());
-  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16);
+  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16, e->d_sym.as<int8_t>());
   cls.push_back(6); fl.push_back(0.0);
   P3_CUDA(rec());
   P3_CUDA(cudaStreamSynchronize(e->stream));

@@ -36,14 +36,18 @@ __device__ __forceinline__ float group_reduce(float v, bool is_max, float* s_scr
 }
 
 // softmax over s_in[0..n) -> out[0..n) (global), accurate expf as core::Softmax (vmath.h:169-178)
-__device__ void group_softmax(const float* s_in, int n, float* out, float* s_scratch, int g, int gtid) {
+// sym != 0: out[i] = p[T(sym, i)] for board points (ApplyInverse, cc/game/symmetry.h:53-62), the pass entry stays in place
+__device__ void group_softmax(const float* s_in, int n, float* out, float* s_scratch, int g, int gtid, int sym = 0) {
   float m = -INFINITY;
   for (int i = gtid; i < n; i += kGT) m = fmaxf(m, s_in[i]);
   m = group_reduce(m, true, s_scratch, g, gtid);
   float s = 0.0f;
   for (int i = gtid; i < n; i += kGT) s += expf(s_in[i] - m);
   s = group_reduce(s, false, s_scratch, g, gtid);
-  for (int i = gtid; i < n; i += kGT) out[i] = expf(s_in[i] - m) / s;
+  for (int i = gtid; i < n; i += kGT) {
+    const int src = (sym != 0 && i < P3_NUM_BOARD_LOCS) ? sym_transform_index(sym, i) : i;
+    out[i] = expf(s_in[src] - m) / s;
+  }
 }
 
 // Head weights staged once per CTA (shared by its 4 position groups): every dense layer then reads shared memory instead of
@@ -66,7 +70,7 @@ constexpr int kGroupFloats = 4 * P3_MAX_MOVES + P3_NUM_SCORE_LOGITS + 2 * kGT + 
 template <bool kAccurate>
 __global__ void __launch_bounds__(kThreads, 1)
 heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __restrict__ results,
-             p3_aux_result* __restrict__ auxs, int n) {
+             p3_aux_result* __restrict__ auxs, int n, const int8_t* __restrict__ syms) {
   extern __shared__ __align__(16) float hsm[];
   const int Ch = hw.Ch, Cv = hw.Cv, W3 = 3 * Ch;
   SmemWeights w;
@@ -117,6 +121,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
     const float* base = pgv + static_cast<size_t>(b) * kRowsPerPos * W3;
     p3_infer_result& res = results[b];
     p3_aux_result& aux = auxs[b];
+    const int sym = syms ? syms[b] : 0;
 
     // ---- pass 1: global pools.  g -> mish(BN(g)) (GlobalPoolBias, model.py:697-699), v raw (model.py:890)
     {
@@ -240,14 +245,14 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
 
     // ---- outputs
     for (int i = tid; i < P3_MAX_MOVES; i += kGT) {
-      res.move_logits[i] = s_logits[0][i];
+      res.move_logits[i] = s_logits[0][(sym != 0 && i < P3_NUM_BOARD_LOCS) ? sym_transform_index(sym, i) : i];
       aux.pi_logits_aux[i] = s_logits[1][i];
       aux.pi_logits_soft[i] = s_logits[2][i];
       aux.pi_logits_optimistic[i] = s_logits[3][i];
     }
     for (int i = tid; i < P3_NUM_SCORE_LOGITS; i += kGT) aux.score_logits[i] = s_score[i];
-    group_softmax(s_logits[0], P3_MAX_MOVES, res.move_probs, s_scratch, g, tid);          // 01:pi
-    group_softmax(s_logits[3], P3_MAX_MOVES, res.opt_move_probs, s_scratch, g, tid);      // trt_engine.cc:347
+    group_softmax(s_logits[0], P3_MAX_MOVES, res.move_probs, s_scratch, g, tid, sym);      // 01:pi
+    group_softmax(s_logits[3], P3_MAX_MOVES, res.opt_move_probs, s_scratch, g, tid, sym);  // trt_engine.cc:347
     group_softmax(s_score, P3_NUM_SCORE_LOGITS, res.score_probs, s_scratch, g, tid);      // 06:score_probs
     group_softmax(s_mcts, 51, aux.mcts_dist_probs, s_scratch, g, tid);                    // 24
     if (tid < 51) aux.mcts_dist_logits[tid] = s_mcts[tid];
@@ -300,7 +305,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
 }  // namespace
 
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream, bool accurate) {
+                 cudaStream_t stream, bool accurate, const int8_t* sym) {
   if (hw.Ch > kMaxCh || hw.Cv > kMaxCv || 2 * hw.Ch > kGT || hw.Ch % 4 != 0 || hw.Cv + 128 > kGT)
     return fail(P3_ERR_UNSUPPORTED, "heads: head channels / c_val not supported");
   const size_t smem = (static_cast<size_t>((heads_weight_floats(hw.Ch, hw.Cv) + 3) & ~3) + static_cast<size_t>(kGroups) * kGroupFloats) * sizeof(float);
@@ -312,8 +317,8 @@ int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(sms, (n + kGroups - 1) / kGroups);
-  if (accurate) heads_kernel<true><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n);
-  else heads_kernel<false><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n);
+  if (accurate) heads_kernel<true><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym);
+  else heads_kernel<false><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

@@ -96,6 +96,12 @@ class B200Engine:
         else:
             check(lib.p3_engine_load_batch(self._h, batch_id, ctypes.cast(ctypes.byref(features), ctypes.c_void_p)))
 
+    def LoadBatchSym(self, batch_id: int, features, sym: int) -> None:
+        """NNInterface::LoadBatch with the symmetry applied on the GPU (nn_interface.cc:245-277): ``features`` in the game's
+        own orientation, ``sym`` = game::Symmetry 0..7; GetBatch then returns the un-rotated policies (nn_interface.h:263-287)."""
+        arr = np.ascontiguousarray(np.asarray(features, dtype=GO_FEATURES_DTYPE).reshape(1))
+        check(lib.p3_engine_load_batch_sym(self._h, batch_id, ptr(arr), int(sym)))
+
     def RunInference(self) -> None:
         """engine.h:36"""
         check(lib.p3_engine_run_inference(self._h))

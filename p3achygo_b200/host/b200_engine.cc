@@ -33,6 +33,9 @@ std::unique_ptr<B200Engine> B200Engine::Create(std::string path, int batch_size,
 
 B200Engine::~B200Engine() { p3_engine_destroy(engine_); }
 void B200Engine::LoadBatch(int batch_id, const GoFeatures& features) { P3_CHECK(p3_engine_load_batch(engine_, batch_id, &features)); }
+void B200Engine::LoadBatchSym(int batch_id, const GoFeatures& features, int sym) {
+  P3_CHECK(p3_engine_load_batch_sym(engine_, batch_id, &features, sym));
+}
 void B200Engine::RunInference() { P3_CHECK(p3_engine_run_inference(engine_)); }
 void B200Engine::GetBatch(int batch_id, NNInferResult& result) { P3_CHECK(p3_engine_get_batch(engine_, batch_id, &result)); }
 void B200Engine::GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) {

@@ -19,6 +19,9 @@ class B200Engine final : public Engine {
   void RunInference() override;
   void GetBatch(int batch_id, NNInferResult& result) override;
   void GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) override;
+  // NNInterface::LoadBatch / GetBatch with the symmetry handled on the GPU (nn_interface.cc:245-277, nn_interface.h:263-287):
+  // features in the game's own orientation + the symmetry; GetBatch then returns the un-rotated policies.
+  void LoadBatchSym(int batch_id, const GoFeatures& features, int sym);
 
   p3_engine* handle() { return engine_; }
   int batch_size() const { return batch_size_; }

@@ -230,3 +230,56 @@ def test_engine_matches_reference_model_golden(config, precision_name, weight_di
         assert np.abs(q[:, k] - z[f"{config}/{nm}"].reshape(n)).max() <= tv
     print(config, precision_name, "worst vs reference model code:", {k: f"{v[0]:.2e}" for k, v in worst.items()})
     eng.close()
+
+
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+def test_symmetry_on_gpu_equals_host_symmetry(precision_name, weight_dir, golden_positions):
+    """p3_engine_load_batch_sym (symmetry applied by the encode kernel, un-applied by the heads kernel) against the
+    reference's host-side handling restated with the pinned oracle: ApplySymmetry on board / derived grids / last moves
+    before LoadBatch (cc/nn/nn_interface.cc:245-277), ApplyInverse on the 361 board entries of move_logits, move_probs and
+    opt_move_probs after GetBatch (cc/nn/nn_interface.h:263-287).  Same planes bit for bit, same results bit for bit."""
+    import ctypes
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200._lib import GO_FEATURES_DTYPE
+    L = oracle_lib.oracle()
+    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    feats = golden_positions["feats"][40:48]
+    B = 8
+    host = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=prec)
+    dev = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=prec)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for b in range(B):
+        sym = b  # all eight symmetries
+        f = np.array(feats[b:b + 1], dtype=GO_FEATURES_DTYPE)
+        fs = f.copy()
+        for grid in ("board", "stones_atari", "stones_two_liberties", "stones_three_liberties", "stones_laddered"):
+            src = np.ascontiguousarray(f[grid][0], dtype=np.int8)
+            dst = np.zeros(361, dtype=np.int8)
+            L.orc_apply_symmetry_i8(sym, vp(src), vp(dst))
+            fs[grid][0] = dst
+        for k in range(5):
+            i, j = (int(v) for v in f["last_moves"][0][k])
+            if 0 <= i < 19 and 0 <= j < 19:  # passes {19,0} and no-ops {-1,-1} are not transformed
+                t = L.orc_transform_index(sym, i * 19 + j)
+                fs["last_moves"][0][k] = (t // 19, t % 19)
+        host.LoadBatch(b, fs[0])
+        dev.LoadBatchSym(b, f[0], sym)
+    host.RunInference()
+    dev.RunInference()
+    for b in range(B):
+        ph, sh = host.GetPlanes(b)
+        pd, sd = dev.GetPlanes(b)
+        assert np.array_equal(ph, pd) and np.array_equal(sh, sd), f"planes differ for symmetry {b}"
+        rh, rd = host.GetBatch(b), dev.GetBatch(b)
+        for field in ("move_logits", "move_probs", "opt_move_probs"):
+            src = np.ascontiguousarray(np.asarray(rh[field], dtype=np.float32)[:361])
+            inv = np.zeros(361, dtype=np.float32)
+            L.orc_apply_inverse_f32(b, vp(src), vp(inv))
+            got = np.asarray(rd[field], dtype=np.float32)
+            assert np.array_equal(got[:361], inv), f"{field} differs for symmetry {b}"
+            assert got[361] == np.asarray(rh[field], dtype=np.float32)[361]
+        for field in ("value_probs", "score_probs", "err2_outcome"):
+            assert np.array_equal(np.asarray(rh[field]), np.asarray(rd[field]))
+    host.close()
+    dev.close()
