@@ -841,13 +841,25 @@ int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* f
 int p3_engine_run_inference(p3_engine* e) {
   if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
   P3_CUDA(cudaSetDevice(e->device));
+  static const bool trace = std::getenv("P3_TIME_RUN") != nullptr;  // perf experiments: where RunInference's wall time goes
+  if (trace) P3_CUDA(cudaEventRecord(e->ev[0], e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_sym.p, e->h_sym, e->batch, cudaMemcpyHostToDevice, e->stream));
+  if (trace) P3_CUDA(cudaEventRecord(e->ev[1], e->stream));
   int rc = e->enqueue_device_maybe_graph(e->results_to_host);
   if (rc) return rc;
+  if (trace) P3_CUDA(cudaEventRecord(e->ev[2], e->stream));
   if (!e->results_to_host)
     P3_CUDA(cudaMemcpyAsync(e->h_results, e->d_results.p, sizeof(p3_infer_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
+  if (trace) P3_CUDA(cudaEventRecord(e->ev[3], e->stream));
   P3_CUDA(cudaStreamSynchronize(e->stream));
+  if (trace) {
+    float h2d = 0, dev = 0, d2h = 0;
+    cudaEventElapsedTime(&h2d, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&dev, e->ev[1], e->ev[2]);
+    cudaEventElapsedTime(&d2h, e->ev[2], e->ev[3]);
+    std::fprintf(stderr, "[p3 run] h2d %.1f us  device %.1f us  d2h %.1f us\n", h2d * 1e3f, dev * 1e3f, d2h * 1e3f);
+  }
   return P3_OK;
 }
 
