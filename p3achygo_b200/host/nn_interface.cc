@@ -1,0 +1,249 @@
+#include "nn_interface.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "b200_engine.h"
+
+namespace nn {
+
+NNInterfaceB200::NNInterfaceB200(int num_threads, int64_t timeout_us, std::unique_ptr<Engine> engine)
+    : num_threads_(num_threads), timeout_us_(timeout_us), engine_(std::move(engine)), thread_info_(num_threads),
+      num_registered_threads_(num_threads) {
+  b200_ = dynamic_cast<B200Engine*>(engine_.get());
+  if (num_threads_ > 1) infer_thread_ = std::thread(&NNInterfaceB200::InferLoop, this);
+}
+
+NNInterfaceB200::~NNInterfaceB200() {  // nn_interface.cc:82-90
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    running_.store(false, std::memory_order_release);
+  }
+  infer_cv_.notify_all();
+  if (infer_thread_.joinable()) infer_thread_.join();
+}
+
+void NNInterfaceB200::RegisterThread(int thread_id) {
+  std::lock_guard<std::mutex> l(mu_);
+  ThreadInfo& t = thread_info_[thread_id];
+  if (t.registered) return;
+  t.registered = true;
+  t.loaded_for_inference = false;
+  t.res_ready.store(false, std::memory_order_relaxed);
+  ++num_registered_threads_;
+}
+
+void NNInterfaceB200::UnregisterThread(int thread_id) {
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    ThreadInfo& t = thread_info_[thread_id];
+    if (!t.registered) return;
+    t.registered = false;
+    t.loaded_for_inference = false;
+    --num_registered_threads_;
+  }
+  infer_cv_.notify_all();  // the remaining threads may now satisfy ShouldInfer
+}
+
+void NNInterfaceB200::SignalLoadedAndBlockUntilReady(int thread_id) {  // nn_interface.h:293-309
+  if (num_threads_ == 1) {
+    engine_->RunInference();
+    num_inferences_.fetch_add(1, std::memory_order_relaxed);
+    return;
+  }
+  ThreadInfo& t = thread_info_[thread_id];
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    t.loaded_for_inference = true;
+    t.res_ready.store(false, std::memory_order_relaxed);
+  }
+  infer_cv_.notify_all();
+  std::unique_lock<std::mutex> l(mu_);
+  ready_cv_.wait(l, [&]() { return t.res_ready.load(std::memory_order_acquire); });
+}
+
+NNInferResult NNInterfaceB200::LoadAndGetInference(int thread_id, const GoFeatures& features) {
+  engine_->LoadBatch(thread_id, features);  // no lock held (nn_interface.cc:276)
+  SignalLoadedAndBlockUntilReady(thread_id);
+  NNInferResult r;
+  engine_->GetBatch(thread_id, r);
+  thread_info_[thread_id].res_ready.store(false, std::memory_order_release);  // nn_interface.h:256-261
+  return r;
+}
+
+NNInferResult NNInterfaceB200::LoadAndGetInferenceSym(int thread_id, const GoFeatures& features, int sym) {
+  if (!b200_) {
+    std::fprintf(stderr, "NNInterfaceB200::LoadAndGetInferenceSym needs a B200Engine\n");
+    std::abort();
+  }
+  b200_->LoadBatchSym(thread_id, features, sym);
+  SignalLoadedAndBlockUntilReady(thread_id);
+  NNInferResult r;
+  engine_->GetBatch(thread_id, r);
+  thread_info_[thread_id].res_ready.store(false, std::memory_order_release);
+  return r;
+}
+
+void NNInterfaceB200::InferLoop() {
+  while (running_.load(std::memory_order_acquire)) Infer();
+}
+
+bool NNInterfaceB200::ShouldInfer() const {  // kAuto branch of nn_interface.cc:373-400
+  if (!running_.load(std::memory_order_acquire)) return true;
+  bool exists_pending = false;
+  for (const ThreadInfo& t : thread_info_) {
+    if (!t.registered) continue;
+    if (!t.loaded_for_inference) return false;
+    exists_pending = true;
+  }
+  return exists_pending;
+}
+
+void NNInterfaceB200::Infer() {  // nn_interface.cc:286-371
+  std::unique_lock<std::mutex> l(mu_);
+  if (timeout_us_ > 0)
+    infer_cv_.wait_for(l, std::chrono::microseconds(timeout_us_), [this]() { return ShouldInfer(); });
+  else
+    infer_cv_.wait(l, [this]() { return ShouldInfer(); });
+  if (!running_.load(std::memory_order_acquire) || num_registered_threads_ == 0) return;
+  // never overwrite an unread result
+  for (const ThreadInfo& t : thread_info_)
+    if (t.res_ready.load(std::memory_order_acquire)) return;
+  bool any_loaded = false;
+  for (const ThreadInfo& t : thread_info_) any_loaded = any_loaded || t.loaded_for_inference;
+  if (!any_loaded) return;
+  // Only the slots that are loaded NOW get this run's results: a slot whose worker is still inside LoadBatch (or loads
+  // while the engine runs) is marked loaded later and waits for the next cycle (nn_interface.cc:355-369).  The reference
+  // holds mu_ across RunInference; workers only need mu_ to mark themselves loaded, so releasing it here is equivalent for
+  // them and lets them queue up for the next cycle while the GPU works.
+  std::vector<char> in_batch(num_threads_, 0);
+  for (int i = 0; i < num_threads_; ++i) in_batch[i] = thread_info_[i].registered && thread_info_[i].loaded_for_inference;
+  l.unlock();
+  engine_->RunInference();
+  num_inferences_.fetch_add(1, std::memory_order_relaxed);
+  l.lock();
+  for (int i = 0; i < num_threads_; ++i) {
+    if (!in_batch[i]) continue;
+    ThreadInfo& t = thread_info_[i];
+    t.loaded_for_inference = false;
+    t.res_ready.store(true, std::memory_order_release);
+  }
+  l.unlock();
+  ready_cv_.notify_all();
+}
+
+}  // namespace nn
+
+// =====================================================================================================================
+// C entry points for the tests (ctypes)
+// =====================================================================================================================
+namespace {
+
+// Port of cc/nn/__tests__/nn_interface_sync_test.cc: an engine whose RunInference writes a per-slot function to many
+// elements (yielding between slots) and whose GetBatch checks (1) no torn read, (2) result generation > load generation,
+// (3) own slot's value.
+class CountingEngine : public nn::Engine {
+ public:
+  static constexpr int kSlotElems = 32;
+  static constexpr int kPrime = (1 << 19) - 1;
+  static int SlotFn(int tid) { return (tid + tid) % kPrime; }
+  explicit CountingEngine(int n) : n_(n), buffer_(n * kSlotElems), result_gen_(n), load_gen_(n) {}
+  Kind kind() override { return Kind::kUnknown; }
+  std::string path() override { return ""; }
+  void GetOwnership(int, std::array<float, P3_NUM_BOARD_LOCS>&) override {}
+  void LoadBatch(int t, const nn::GoFeatures&) override {
+    load_gen_[t].store(generation_.load(std::memory_order_acquire), std::memory_order_release);
+  }
+  void RunInference() override {
+    const int gen = generation_.fetch_add(1, std::memory_order_relaxed) + 1;
+    for (int t = 0; t < n_; ++t) {
+      const int f = SlotFn(t);
+      for (int i = 0; i < kSlotElems; ++i) buffer_[t * kSlotElems + i].store(f, std::memory_order_relaxed);
+      result_gen_[t].store(gen, std::memory_order_relaxed);
+      std::this_thread::yield();
+    }
+  }
+  void GetBatch(int id, nn::NNInferResult& r) override {
+    int vals[kSlotElems];
+    for (int i = 0; i < kSlotElems; ++i) {
+      vals[i] = buffer_[id * kSlotElems + i].load(std::memory_order_relaxed);
+      std::this_thread::yield();
+    }
+    for (int i = 1; i < kSlotElems; ++i)
+      if (vals[i] != vals[0]) race.store(true);
+    if (result_gen_[id].load(std::memory_order_relaxed) <= load_gen_[id].load(std::memory_order_acquire)) stale.store(true);
+    if (vals[0] != SlotFn(id)) wrong_slot.store(true);
+    r.move_logits[0] = static_cast<float>(vals[0]);
+  }
+  std::atomic<bool> race{false}, stale{false}, wrong_slot{false};
+
+ private:
+  const int n_;
+  std::atomic<int> generation_{0};
+  std::vector<std::atomic<int>> buffer_, result_gen_, load_gen_;
+};
+
+}  // namespace
+
+extern "C" {
+
+// The reference's sync stress test on NNInterfaceB200: `threads` workers (every 8th one slow enough to force partial,
+// timed-out batches) hammer LoadAndGetInference for `millis` ms.  out[0..3] = race, stale, wrong-slot, wrong-value counts
+// (all must be 0), out[4] = inference cycles, out[5] = evaluations served.
+int p3_host_iface_sync_test(int threads, int millis, int timeout_us, long long* out) {
+  auto* engine = new CountingEngine(threads);
+  std::atomic<long long> served{0}, wrong_value{0};
+  {
+    nn::NNInterfaceB200 iface(threads, timeout_us, std::unique_ptr<nn::Engine>(engine));
+    std::atomic<bool> stop{false};
+    std::vector<std::thread> pool;
+    for (int tid = 0; tid < threads; ++tid)
+      pool.emplace_back([&, tid]() {
+        std::mt19937 rng(static_cast<uint32_t>(tid) * 2654435761u);
+        std::uniform_int_distribution<int> jitter_us(100, 1000), slow_ms(5, 50);
+        const bool is_slow = tid % 8 == 0;
+        nn::GoFeatures f{};
+        while (!stop.load(std::memory_order_relaxed)) {
+          if (is_slow) std::this_thread::sleep_for(std::chrono::milliseconds(slow_ms(rng)));
+          else std::this_thread::sleep_for(std::chrono::microseconds(jitter_us(rng)));
+          const nn::NNInferResult r = iface.LoadAndGetInference(tid, f);
+          if (static_cast<int>(r.move_logits[0]) != CountingEngine::SlotFn(tid)) wrong_value.fetch_add(1);
+          served.fetch_add(1, std::memory_order_relaxed);
+        }
+        iface.UnregisterThread(tid);
+      });
+    std::this_thread::sleep_for(std::chrono::milliseconds(millis));
+    stop.store(true);
+    for (auto& t : pool) t.join();
+    out[4] = static_cast<long long>(iface.num_inferences());
+    out[0] = engine->race.load();
+    out[1] = engine->stale.load();
+    out[2] = engine->wrong_slot.load();
+  }
+  out[3] = wrong_value.load();
+  out[5] = served.load();
+  return 0;
+}
+
+// `threads` workers each evaluate `per_thread` positions through NNInterfaceB200 over a real B200 engine with `threads`
+// slots (1024 is fine: no kMaxNumThreads cap); thread t evaluates positions t, t + threads, ... and stores NNInferResult
+// records at results[position].  use_sym != 0: LoadAndGetInferenceSym with symmetry (position % 8).
+int p3_host_iface_run(const char* weights_path, int device, int threads, int version, int precision, const p3_go_features* positions,
+                      int n_positions, int use_sym, int timeout_us, p3_infer_result* results, long long* n_inferences) {
+  auto engine = nn::B200Engine::Create(weights_path, threads, version, device, precision);
+  nn::NNInterfaceB200 iface(threads, timeout_us, std::move(engine));
+  std::vector<std::thread> pool;
+  for (int tid = 0; tid < threads; ++tid)
+    pool.emplace_back([&, tid]() {
+      for (int p = tid; p < n_positions; p += threads)
+        results[p] = use_sym ? iface.LoadAndGetInferenceSym(tid, positions[p], p % 8) : iface.LoadAndGetInference(tid, positions[p]);
+      iface.UnregisterThread(tid);
+    });
+  for (auto& t : pool) t.join();
+  if (n_inferences) *n_inferences = static_cast<long long>(iface.num_inferences());
+  return 0;
+}
+
+}  // extern "C"
