@@ -59,6 +59,7 @@ struct ConvEpilogue {
   const void* residual = nullptr;   // [rows, cout] fp32 (fp16 if raw_f16), added to the accumulator (may alias raw_out)
   void* raw_out = nullptr;          // [rows, cout] fp32 (fp16 if raw_f16) raw sum (residual stream), or null
   bool raw_f16 = false;             // the residual stream is stored as IEEE fp16 (bf16 engine)
+  bool raw_transposed = false;      // raw_out is written channel-major, [cout, rows] fp32 (head conv -> heads kernel)
   void* act_out = nullptr;          // [rows, cout] activated copy in the operand type, or null
   const float* scale = nullptr;     // [cout] next layer's folded BN (kActMishBN)
   const float* shift = nullptr;
@@ -189,7 +190,8 @@ struct HeadWeights {
   const float *score_w, *score_b;              // [Cv], [1]
   const float* scores;                         // [800]
 };
-// pgv [n*400, 3*Ch] fp32 (p | g | v); results/aux device arrays of n.
+// pgv: the head conv output, channel-major [3*Ch, n*400] fp32 (p | g | v), so that both the per-channel pooling and the
+// per-point policy pass read it coalesced; results/aux device arrays of n.
 // sym (optional, [n]): the symmetry each slot's input was rotated by; move_logits / move_probs / opt_move_probs come back
 // un-rotated (ApplyInverse, cc/nn/nn_interface.h:263-287), the pass entry untouched.
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,

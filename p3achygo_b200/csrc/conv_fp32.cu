@@ -22,7 +22,7 @@ struct Taps {
 __global__ void __launch_bounds__(256)
 conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ w, int rows, int cin, int cout, int taps,
                  Taps tap, const float* residual, float* raw_out, float* act_out, const float* __restrict__ scale,
-                 const float* __restrict__ shift, int act_mode) {
+                 const float* __restrict__ shift, int act_mode, int raw_transposed) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -81,7 +81,7 @@ conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ w, int 
         v = acc[i][j];
         if (residual) v += residual[idx];
       }
-      if (raw_out) raw_out[idx] = v;
+      if (raw_out) raw_out[raw_transposed ? static_cast<size_t>(n) * rows + m : idx] = v;
       if (act_out) {
         float a = 0.0f;
         if (live) {
@@ -105,7 +105,8 @@ int conv_fp32_launch(const float* in, const float* w, int rows, int cin, int cou
   dim3 grid((rows + BM - 1) / BM, (cout + BN - 1) / BN);
   conv_fp32_kernel<<<grid, 256, 0, stream>>>(in, w, rows, cin, cout, taps, tap, reinterpret_cast<const float*>(ep.residual),
                                              reinterpret_cast<float*>(ep.raw_out),
-                                             reinterpret_cast<float*>(ep.act_out), ep.scale, ep.shift, ep.act_mode);
+                                             reinterpret_cast<float*>(ep.act_out), ep.scale, ep.shift, ep.act_mode,
+                                             ep.raw_transposed ? 1 : 0);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

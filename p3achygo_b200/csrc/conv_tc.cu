@@ -109,7 +109,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
-               const float* __restrict__ shift, int act_mode, int raw_f16, int debug, unsigned long long* trace) {
+               const float* __restrict__ shift, int act_mode, int raw_f16, int raw_t, int debug, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -369,6 +369,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ptx::sts_u4(wp + (((half * 2 + j) ^ ((r >> 1) & 3)) << 4),
                         make_uint4(pack_f16(x[8 * j], x[8 * j + 1]), pack_f16(x[8 * j + 2], x[8 * j + 3]),
                                    pack_f16(x[8 * j + 4], x[8 * j + 5]), pack_f16(x[8 * j + 6], x[8 * j + 7])));
+        } else if (has_raw && raw_t) {  // channel-major output: staging tile [32 columns][128 rows] fp32, plain layout
+          const uint32_t wp = ptx::smem_u32(my_raw) + static_cast<uint32_t>(half * 16 * kTileM + r) * 4u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(wp + static_cast<uint32_t>(j * kTileM) * 4u), "f"(x[j]) : "memory");
         } else if (has_raw) {
           const uint32_t wp = ptx::smem_u32(my_raw) + f32_row;
 #pragma unroll
@@ -384,7 +389,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (tr) tc[6] = clock64();
         ptx::named_bar_sync(bar_b, kGrpThreads);
         if (leader && !(debug & 8)) {
-          if (has_raw) ptx::tma_store_2d(&map_raw, my_raw, n0 + c * 32, m0);
+          if (has_raw && raw_t) ptx::tma_store_2d(&map_raw, my_raw, m0, n0 + c * 32);
+          else if (has_raw) ptx::tma_store_2d(&map_raw, my_raw, n0 + c * 32, m0);
           if (has_act) ptx::tma_store_2d(&map_act, my_act, n0 + c * 32, m0);
           ptx::bulk_commit();
         }
@@ -1107,7 +1113,10 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
     const int raw_es = ep.raw_f16 ? 2 : 4;
     const CUtensorMapSwizzle raw_sw = ep.raw_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     if (rc == P3_OK && ep.residual) rc = make_map_2d(&p->map_res, ep.residual, raw_dt, raw_es, cout, rows, 32, kTileM, raw_sw);
-    if (rc == P3_OK && ep.raw_out) rc = make_map_2d(&p->map_raw, ep.raw_out, raw_dt, raw_es, cout, rows, 32, kTileM, raw_sw);
+    if (rc == P3_OK && ep.raw_out && ep.raw_transposed)  // [cout, rows] fp32: boxes of 32 channels x 128 rows, rows contiguous
+      rc = make_map_2d(&p->map_raw, ep.raw_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cout, kTileM, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+    else if (rc == P3_OK && ep.raw_out)
+      rc = make_map_2d(&p->map_raw, ep.raw_out, raw_dt, raw_es, cout, rows, 32, kTileM, raw_sw);
     if (rc == P3_OK && ep.act_out)
       rc = make_map_2d(&p->map_act, ep.act_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cout, rows, 32, kTileM,
                        CU_TENSOR_MAP_SWIZZLE_64B);
@@ -1160,7 +1169,7 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
         p->stages, p->tmem_cols, ep.residual != nullptr && !(p->debug & 32), ep.raw_out != nullptr, ep.act_out != nullptr,
-        ep.scale, ep.shift, ep.act_mode, ep.raw_f16 ? 1 : 0, p->debug >> 8, p->trace);
+        ep.scale, ep.shift, ep.act_mode, ep.raw_f16 ? 1 : 0, (ep.raw_transposed && !ep.raw_f16) ? 1 : 0, p->debug >> 8, p->trace);
   }
   P3_CUDA(cudaGetLastError());
   return P3_OK;

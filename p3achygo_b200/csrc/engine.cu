@@ -675,6 +675,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.layer = e.head_conv;
     s.in = head_in;
     s.ep.raw_out = e.pgv.as<float>();
+    s.ep.raw_transposed = true;  // channel-major [3Ch, rows]: what the heads kernel reads coalesced
     if (e.bf16) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(head_in), e.head_conv->w_bf16.as<__nv_bfloat16>(),
                                   e.rows, C, 3 * Ch, 1, e.head_conv->tap_off.data(), s.ep, &e.head_conv->plan);

@@ -5,7 +5,7 @@
 //
 // Input: `pgv` = the three head 1x1 convs (conv_p | conv_g | conv_v, python/model.py:784-785,889)
 // evaluated as ONE GEMM over the raw trunk output, fp32 [n*400, 3*Ch] in the padded board-row layout.
-// Persistent CTAs, 4 positions in flight per CTA (one per 256-thread group), head weights staged once in shared memory;
+// Persistent CTAs, 8 positions in flight per CTA (one per 128-thread group), head weights staged once in shared memory;
 // reads 361*3Ch*4 B and writes ~9.7 KB per position, warp-shuffle reductions, fp32.
 #include <algorithm>
 #include <string>
@@ -16,8 +16,8 @@
 namespace p3 {
 namespace {
 
-constexpr int kGroups = 4;            // positions in flight per CTA
-constexpr int kGT = 256;              // threads per group (one position)
+constexpr int kGroups = 8;            // positions in flight per CTA (148 x 8 >= 1024: the BASELINE batch is one round)
+constexpr int kGT = 128;              // threads per group (one position)
 constexpr int kThreads = kGroups * kGT;
 constexpr int kMaxCh = 64;
 constexpr int kMaxCv = 128;
@@ -65,14 +65,15 @@ constexpr int kGroupFloats = 4 * P3_MAX_MOVES + P3_NUM_SCORE_LOGITS + 2 * kGT + 
 
 // kAccurate: libm-grade mish / exp (the fp32 parity engine).  The bf16 engine uses the ex2 / rcp forms (rel. err ~1e-6,
 // far below the bf16 rounding of its inputs): the 800 x Cv mish evaluations of the score head dominate the arithmetic.
-// Persistent CTAs of 4 x 256 threads; a 256-thread group evaluates one position at a time, synchronising on its own
-// named barrier.
+// Persistent CTAs of 8 x 128 threads; a 128-thread group evaluates one position at a time, synchronising on its own
+// named barrier (the kernel is bound by the latency of a position's serial phases, so positions in flight matter).
 template <bool kAccurate>
 __global__ void __launch_bounds__(kThreads, 1)
 heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __restrict__ results,
              p3_aux_result* __restrict__ auxs, int n, const int8_t* __restrict__ syms) {
+  const size_t R = static_cast<size_t>(n) * kRowsPerPos;  // pgv is channel-major: element (row, c) at pgv[c * R + row]
   extern __shared__ __align__(16) float hsm[];
-  const int Ch = hw.Ch, Cv = hw.Cv, W3 = 3 * Ch;
+  const int Ch = hw.Ch, Cv = hw.Cv;
   SmemWeights w;
   {
     float* p = hsm;
@@ -118,109 +119,112 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
   float* s_misc = s_scratch + 8;                  // gamma_mult, gamma
 
   for (int b = blockIdx.x * kGroups + g; b < n; b += gridDim.x * kGroups) {
-    const float* base = pgv + static_cast<size_t>(b) * kRowsPerPos * W3;
+    const float* base = pgv + static_cast<size_t>(b) * kRowsPerPos;  // + c * R + padded row
     p3_infer_result& res = results[b];
     p3_aux_result& aux = auxs[b];
     const int sym = syms ? syms[b] : 0;
 
-    // ---- pass 1: global pools.  g -> mish(BN(g)) (GlobalPoolBias, model.py:697-699), v raw (model.py:890)
+    // ---- pass 1: global pools.  g -> mish(BN(g)) (GlobalPoolBias, model.py:697-699), v raw (model.py:890).  A warp owns a
+    // channel at a time and strides over the position's padded rows (contiguous in the channel-major layout).
     {
-      const int cols = 2 * Ch, groups = kGT / cols;
-      const int col = tid % cols, grp = tid / cols;
-      float sum = 0.0f, mx = -INFINITY;
-      if (grp < groups) {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int col = warp; col < 2 * Ch; col += kGT / 32) {  // col < Ch: g channel, else v channel
         const bool is_g = col < Ch;
         const float sc = is_g ? w.gp_scale[col] : 1.0f, sh = is_g ? w.gp_shift[col] : 0.0f;
-#pragma unroll 6
-        for (int p = grp; p < P3_NUM_BOARD_LOCS; p += groups) {
-          float x = __ldg(base + static_cast<size_t>(board_row(p)) * W3 + Ch + col);
-          if (is_g) x = mish_f32<kAccurate>(fmaf(x, sc, sh));
-          sum += x;
-          mx = fmaxf(mx, x);
+        const float* src = base + static_cast<size_t>(Ch + col) * R;
+        // all 12 loads of the lane are issued before the first use (the kernel is bound by load latency, not bandwidth)
+        constexpr int kIters = (kRowsPerPos - kRowBase + 31) / 32;  // 12
+        float xv[kIters];
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+          const int q = kRowBase + lane + 32 * k;
+          xv[k] = q < kRowsPerPos ? __ldg(src + q) : 0.0f;
         }
-      }
-      s_part[tid] = sum;
-      s_part[kGT + tid] = mx;
-      group_sync(g);
-      if (tid < cols) {
-        float s = 0.0f, m = -INFINITY;
-        for (int k = 0; k < groups; ++k) {
-          s += s_part[k * cols + tid];
-          m = fmaxf(m, s_part[kGT + k * cols + tid]);
+        float sum = 0.0f, mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+          const int q = kRowBase + lane + 32 * k;
+          if (q < kRowsPerPos && (q - kRowBase) % kRowPitch != 19) {  // the zero column of the layout is not a board point
+            const float x = is_g ? mish_f32<kAccurate>(fmaf(xv[k], sc, sh)) : xv[k];
+            sum += x;
+            mx = fmaxf(mx, x);
+          }
         }
-        const float mean = s / static_cast<float>(P3_NUM_BOARD_LOCS);
-        if (tid < Ch) {  // GlobalPool: concat(mean, max) (model.py:643-647)
-          s_gp[tid] = mean;
-          s_gp[Ch + tid] = m;
-        } else {
-          s_vp[tid - Ch] = mean;
-          s_vp[Ch + tid - Ch] = m;
+        sum = warp_sum(sum);
+        mx = warp_max(mx);
+        if (lane == 0) {  // GlobalPool: concat(mean, max) (model.py:643-647)
+          const float mean = sum / static_cast<float>(P3_NUM_BOARD_LOCS);
+          if (is_g) {
+            s_gp[col] = mean;
+            s_gp[Ch + col] = mx;
+          } else {
+            s_vp[col - Ch] = mean;
+            s_vp[Ch + col - Ch] = mx;
+          }
         }
       }
       group_sync(g);
     }
 
-    // ---- small dense layers on the pooled vectors
-    if (tid < Ch) {  // g_biases = dense(g_pooled) (model.py:700)
-      float a = w.gp_dense_b[tid];
-      for (int i = 0; i < 2 * Ch; ++i) a = fmaf(s_gp[i], w.gp_dense_w[i * Ch + tid], a);
-      s_pbias[tid] = a;
-    }
-    if (tid >= 64 && tid < 68) {  // pass logits: dense(g_pooled) - 3 (model.py:795,803,805); bias holds the -3
-      const int k = tid - 64;
-      float a = w.pass_b[k];
-      for (int i = 0; i < 2 * Ch; ++i) a = fmaf(s_gp[i], w.pass_w[i * 4 + k], a);
-      s_logits[k][P3_NUM_BOARD_LOCS] = a;
-    }
-    if (tid >= 128 && tid < 128 + Cv) {  // value embeddings (model.py:893-894, 908-909, 935)
-      const int j = tid - 128;
-      float e = w.outcome_pre_b[j], g2 = w.gamma_pre_b[j], sb = w.score_pre_b[j];
-      for (int i = 0; i < 2 * Ch; ++i) {
-        const float v = s_vp[i];
-        e = fmaf(v, w.outcome_pre_w[i * Cv + j], e);
-        g2 = fmaf(v, w.gamma_pre_w[i * Cv + j], g2);
-        sb = fmaf(v, w.score_pre_w[i * Cv + j], sb);
+    // ---- small dense layers on the pooled vectors: one work item per thread
+    for (int idx = tid; idx < Ch + 4 + Cv; idx += kGT) {
+      if (idx < Ch) {  // g_biases = dense(g_pooled) (model.py:700)
+        float a = w.gp_dense_b[idx];
+        for (int i = 0; i < 2 * Ch; ++i) a = fmaf(s_gp[i], w.gp_dense_w[i * Ch + idx], a);
+        s_pbias[idx] = a;
+      } else if (idx < Ch + 4) {  // pass logits: dense(g_pooled) - 3 (model.py:795,803,805); bias holds the -3
+        const int k = idx - Ch;
+        float a = w.pass_b[k];
+        for (int i = 0; i < 2 * Ch; ++i) a = fmaf(s_gp[i], w.pass_w[i * 4 + k], a);
+        s_logits[k][P3_NUM_BOARD_LOCS] = a;
+      } else {  // value embeddings (model.py:893-894, 908-909, 935)
+        const int j = idx - Ch - 4;
+        float e = w.outcome_pre_b[j], g2 = w.gamma_pre_b[j], sb = w.score_pre_b[j];
+        for (int i = 0; i < 2 * Ch; ++i) {
+          const float v = s_vp[i];
+          e = fmaf(v, w.outcome_pre_w[i * Cv + j], e);
+          g2 = fmaf(v, w.gamma_pre_w[i * Cv + j], g2);
+          sb = fmaf(v, w.score_pre_w[i * Cv + j], sb);
+        }
+        s_e[j] = mish_f32<kAccurate>(e);
+        s_g2[j] = mish_f32<kAccurate>(g2);
+        s_base[j] = sb;                              // W_v . v_pooled + b : the per-position part of score_pre
+        s_ws[j] = w.score_pre_w[2 * Ch * Cv + j];    // weight of the score-bin input
       }
-      s_e[j] = mish_f32<kAccurate>(e);
-      s_g2[j] = mish_f32<kAccurate>(g2);
-      s_base[j] = sb;                              // W_v . v_pooled + b : the per-position part of score_pre
-      s_ws[j] = w.score_pre_w[2 * Ch * Cv + j];    // weight of the score-bin input
     }
     group_sync(g);
-    if (tid < 14) {  // outcome_q_output (model.py:895)
-      float a = w.outcome_b[tid];
-      for (int j = 0; j < Cv; ++j) a = fmaf(s_e[j], w.outcome_w[j * 14 + tid], a);
-      s_o[tid] = a;
-    } else if (tid >= 32 && tid < 32 + 51) {  // mcts value distribution logits (model.py:903)
-      const int k = tid - 32;
-      float a = w.mcts_b[k];
-      for (int j = 0; j < Cv; ++j) a = fmaf(s_e[j], w.mcts_w[j * 51 + k], a);
-      s_mcts[k] = a;
-    } else if (tid == 96) {  // gamma (model.py:908-910) and its multiplier min(softplus(gamma), 10) (model.py:949-951)
-      float a = w.gamma_b[0];
-      for (int j = 0; j < Cv; ++j) a = fmaf(s_g2[j], w.gamma_w[j], a);
-      s_misc[1] = a;
-      s_misc[0] = fminf(softplus_f32(a), 10.0f);
+    for (int idx = tid; idx < 14 + 51 + 1; idx += kGT) {
+      if (idx < 14) {  // outcome_q_output (model.py:895)
+        float a = w.outcome_b[idx];
+        for (int j = 0; j < Cv; ++j) a = fmaf(s_e[j], w.outcome_w[j * 14 + idx], a);
+        s_o[idx] = a;
+      } else if (idx < 14 + 51) {  // mcts value distribution logits (model.py:903)
+        const int k = idx - 14;
+        float a = w.mcts_b[k];
+        for (int j = 0; j < Cv; ++j) a = fmaf(s_e[j], w.mcts_w[j * 51 + k], a);
+        s_mcts[k] = a;
+      } else {  // gamma (model.py:908-910) and its multiplier min(softplus(gamma), 10) (model.py:949-951)
+        float a = w.gamma_b[0];
+        for (int j = 0; j < Cv; ++j) a = fmaf(s_g2[j], w.gamma_w[j], a);
+        s_misc[1] = a;
+        s_misc[0] = fminf(softplus_f32(a), 10.0f);
+      }
     }
 
-    // ---- pass 2: per-point policy logits (model.py:787-812) and ownership (model.py:906-907); a thread owns a point and
-    // reads its p and v channels as independent 16-byte loads
+    // ---- pass 2: per-point policy logits (model.py:787-812) and ownership (model.py:906-907); a thread owns a point, and
+    // neighbouring threads read neighbouring rows of each channel
     for (int p = tid; p < P3_NUM_BOARD_LOCS; p += kGT) {
-      const float4* row = reinterpret_cast<const float4*>(base + static_cast<size_t>(board_row(p)) * W3);
+      const float* row = base + board_row(p);
       float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f, own = 0.0f;
-      for (int c4 = 0; c4 < Ch / 4; ++c4) {
-        const float4 pv = __ldg(row + c4), vv = __ldg(row + (2 * Ch) / 4 + c4);
-        const float px[4] = {pv.x, pv.y, pv.z, pv.w}, vx[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 4 * c4 + k;
-          const float a = mish_f32<kAccurate>(px[k] + s_pbias[c]);
-          l0 = fmaf(a, w.moves_w[c], l0);
-          l1 = fmaf(a, w.moves_w[Ch + c], l1);
-          l2 = fmaf(a, w.moves_w[2 * Ch + c], l2);
-          l3 = fmaf(a, w.moves_w[3 * Ch + c], l3);
-          own = fmaf(vx[k], w.own_w[c], own);
-        }
+#pragma unroll 8
+      for (int c = 0; c < Ch; ++c) {
+        const float pv = __ldg(row + static_cast<size_t>(c) * R), vv = __ldg(row + static_cast<size_t>(2 * Ch + c) * R);
+        const float a = mish_f32<kAccurate>(pv + s_pbias[c]);
+        l0 = fmaf(a, w.moves_w[c], l0);
+        l1 = fmaf(a, w.moves_w[Ch + c], l1);
+        l2 = fmaf(a, w.moves_w[2 * Ch + c], l2);
+        l3 = fmaf(a, w.moves_w[3 * Ch + c], l3);
+        own = fmaf(vv, w.own_w[c], own);
       }
       s_logits[0][p] = l0;
       s_logits[1][p] = l1;
@@ -230,15 +234,21 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
     }
     group_sync(g);
 
-    // ---- score distribution logits (model.py:925-951), factored: mish(base + w_s * s_i) . w_out + b
+    // ---- score distribution logits (model.py:925-951), factored: mish(base + w_s * s_i) . w_out + b.  A thread evaluates
+    // two bins per pass (i, i + 400) so the per-channel constants are read once for both and the two chains interleave.
     {
       const float gm = s_misc[0], sb0 = w.score_b[0];
-      for (int i = tid; i < P3_NUM_SCORE_LOGITS; i += kGT) {
-        const float si = w.scores[i];
-        float a = sb0;
-#pragma unroll 8
-        for (int j = 0; j < Cv; ++j) a = fmaf(mish_f32<kAccurate>(fmaf(s_ws[j], si, s_base[j])), w.score_w[j], a);
-        s_score[i] = gm * a;
+      for (int i = tid; i < P3_NUM_SCORE_LOGITS / 2; i += kGT) {
+        const float si0 = w.scores[i], si1 = w.scores[i + P3_NUM_SCORE_LOGITS / 2];
+        float a0 = sb0, a1 = sb0;
+#pragma unroll 4
+        for (int j = 0; j < Cv; ++j) {
+          const float ws = s_ws[j], bs = s_base[j], wo = w.score_w[j];
+          a0 = fmaf(mish_f32<kAccurate>(fmaf(ws, si0, bs)), wo, a0);
+          a1 = fmaf(mish_f32<kAccurate>(fmaf(ws, si1, bs)), wo, a1);
+        }
+        s_score[i] = gm * a0;
+        s_score[i + P3_NUM_SCORE_LOGITS / 2] = gm * a1;
       }
     }
     group_sync(g);
@@ -306,7 +316,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
 
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
                  cudaStream_t stream, bool accurate, const int8_t* sym) {
-  if (hw.Ch > kMaxCh || hw.Cv > kMaxCv || 2 * hw.Ch > kGT || hw.Ch % 4 != 0 || hw.Cv + 128 > kGT)
+  if (hw.Ch > kMaxCh || hw.Cv > kMaxCv || 2 * hw.Ch > kGT || hw.Ch % 4 != 0)
     return fail(P3_ERR_UNSUPPORTED, "heads: head channels / c_val not supported");
   const size_t smem = (static_cast<size_t>((heads_weight_floats(hw.Ch, hw.Cv) + 3) & ~3) + static_cast<size_t>(kGroups) * kGroupFloats) * sizeof(float);
   if (smem > 227 * 1024) return fail(P3_ERR_UNSUPPORTED, "heads: weights do not fit in shared memory");
