@@ -14,7 +14,8 @@
 // staging fit in shared memory; the A tile is rebuilt per slice, which is cheap next to the stores):
 //   warp 0        stages the plane masks and the game-state bias of the next tile
 //   warp 1        MMA issuer, owns TMEM (two accumulator stages)
-//   warps 2-17    build A(it + 1) as soon as the MMAs of tile it have read A, then run the epilogue of tile it
+//   warps 2-9     builders: expand the masks of tile it + 1 into the A tile as soon as the MMAs of tile it have read it
+//   warps 10-17   epilogue of tile it, concurrently with the builders and the tensor core
 //                 (+ game-state bias, fp16 residual stream and bf16 mish(BN_0(x)) copy; a TMEM lane quarter's 4 warps fill
 //                 one 32-row x 64-column box per output, which leaves as a TMA bulk store — per-thread 32-byte stores
 //                 ran at 1.6 TB/s) while the tensor core works on tile it + 1.
@@ -36,8 +37,9 @@ constexpr int kItK = kItTaps * 16;         // 400
 constexpr int kItKc = kItK / 8;            // 50 core matrices along K
 constexpr int kItSbo = kItKc * 128;        // 6400 B between 8-row groups
 constexpr int kItABytes = 16 * kItSbo;     // 128 rows: 102 400 B
-constexpr int kItWorkers = 16 * 32;        // 512
-constexpr int kItThreads = 64 + kItWorkers;
+constexpr int kItBuildWarps = 8, kItEpiWarps = 8;
+constexpr int kItBuilders = kItBuildWarps * 32;  // 256
+constexpr int kItThreads = 64 + (kItBuildWarps + kItEpiWarps) * 32;  // 576
 constexpr int kItPadW = kMaskPadW, kItPadH = kMaskPadH;  // zero-bordered mask grid: (r + 2) * 24 + (c + 2)
 constexpr int kItNw = 64;                  // output channels per CTA (N slice)
 constexpr int kItBoxBytes = 32 * 128;      // 32 rows x 64 two-byte elements, 128B swizzle
@@ -100,7 +102,7 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     ptx::mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], 16);
+      ptx::mbar_init(&acc_empty[s], kItEpiWarps);
       ptx::mbar_init(&stage_ready[s], 1);
       ptx::mbar_init(&stage_free[s], 1);
     }
@@ -150,18 +152,13 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp >= 2) {
-    // ===== workers =====
-    const int wt = tid - 64;               // 0..511
-    const int ew = warp - 2;
-    const int brow = wt & 127;             // row of the tile this thread builds (fixed), taps wt / 128 + 4 k
-    const int q = warp & 3;                // TMEM lane quarter
-    const int cg = ew >> 2;                // which quarter of the slice's columns
+  } else if (warp < 2 + kItBuildWarps) {
+    // ===== builders =====
+    const int bt = tid - 64;               // 0..255
+    const int brow = bt & 127;             // row of the tile this thread builds (fixed), taps bt / 128 + 2 k
     const uint32_t a_row = ptx::smem_u32(smem_a) + static_cast<uint32_t>(brow >> 3) * kItSbo + static_cast<uint32_t>(brow & 7) * 16u;
     const uint32_t lut = ptx::smem_u32(s_lut);
-    const uint32_t sc = ptx::smem_u32(s_sc), sh = ptx::smem_u32(s_sh);
-
-    auto build = [&](int it) {
+    for (int it = 0; it < n_it; ++it) {
       const int m0 = (cta_in_slice + it * ctas_per_slice) * 128;
       const int b0 = m0 / kRowsPerPos;
       const int sb = it & 1;
@@ -172,15 +169,16 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       const bool live = m < rows && row_is_live(qq);
       const int r = (qq - kRowBase) / kRowPitch, c = (qq - kRowBase) % kRowPitch;
       const uint16_t* mg = s_mask + (sb * 2 + pb) * kItPadH * kItPadW + r * kItPadW + c;  // (r + dy + 2, c + dx + 2) = mg[(dy+2)*24 + dx+2]
-      uint32_t mk[7];
+      constexpr int kPer = (kItTaps + 1) / 2;  // 13
+      uint32_t mk[kPer];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {  // this thread's taps: wt / 128 + 4 k
-        const int t = (wt >> 7) + 4 * k;
+      for (int k = 0; k < kPer; ++k) {  // this thread's taps: bt / 128 + 2 k
+        const int t = (bt >> 7) + 2 * k;
         mk[k] = (live && t < kItTaps) ? mg[(t / 5) * kItPadW + (t % 5)] : 0u;
       }
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        const int t = (wt >> 7) + 4 * k;
+      for (int k = 0; k < kPer; ++k) {
+        const int t = (bt >> 7) + 2 * k;
         if (t < kItTaps && !(debug & 2)) {
           const float4 lo = ptx::lds_f4_const(lut + (mk[k] & 0xffu) * 16u), hi = ptx::lds_f4_const(lut + (mk[k] >> 8) * 16u);
           ptx::sts_f4(a_row + static_cast<uint32_t>(t) * 256u, lo);
@@ -188,16 +186,21 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
         }
       }
       ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, kItWorkers);
-      if (wt == 0) {
+      ptx::named_bar_sync(1, kItBuilders);
+      if (bt == 0) {
         ptx::mbar_arrive(a_full);
         ptx::mbar_arrive(&stage_free[sb]);
       }
-    };
-
+    }
+  } else {
+    // ===== epilogue: 2 warps per TMEM lane quarter, thread = one row x 32 of the slice's 64 columns =====
+    const int ew = warp - 2 - kItBuildWarps;  // 0..7
+    const int q = warp & 3;                   // TMEM lane quarter
+    const int cg = ew >> 2;                   // which half of the slice's columns
+    const uint32_t sc = ptx::smem_u32(s_sc), sh = ptx::smem_u32(s_sh);
     const bool qleader = cg == 0 && lane == 0;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    const uint32_t ch0 = ((2u * cg) ^ sw) << 4, ch1 = ((2u * cg + 1u) ^ sw) << 4;  // this thread's 2 chunks of the box row
+    // this thread's 4 chunks of the 128-byte box row: columns cg * 32 + h * 16 + {0..7, 8..15}
     const uint32_t box_raw = ptx::smem_u32(smem_stage) + static_cast<uint32_t>(q) * (2 * kItBoxBytes);
     const uint32_t box_act = box_raw + kItBoxBytes;
     auto epilogue = [&](int it) {
@@ -205,30 +208,33 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       const int m0 = (cta_in_slice + it * ctas_per_slice) * 128;
       const int m = m0 + q * 32 + lane;
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
-      const int col = cg * 16;
       // game-state bias of this row's position (precomputed by the encode kernel; L2-resident), fetched ahead of the wait
-      float4 g4[4];
-      {
-        const float4* gp = reinterpret_cast<const float4*>(gs + static_cast<size_t>(min(m / kRowsPerPos, n - 1)) * C + n0 + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) g4[i] = __ldg(gp + i);
-      }
+      const float4* gp = reinterpret_cast<const float4*>(gs + static_cast<size_t>(min(m / kRowsPerPos, n - 1)) * C + n0 + cg * 32);
+      // the quarter's previous stores have read the boxes (waited for by the quarter leader before the barrier)
+      if (qleader) ptx::bulk_wait_read<0>();
+      ptx::named_bar_sync(2 + q, 64);
       ptx::mbar_wait(&acc_full[as], (static_cast<uint32_t>(it) >> 1) & 1u);
       ptx::tc_fence_after_sync();
+      const uint32_t ro = static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+      const int col = cg * 32 + h * 16;
       uint32_t v[16];
       ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * n_w + col), v);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
-      if (debug & 4) return;
+      if (h == 1) {
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+      }
       float x[16], a[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        x[4 * i] = __uint_as_float(v[4 * i]) + g4[i].x;
-        x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + g4[i].y;
-        x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + g4[i].z;
-        x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + g4[i].w;
+        const float4 g4 = __ldg(gp + 4 * h + i);
+        x[4 * i] = __uint_as_float(v[4 * i]) + g4.x;
+        x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + g4.y;
+        x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + g4.z;
+        x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + g4.w;
       }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -255,16 +261,16 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
       uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
       if (!live) r0 = r1 = p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout are zeros
-      // the quarter's previous stores have read the boxes -> fill them -> one TMA store per output
-      if (qleader) ptx::bulk_wait_read<0>();
-      ptx::named_bar_sync(2 + q, 128);
-      const uint32_t ro = static_cast<uint32_t>(lane) * 128u;
-      ptx::sts_u4(box_raw + ro + ch0, r0);
-      ptx::sts_u4(box_raw + ro + ch1, r1);
-      ptx::sts_u4(box_act + ro + ch0, p0);
-      ptx::sts_u4(box_act + ro + ch1, p1);
+      if (!(debug & 4)) {
+        const uint32_t c0 = ((4u * cg + 2u * h) ^ sw) << 4, c1 = ((4u * cg + 2u * h + 1u) ^ sw) << 4;
+        ptx::sts_u4(box_raw + ro + c0, r0);
+        ptx::sts_u4(box_raw + ro + c1, r1);
+        ptx::sts_u4(box_act + ro + c0, p0);
+        ptx::sts_u4(box_act + ro + c1, p1);
+      }
+      }
       ptx::fence_proxy_async();
-      ptx::named_bar_sync(2 + q, 128);
+      ptx::named_bar_sync(2 + q, 64);
       if (qleader) {
         ptx::tma_store_2d(&map_raw, nullptr, 0, 0, box_raw, n0, m0 + q * 32);
         ptx::tma_store_2d(&map_act, nullptr, 0, 0, box_act, n0, m0 + q * 32);
@@ -272,11 +278,7 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       }
     };
 
-    for (int it = 0; it < n_it; ++it) {
-      build(it);
-      if (it > 0) epilogue(it - 1);
-    }
-    if (n_it > 0) epilogue(n_it - 1);
+    for (int it = 0; it < n_it; ++it) epilogue(it);
     if (qleader) ptx::bulk_wait_all();
   }
 

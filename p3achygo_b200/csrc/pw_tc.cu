@@ -235,7 +235,13 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const uint32_t acc_empty_l = ptx::mapa_shared(ptx::smem_u32(acc_empty), 0);
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sc = ptx::smem_u32(s_scale), sh = ptx::smem_u32(s_shift);
-    uint32_t s = 0;
+    uint32_t ob = 0, ob_phase = 0;  // staging box of the current box-step (ordinal mod n_boxes) and its use parity
+    auto next_box = [&]() {
+      if (++ob == static_cast<uint32_t>(n_boxes)) {
+        ob = 0;
+        ob_phase ^= 1u;
+      }
+    };
     for (int it = 0; it < n_it; ++it) {
       const int as = it & 1;
       const int m = (pair_in_slice + it * pairs_per_slice) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
@@ -246,9 +252,8 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int col = j * 64 + cg * 16;
         uint32_t v[16];
         ptx::tmem_ld_32x16(lane_addr + static_cast<uint32_t>(as * n_tile + col), v);
-        uint32_t ob = s % n_boxes;
         uint32_t obuf = box_base + ob * kPwBoxBytes;
-        ptx::mbar_wait(&my_ready[ob], (s / n_boxes) & 1u);
+        ptx::mbar_wait(&my_ready[ob], ob_phase);
         float x[16];
         if (has_res) {
           const float4 t0 = ptx::lds_f4(obuf + ch0), t1 = ptx::lds_f4(obuf + ch1);
@@ -279,7 +284,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
-          ++s;
+          next_box();
         }
         if (has_act) {
           float a[16];
@@ -294,16 +299,15 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
           uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
           if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
           if (has_raw) {  // second box of the slab
-            ob = s % n_boxes;
             obuf = box_base + ob * kPwBoxBytes;
-            ptx::mbar_wait(&my_ready[ob], (s / n_boxes) & 1u);
+            ptx::mbar_wait(&my_ready[ob], ob_phase);
           }
           ptx::sts_u4(obuf + ch0, p0);
           ptx::sts_u4(obuf + ch1, p1);
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
-          ++s;
+          next_box();
         }
       }
     }
