@@ -662,13 +662,17 @@ __device__ __forceinline__ unsigned long long global_timer() {
 }
 constexpr int kPairMaxN = 128;
 
-template <int kCpw>  // epilogue columns per warp = N / 4
+// kRes: the layer closes a residual block at this width (classic blocks, the inner blocks of nested-bottleneck nets):
+// `res` (fp16 [rows, cout], may be null) is added to the accumulator, the sum goes to `raw` (fp16, may be null, may alias
+// res) and its activation to act_out.  Those two streams use 32-byte per-thread loads / stores (shared memory is full).
+template <int kCpw, bool kRes>  // epilogue columns per warp = N / 4
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                        const __grid_constant__ CUtensorMap map_o64, const __grid_constant__ CUtensorMap map_o32, int rows,
                        int cin, int cout, int n_half, int stages, int staged, int tmem_cols, TcTaps tap,
                        __nv_bfloat16* __restrict__ act_out, const float* __restrict__ scale,
-                       const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace) {
+                       const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace,
+                       const __half* res, __half* raw) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // P3_TC_TRACE: globaltimer stamps of CTA 0 (ns since its first instruction), summed over launches
@@ -850,7 +854,35 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         uint32_t v[kW];
         if (kW == 16) ptx::tmem_ld_32x16(taddr + col, v);
         else ptx::tmem_ld_32x8(taddr + col, v);
+        uint4 rq[kW / 8];
+        if (kRes) {  // residual values of this row, in flight while the TMEM load completes
+#pragma unroll
+          for (int g = 0; g < kW / 8; ++g) rq[g] = make_uint4(0, 0, 0, 0);
+          if (res != nullptr && in_range) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res + static_cast<size_t>(m) * cout + n0 + c0 + col);
+#pragma unroll
+            for (int g = 0; g < kW / 8; ++g) rq[g] = rp[g];
+          }
+        }
         ptx::tmem_ld_wait();
+        if (kRes) {
+#pragma unroll
+          for (int g = 0; g < kW / 8; ++g) {
+            const uint32_t u[4] = {rq[g].x, rq[g].y, rq[g].z, rq[g].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+              const float x0 = __uint_as_float(v[g * 8 + 2 * i]) + f2.x, x1 = __uint_as_float(v[g * 8 + 2 * i + 1]) + f2.y;
+              v[g * 8 + 2 * i] = __float_as_uint(x0);
+              v[g * 8 + 2 * i + 1] = __float_as_uint(x1);
+              o[i] = pack_f16(x0, x1);
+            }
+            // padding rows need no masking: their A rows and residual rows are zeros (layout invariant)
+            if (raw != nullptr && in_range)
+              *reinterpret_cast<uint4*>(raw + static_cast<size_t>(m) * cout + n0 + c0 + col + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
         if (last) {
           ptx::tc_fence_before_sync();
           __syncwarp();
@@ -963,13 +995,13 @@ int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_
 
 typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int,
                              int, int, int, TcTaps, __nv_bfloat16*,
-                             const float*, const float*, int, int, unsigned long long*);
-PairKernelFn pair_kernel_for(int N) {
+                             const float*, const float*, int, int, unsigned long long*, const __half*, __half*);
+PairKernelFn pair_kernel_for(int N, bool res = false) {
   switch (N) {
-    case 128: return tc_conv3x3_pair_kernel<32>;
-    case 96: return tc_conv3x3_pair_kernel<24>;
-    case 64: return tc_conv3x3_pair_kernel<16>;
-    default: return tc_conv3x3_pair_kernel<8>;
+    case 128: return res ? tc_conv3x3_pair_kernel<32, true> : tc_conv3x3_pair_kernel<32, false>;
+    case 96: return res ? tc_conv3x3_pair_kernel<24, true> : tc_conv3x3_pair_kernel<24, false>;
+    case 64: return res ? tc_conv3x3_pair_kernel<16, true> : tc_conv3x3_pair_kernel<16, false>;
+    default: return res ? tc_conv3x3_pair_kernel<8, true> : tc_conv3x3_pair_kernel<8, false>;
   }
 }
 
@@ -1015,7 +1047,9 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
                 ep.raw_out == nullptr && ep.act_out != nullptr && !(env_res && std::atoi(env_res) == 0);
   // CTA-pair kernel: largest N = 2 * n_half in {128, 96, 64, 32} dividing cout whose weight half fits next to >= 2 A stages
   const char* env_pair = std::getenv("P3_TC_PAIR");
-  if (shifts_ok && ep.residual == nullptr && ep.raw_out == nullptr && ep.act_out != nullptr &&
+  const bool with_res = ep.residual != nullptr || ep.raw_out != nullptr;
+  const char* env_pr = std::getenv("P3_TC_PAIR_RES");
+  if (shifts_ok && (!with_res || (ep.raw_f16 && !(env_pr && std::atoi(env_pr) == 0))) && ep.act_out != nullptr &&
       !(env_pair && std::atoi(env_pair) == 0) && !(env_res && std::atoi(env_res) == 0)) {
     for (int N = kPairMaxN; N >= 32 && !p->pair; N -= 32) {
       if (cout % N != 0) continue;
@@ -1063,7 +1097,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
                        cpw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : cpw == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
     }
     if (rc == P3_OK) {
-      cudaError_t e = cudaFuncSetAttribute(pair_kernel_for(p->n_tile), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      cudaError_t e = cudaFuncSetAttribute(pair_kernel_for(p->n_tile, with_res), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
       if (e != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
     }
     int max_pairs = sms / 2;
@@ -1073,7 +1107,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
       cfg.blockDim = dim3(kPairThreads);
       cfg.dynamicSmemBytes = p->smem_bytes;
       int n_clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&n_clusters, pair_kernel_for(p->n_tile), &cfg) == cudaSuccess && n_clusters > 0)
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, pair_kernel_for(p->n_tile, with_res), &cfg) == cudaSuccess && n_clusters > 0)
         max_pairs = std::min(max_pairs, n_clusters);
       else
         cudaGetLastError();
@@ -1158,9 +1192,11 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
   if (p->pair) {
-    P3_CUDA(tc_launch_pdl(pair_kernel_for(p->n_tile), p->grid, kPairThreads, p->smem_bytes, stream, p->map_a, p->map_w, p->map_raw,
-                          p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0, p->tmem_cols, p->tap,
-                          reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff, p->trace));
+    const bool with_res = ep.residual != nullptr || ep.raw_out != nullptr;
+    P3_CUDA(tc_launch_pdl(pair_kernel_for(p->n_tile, with_res), p->grid, kPairThreads, p->smem_bytes, stream, p->map_a, p->map_w,
+                          p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0, p->tmem_cols,
+                          p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff,
+                          p->trace, reinterpret_cast<const __half*>(ep.residual), reinterpret_cast<__half*>(ep.raw_out)));
   } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
