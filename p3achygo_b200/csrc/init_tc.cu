@@ -38,6 +38,7 @@ constexpr int kItKc = kItK / 8;            // 50 core matrices along K
 constexpr int kItSbo = kItKc * 128;        // 6400 B between 8-row groups
 constexpr int kItABytes = 16 * kItSbo;     // 128 rows: 102 400 B
 constexpr int kItBuildWarps = 8, kItEpiWarps = 8;
+constexpr int kItMaskStages = 6;           // plane-mask grids in flight (the bulk copies are latency-, not bandwidth-bound)
 constexpr int kItBuilders = kItBuildWarps * 32;  // 256
 constexpr int kItThreads = 64 + (kItBuildWarps + kItEpiWarps) * 32;  // 576
 constexpr int kItPadW = kMaskPadW, kItPadH = kMaskPadH;  // zero-bordered mask grid: (r + 2) * 24 + (c + 2)
@@ -60,16 +61,17 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
   uint8_t* smem_a = smem_w + w_bytes;
   uint8_t* smem_stage = smem_a + kItABytes;                                        // [4 quarters][raw, act][32 rows x 128 B]
   uint4* s_lut = reinterpret_cast<uint4*>(smem_stage + 4 * 2 * kItBoxBytes);       // [256] byte -> 8 bf16 {0, 1}
-  uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_lut + 256);                     // [2 tiles][2 positions][23 * 24] zero-bordered
-  float* s_sc = reinterpret_cast<float*>(s_mask + 4 * kItPadH * kItPadW);          // [n_w] (x log2 e)
+  uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_lut + 256);                     // [kItMaskStages tiles][2 positions][23 * 24] zero-bordered
+  float* s_gs = reinterpret_cast<float*>(s_mask + kItMaskStages * 2 * kItPadH * kItPadW);  // [kItMaskStages][2 positions][n_w] game-state bias
+  float* s_sc = s_gs + kItMaskStages * 2 * kItNw;                                          // [n_w] (x log2 e)
   float* s_sh = s_sc + 128;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(s_sh + 128);
   uint64_t* a_empty = a_full + 1;
   uint64_t* acc_full = a_empty + 1;   // [2]
   uint64_t* acc_empty = acc_full + 2; // [2]
-  uint64_t* stage_ready = acc_empty + 2;  // [2] masks + game-state bias of a tile staged by warp 0
-  uint64_t* stage_free = stage_ready + 2; // [2] the workers have read the masks
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stage_free + 2);
+  uint64_t* stage_ready = acc_empty + 2;              // [kItMaskStages] masks of a tile staged by warp 0
+  uint64_t* stage_free = stage_ready + kItMaskStages; // [kItMaskStages] the builders have read the masks
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stage_free + kItMaskStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_slices = C / n_w;
@@ -103,8 +105,10 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
       ptx::mbar_init(&acc_empty[s], kItEpiWarps);
+    }
+    for (int s = 0; s < kItMaskStages; ++s) {
       ptx::mbar_init(&stage_ready[s], 1);
-      ptx::mbar_init(&stage_free[s], 1);
+      ptx::mbar_init(&stage_free[s], 1 + kItEpiWarps);  // the builders (masks) and every epilogue warp (bias) are done with it
     }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
@@ -121,15 +125,18 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     // ===== stager: bulk-copies the zero-bordered plane-mask grids of the (at most two) positions a tile touches, one tile
     // ahead of the workers =====
     for (int it = 0; it < n_it; ++it) {
-      const int sb = it & 1;
-      ptx::mbar_wait(&stage_free[sb], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
+      const int sb = it % kItMaskStages;
+      ptx::mbar_wait(&stage_free[sb], ((static_cast<uint32_t>(it / kItMaskStages)) & 1u) ^ 1u);
       const int m0 = (cta_in_slice + it * ctas_per_slice) * 128;
       const int b0 = m0 / kRowsPerPos;
       const int npos = (b0 + 1 < n) ? 2 : 1;
       if (lane == 0) {
-        ptx::mbar_arrive_expect_tx(&stage_ready[sb], static_cast<uint32_t>(npos * kItPadH * kItPadW * 2));
+        ptx::mbar_arrive_expect_tx(&stage_ready[sb], static_cast<uint32_t>(npos * (kItPadH * kItPadW * 2 + n_w * 4)));
         ptx::bulk_load_1d(s_mask + sb * 2 * kItPadH * kItPadW, masks_padded + static_cast<size_t>(b0) * kItPadH * kItPadW,
                           static_cast<uint32_t>(npos * kItPadH * kItPadW * 2), &stage_ready[sb]);
+        for (int pb = 0; pb < npos; ++pb)  // this slice's game-state bias of the tile's position(s)
+          ptx::bulk_load_1d(s_gs + (sb * 2 + pb) * kItNw, gs + static_cast<size_t>(b0 + pb) * C + n0, static_cast<uint32_t>(n_w * 4),
+                            &stage_ready[sb]);
       }
       __syncwarp();
     }
@@ -161,8 +168,8 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     for (int it = 0; it < n_it; ++it) {
       const int m0 = (cta_in_slice + it * ctas_per_slice) * 128;
       const int b0 = m0 / kRowsPerPos;
-      const int sb = it & 1;
-      ptx::mbar_wait(&stage_ready[sb], (static_cast<uint32_t>(it) >> 1) & 1u);
+      const int sb = it % kItMaskStages;
+      ptx::mbar_wait(&stage_ready[sb], static_cast<uint32_t>(it / kItMaskStages) & 1u);
       ptx::mbar_wait(a_empty, (static_cast<uint32_t>(it) & 1u) ^ 1u);  // the MMAs of the previous tile have read A
       const int m = m0 + brow;
       const int pb = m / kRowsPerPos - b0, qq = m % kRowsPerPos;
@@ -208,11 +215,9 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       const int m0 = (cta_in_slice + it * ctas_per_slice) * 128;
       const int m = m0 + q * 32 + lane;
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
-      // game-state bias of this row's position (precomputed by the encode kernel; L2-resident), fetched ahead of the wait
-      const float4* gp = reinterpret_cast<const float4*>(gs + static_cast<size_t>(min(m / kRowsPerPos, n - 1)) * C + n0 + cg * 32);
-      // the quarter's previous stores have read the boxes (waited for by the quarter leader before the barrier)
-      if (qleader) ptx::bulk_wait_read<0>();
-      ptx::named_bar_sync(2 + q, 64);
+      // game-state bias of this row's position: staged in shared memory with the tile's masks (the builders waited for it)
+      const int sb = it % kItMaskStages;
+      const uint32_t gp = ptx::smem_u32(s_gs + (sb * 2 + (m < rows ? m / kRowsPerPos - m0 / kRowsPerPos : 0)) * kItNw + cg * 32);
       ptx::mbar_wait(&acc_full[as], (static_cast<uint32_t>(it) >> 1) & 1u);
       ptx::tc_fence_after_sync();
       const uint32_t ro = static_cast<uint32_t>(lane) * 128u;
@@ -222,19 +227,22 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       uint32_t v[16];
       ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * n_w + col), v);
       ptx::tmem_ld_wait();
-      if (h == 1) {
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
-      }
       float x[16], a[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 g4 = __ldg(gp + 4 * h + i);
+        const float4 g4 = ptx::lds_f4(gp + static_cast<uint32_t>(4 * h + i) * 16u);
         x[4 * i] = __uint_as_float(v[4 * i]) + g4.x;
         x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + g4.y;
         x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + g4.z;
         x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + g4.w;
+      }
+      if (h == 1) {  // the accumulator and the bias are in registers: hand both stages back
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&acc_empty[as]);
+          ptx::mbar_arrive(&stage_free[sb]);
+        }
       }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -261,6 +269,12 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
       uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
       if (!live) r0 = r1 = p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout are zeros
+      if (h == 0) {
+        // the quarter's previous stores have read the boxes: waited for by the quarter leader AFTER the first pass's math,
+        // which so overlaps the TMA engine's reads
+        if (qleader) ptx::bulk_wait_read<0>();
+        ptx::named_bar_sync(2 + q, 64);
+      }
       if (!(debug & 4)) {
         const uint32_t c0 = ((4u * cg + 2u * h) ^ sw) << 4, c1 = ((4u * cg + 2u * h + 1u) ^ sw) << 4;
         ptx::sts_u4(box_raw + ro + c0, r0);
@@ -292,7 +306,7 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
 
 int init_tc_slice_width(int) { return kItNw; }
 size_t init_tc_smem_bytes(int n_w) {
-  return static_cast<size_t>(n_w / 8) * kItSbo + kItABytes + 4 * 2 * kItBoxBytes + 256 * 16 + 4 * kItPadH * kItPadW * 2 + 2 * 128 * 4 + 128 + 1024;
+  return static_cast<size_t>(n_w / 8) * kItSbo + kItABytes + 4 * 2 * kItBoxBytes + 256 * 16 + kItMaskStages * 2 * (kItPadH * kItPadW * 2 + kItNw * 4) + 2 * 128 * 4 + 256 + 1024;
 }
 
 }  // namespace
