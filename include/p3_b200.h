@@ -150,6 +150,24 @@ int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result);
 /* nn::Engine::GetOwnership, cc/nn/engine/engine.h:38-39 (TF impl cc/nn/engine/tf_engine.cc:292-299). */
 int p3_engine_get_ownership(p3_engine* e, int batch_id, float own[P3_NUM_BOARD_LOCS]);
 
+/* ---- pipelined form: two slot banks ---------------------------------------------
+ * The reference serialises LoadBatch x B -> RunInference -> GetBatch x B with mu_ held across RunInference
+ * (cc/nn/nn_interface.cc:286-371), so the GPU idles while workers load and read their slots and while the
+ * copies run.  Here the engine owns P3_NUM_BANKS independent sets of `batch_size` slots: a caller fills one
+ * bank while the other is in flight.  Bank 0 is the slot set of the serial calls above.
+ *   p3_engine_load_batch_bank = nn::Engine::LoadBatch on a bank (`sym` as in p3_engine_load_batch_sym, 0 = none);
+ *   p3_engine_submit          = the asynchronous half of nn::Engine::RunInference (trt_engine.cc:238-300):
+ *                               H2D on a copy stream -> the captured step -> D2H on a second copy stream; returns at once;
+ *   p3_engine_wait            = its stream sync (trt_engine.cc:302-304) for that bank only;
+ *   p3_engine_get_batch_bank  = nn::Engine::GetBatch on a bank (valid after p3_engine_wait, until the next submit).
+ * Kernels of both banks run back to back on one stream; results are identical to the serial calls.
+ * A bank must be waited before it is submitted again (P3_ERR_INVALID_ARG otherwise). */
+#define P3_NUM_BANKS 2
+int p3_engine_load_batch_bank(p3_engine* e, int bank, int batch_id, const p3_go_features* features, int sym);
+int p3_engine_submit(p3_engine* e, int bank);
+int p3_engine_wait(p3_engine* e, int bank);
+int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result);
+
 /* nn::Engine::kind()/path(), cc/nn/engine/engine.h:33-34. */
 const char* p3_engine_path(const p3_engine* e);
 int p3_engine_batch_size(const p3_engine* e);

@@ -11,8 +11,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -169,6 +171,22 @@ struct p3_engine {
   int launches = 0;
   bool aux_host_valid = false;
 
+  // Slot banks of the pipelined form (p3_engine_submit / p3_engine_wait): bank 0 shares the pinned staging of the
+  // serial calls, bank 1 has its own.  Copies run on two copy streams so that the H2D of one bank and the D2H of the
+  // other overlap the tower of the bank in flight; the kernels of both banks share `stream` and the activation buffers.
+  struct Bank {
+    p3_go_features* h_feats = nullptr;
+    p3_infer_result* h_results = nullptr;
+    int8_t* h_sym = nullptr;
+    bool owns_host = false;
+    DevBuf d_feats, d_sym, d_results;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+    std::atomic<int> in_flight{0};
+  };
+  Bank banks[P3_NUM_BANKS];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::mutex submit_mu;  // one bank's enqueue sequence at a time (two infer threads may submit concurrently)
+
   ~p3_engine() {
     for (Step& s : program) {
       if (s.bplan) tc_broadcast_plan_destroy(s.bplan);
@@ -179,6 +197,18 @@ struct p3_engine {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (graph_exec_host) cudaGraphExecDestroy(graph_exec_host);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (Bank& b : banks) {
+      if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
+      if (b.ev_done) cudaEventDestroy(b.ev_done);
+      if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
+      if (b.owns_host) {
+        if (b.h_feats) cudaFreeHost(b.h_feats);
+        if (b.h_results) cudaFreeHost(b.h_results);
+        if (b.h_sym) cudaFreeHost(b.h_sym);
+      }
+    }
+    if (h2d_stream) cudaStreamDestroy(h2d_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
     if (stream) cudaStreamDestroy(stream);
     if (h_feats) cudaFreeHost(h_feats);
     if (h_results) cudaFreeHost(h_results);
@@ -385,6 +415,28 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   if ((rc = e.d_masks.alloc(sizeof(uint16_t) * B * 361))) return rc;
   if ((rc = e.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
   if ((rc = e.d_aux.alloc(sizeof(p3_aux_result) * B))) return rc;
+  for (int k = 0; k < P3_NUM_BANKS; ++k) {
+    p3_engine::Bank& bk = e.banks[k];
+    if (k == 0) {
+      bk.h_feats = e.h_feats, bk.h_results = e.h_results, bk.h_sym = e.h_sym;
+    } else {
+      bk.owns_host = true;
+      P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_feats), sizeof(p3_go_features) * B));
+      P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_results), sizeof(p3_infer_result) * B));
+      P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_sym), B));
+      std::memcpy(bk.h_feats, e.h_feats, sizeof(p3_go_features) * B);
+      std::memset(bk.h_results, 0, sizeof(p3_infer_result) * B);
+      std::memset(bk.h_sym, 0, B);
+    }
+    if ((rc = bk.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
+    if ((rc = bk.d_sym.alloc(B))) return rc;
+    if ((rc = bk.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
+    P3_CUDA(cudaEventCreateWithFlags(&bk.ev_h2d, cudaEventDisableTiming));
+    P3_CUDA(cudaEventCreateWithFlags(&bk.ev_done, cudaEventDisableTiming));
+    P3_CUDA(cudaEventCreateWithFlags(&bk.ev_d2h, cudaEventDisableTiming));
+  }
+  P3_CUDA(cudaStreamCreateWithFlags(&e.h2d_stream, cudaStreamNonBlocking));
+  P3_CUDA(cudaStreamCreateWithFlags(&e.d2h_stream, cudaStreamNonBlocking));
   // residual stream: fp32, or IEEE fp16 in the bf16 engine (fp32 accumulation inside every block)
   if ((rc = e.xraw.alloc((e.bf16 ? sizeof(__half) : sizeof(float)) * R * C))) return rc;
   if ((rc = e.actA.alloc(esz * R * C))) return rc;
@@ -821,6 +873,8 @@ void p3_engine_destroy(p3_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  cudaStreamSynchronize(e->h2d_stream);
+  cudaStreamSynchronize(e->d2h_stream);
   delete e;
 }
 
@@ -867,6 +921,61 @@ int p3_engine_run_inference(p3_engine* e) {
 int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result) {
   if (!e || !result || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_batch: bad argument");
   std::memcpy(result, &e->h_results[batch_id], sizeof(p3_infer_result));
+  return P3_OK;
+}
+
+// ---- pipelined form: two slot banks ----------------------------------------------------------------------------------
+
+int p3_engine_load_batch_bank(p3_engine* e, int bank, int batch_id, const p3_go_features* features, int sym) {
+  if (!e || !features || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch || sym < 0 || sym > 7)
+    return fail(P3_ERR_INVALID_ARG, "load_batch_bank: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  std::memcpy(&bk.h_feats[batch_id], features, sizeof(p3_go_features));
+  bk.h_sym[batch_id] = static_cast<int8_t>(sym);
+  return P3_OK;
+}
+
+int p3_engine_submit(p3_engine* e, int bank) {
+  if (!e || bank < 0 || bank >= P3_NUM_BANKS) return fail(P3_ERR_INVALID_ARG, "submit: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (bk.in_flight.exchange(1, std::memory_order_acq_rel))
+    return fail(P3_ERR_INVALID_ARG, "submit: bank already in flight (p3_engine_wait it first)");
+  std::lock_guard<std::mutex> lock(e->submit_mu);
+  P3_CUDA(cudaSetDevice(e->device));
+  const size_t fbytes = sizeof(p3_go_features) * e->batch, rbytes = sizeof(p3_infer_result) * e->batch;
+  // game state of this bank -> its device staging copy, on the H2D stream (overlaps the other bank's kernels)
+  P3_CUDA(cudaMemcpyAsync(bk.d_feats.p, bk.h_feats, fbytes, cudaMemcpyHostToDevice, e->h2d_stream));
+  P3_CUDA(cudaMemcpyAsync(bk.d_sym.p, bk.h_sym, e->batch, cudaMemcpyHostToDevice, e->h2d_stream));
+  P3_CUDA(cudaEventRecord(bk.ev_h2d, e->h2d_stream));
+  // kernels: staging copy -> the step's fixed input buffers, the captured step, results -> the bank's device copy
+  P3_CUDA(cudaStreamWaitEvent(e->stream, bk.ev_h2d, 0));
+  P3_CUDA(cudaMemcpyAsync(e->d_feats.p, bk.d_feats.p, fbytes, cudaMemcpyDeviceToDevice, e->stream));
+  P3_CUDA(cudaMemcpyAsync(e->d_sym.p, bk.d_sym.p, e->batch, cudaMemcpyDeviceToDevice, e->stream));
+  int rc = e->enqueue_device_maybe_graph(false);
+  if (rc) return rc;
+  P3_CUDA(cudaMemcpyAsync(bk.d_results.p, e->d_results.p, rbytes, cudaMemcpyDeviceToDevice, e->stream));
+  P3_CUDA(cudaEventRecord(bk.ev_done, e->stream));
+  // results -> pinned host memory on the D2H stream (overlaps the next bank's kernels)
+  P3_CUDA(cudaStreamWaitEvent(e->d2h_stream, bk.ev_done, 0));
+  P3_CUDA(cudaMemcpyAsync(bk.h_results, bk.d_results.p, rbytes, cudaMemcpyDeviceToHost, e->d2h_stream));
+  P3_CUDA(cudaEventRecord(bk.ev_d2h, e->d2h_stream));
+  return P3_OK;
+}
+
+int p3_engine_wait(p3_engine* e, int bank) {
+  if (!e || bank < 0 || bank >= P3_NUM_BANKS) return fail(P3_ERR_INVALID_ARG, "wait: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (!bk.in_flight.load(std::memory_order_acquire)) return fail(P3_ERR_INVALID_ARG, "wait: bank was not submitted");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaEventSynchronize(bk.ev_d2h));
+  bk.in_flight.store(0, std::memory_order_release);
+  return P3_OK;
+}
+
+int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result) {
+  if (!e || !result || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch)
+    return fail(P3_ERR_INVALID_ARG, "get_batch_bank: bad argument");
+  std::memcpy(result, &e->banks[bank].h_results[batch_id], sizeof(p3_infer_result));
   return P3_OK;
 }
 

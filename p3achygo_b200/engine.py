@@ -112,6 +112,23 @@ class B200Engine:
         check(lib.p3_engine_get_batch(self._h, batch_id, ptr(out)))
         return out[0]
 
+    # -- pipelined form: two slot banks (include/p3_b200.h) ---------------------------
+    def LoadBatchBank(self, bank: int, batch_id: int, features, sym: int = 0) -> None:
+        arr = np.ascontiguousarray(np.asarray(features, dtype=GO_FEATURES_DTYPE).reshape(1))
+        check(lib.p3_engine_load_batch_bank(self._h, bank, batch_id, ptr(arr), int(sym)))
+
+    def Submit(self, bank: int) -> None:
+        """Asynchronous half of RunInference for one bank (H2D -> step -> D2H on copy streams); returns at once."""
+        check(lib.p3_engine_submit(self._h, bank))
+
+    def Wait(self, bank: int) -> None:
+        check(lib.p3_engine_wait(self._h, bank))
+
+    def GetBatchBank(self, bank: int, batch_id: int) -> np.ndarray:
+        out = np.zeros(1, dtype=INFER_RESULT_DTYPE)
+        check(lib.p3_engine_get_batch_bank(self._h, bank, batch_id, ptr(out)))
+        return out[0]
+
     def GetOwnership(self, batch_id: int) -> np.ndarray:
         """engine.h:38-39"""
         own = np.zeros(NUM_LOCS, dtype=np.float32)

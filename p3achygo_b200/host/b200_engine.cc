@@ -38,6 +38,14 @@ void B200Engine::LoadBatchSym(int batch_id, const GoFeatures& features, int sym)
 }
 void B200Engine::RunInference() { P3_CHECK(p3_engine_run_inference(engine_)); }
 void B200Engine::GetBatch(int batch_id, NNInferResult& result) { P3_CHECK(p3_engine_get_batch(engine_, batch_id, &result)); }
+void B200Engine::LoadBatchBank(int bank, int batch_id, const GoFeatures& features, int sym) {
+  P3_CHECK(p3_engine_load_batch_bank(engine_, bank, batch_id, &features, sym));
+}
+void B200Engine::Submit(int bank) { P3_CHECK(p3_engine_submit(engine_, bank)); }
+void B200Engine::Wait(int bank) { P3_CHECK(p3_engine_wait(engine_, bank)); }
+void B200Engine::GetBatchBank(int bank, int batch_id, NNInferResult& result) {
+  P3_CHECK(p3_engine_get_batch_bank(engine_, bank, batch_id, &result));
+}
 void B200Engine::GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) {
   P3_CHECK(p3_engine_get_ownership(engine_, batch_id, own.data()));
 }

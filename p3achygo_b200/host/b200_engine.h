@@ -23,6 +23,14 @@ class B200Engine final : public Engine {
   // features in the game's own orientation + the symmetry; GetBatch then returns the un-rotated policies.
   void LoadBatchSym(int batch_id, const GoFeatures& features, int sym);
 
+  // Pipelined form over the engine's two slot banks (include/p3_b200.h): fill one bank while the other is in flight.
+  // RunInference() == Submit(0) + Wait(0) in effect; results are identical.
+  static constexpr int kNumBanks = P3_NUM_BANKS;
+  void LoadBatchBank(int bank, int batch_id, const GoFeatures& features, int sym = 0);
+  void Submit(int bank);
+  void Wait(int bank);
+  void GetBatchBank(int bank, int batch_id, NNInferResult& result);
+
   p3_engine* handle() { return engine_; }
   int batch_size() const { return batch_size_; }
 

@@ -124,4 +124,58 @@ int p3_host_benchmark(const char* weights_path, int device, int batch, int versi
   return 0;
 }
 
+// The same cycle over the engine's two slot banks: while bank k's step is on the GPU, the workers read the previous
+// results of bank 1-k and load its next positions, and both banks' copies run on the copy streams.  Every position is
+// still loaded from host memory, evaluated, and read back into a caller-owned NNInferResult inside the timed region.
+//   out[0] whole cycle per batch (us, total wall time / steps)   out[1] LoadBatch x B   out[2] GetBatch x B
+//   out[3] Wait (time the host blocked on the GPU)               out[4] checksum of value_probs
+int p3_host_benchmark_pipelined(const char* weights_path, int device, int batch, int version, int precision,
+                                const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
+  auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
+  std::vector<nn::NNInferResult> results(batch);
+  WorkerPool pool(threads);
+  double t_load = 0, t_get = 0, t_wait = 0, checksum = 0;
+  int cursor = 0;
+  const int total = warmup + steps;
+  auto load = [&](int bank) {
+    const int base = cursor;
+    cursor = (cursor + batch) % n_positions;
+    pool.run(batch, [&](int b) { engine->LoadBatchBank(bank, b, positions[(base + b) % n_positions]); });
+  };
+  Clock::time_point t_start = Clock::now();
+  load(0);
+  engine->Submit(0);
+  for (int it = 0; it < total; ++it) {
+    if (it == warmup) {  // drain, then start the clock with bank `it` loaded and submitted inside the timed region
+      engine->Wait(it & 1);
+      t_start = Clock::now();
+      load(it & 1);
+      engine->Submit(it & 1);
+      t_load = t_get = t_wait = 0;
+    }
+    const int cur = it & 1, nxt = cur ^ 1;
+    if (it + 1 < total) {
+      auto l0 = Clock::now();
+      load(nxt);
+      t_load += us_since(l0);
+      engine->Submit(nxt);
+    }
+    auto w0 = Clock::now();
+    engine->Wait(cur);
+    t_wait += us_since(w0);
+    auto g0 = Clock::now();
+    pool.run(batch, [&](int b) { engine->GetBatchBank(cur, b, results[b]); });
+    t_get += us_since(g0);
+    if (it >= warmup)
+      for (int b = 0; b < batch; ++b) checksum += results[b].value_probs[1];
+  }
+  const double total_us = us_since(t_start);
+  out[0] = total_us / steps;
+  out[1] = t_load / steps;
+  out[2] = t_get / steps;
+  out[3] = t_wait / steps;
+  out[4] = checksum;
+  return 0;
+}
+
 }  // extern "C"

@@ -9,42 +9,52 @@
 
 namespace nn {
 
-NNInterfaceB200::NNInterfaceB200(int num_threads, int64_t timeout_us, std::unique_ptr<Engine> engine)
-    : num_threads_(num_threads), timeout_us_(timeout_us), engine_(std::move(engine)), thread_info_(num_threads),
-      num_registered_threads_(num_threads) {
+NNInterfaceB200::NNInterfaceB200(int num_threads, int64_t timeout_us, std::unique_ptr<Engine> engine, int num_banks)
+    : num_threads_(num_threads), timeout_us_(timeout_us), engine_(std::move(engine)), num_banks_(num_banks),
+      slots_per_bank_(num_threads / (num_banks < 1 ? 1 : num_banks)) {
   b200_ = dynamic_cast<B200Engine*>(engine_.get());
-  if (num_threads_ > 1) infer_thread_ = std::thread(&NNInterfaceB200::InferLoop, this);
+  if (num_banks_ < 1 || num_banks_ > B200Engine::kNumBanks || num_threads_ % num_banks_ != 0 || (num_banks_ > 1 && !b200_) ||
+      (num_banks_ > 1 && b200_->batch_size() != slots_per_bank_)) {
+    std::fprintf(stderr, "NNInterfaceB200: %d banks need a B200Engine of batch num_threads / banks\n", num_banks);
+    std::abort();  // LOG(FATAL) in the reference's idiom
+  }
+  for (int k = 0; k < num_banks_; ++k) banks_.emplace_back(new Bank(k, k * slots_per_bank_, slots_per_bank_));
+  if (num_threads_ > 1)
+    for (auto& b : banks_) b->infer_thread = std::thread(&NNInterfaceB200::InferLoop, this, b.get());
 }
 
 NNInterfaceB200::~NNInterfaceB200() {  // nn_interface.cc:82-90
-  {
-    std::lock_guard<std::mutex> l(mu_);
+  for (auto& b : banks_) {
+    std::lock_guard<std::mutex> l(b->mu);
     running_.store(false, std::memory_order_release);
   }
-  infer_cv_.notify_all();
-  if (infer_thread_.joinable()) infer_thread_.join();
+  for (auto& b : banks_) b->infer_cv.notify_all();
+  for (auto& b : banks_)
+    if (b->infer_thread.joinable()) b->infer_thread.join();
 }
 
 void NNInterfaceB200::RegisterThread(int thread_id) {
-  std::lock_guard<std::mutex> l(mu_);
-  ThreadInfo& t = thread_info_[thread_id];
+  Bank& bank = BankOf(thread_id);
+  std::lock_guard<std::mutex> l(bank.mu);
+  ThreadInfo& t = bank.thread_info[thread_id - bank.first];
   if (t.registered) return;
   t.registered = true;
   t.loaded_for_inference = false;
   t.res_ready.store(false, std::memory_order_relaxed);
-  ++num_registered_threads_;
+  ++bank.num_registered;
 }
 
 void NNInterfaceB200::UnregisterThread(int thread_id) {
+  Bank& bank = BankOf(thread_id);
   {
-    std::lock_guard<std::mutex> l(mu_);
-    ThreadInfo& t = thread_info_[thread_id];
+    std::lock_guard<std::mutex> l(bank.mu);
+    ThreadInfo& t = bank.thread_info[thread_id - bank.first];
     if (!t.registered) return;
     t.registered = false;
     t.loaded_for_inference = false;
-    --num_registered_threads_;
+    --bank.num_registered;
   }
-  infer_cv_.notify_all();  // the remaining threads may now satisfy ShouldInfer
+  bank.infer_cv.notify_all();  // the remaining threads may now satisfy ShouldInfer
 }
 
 void NNInterfaceB200::SignalLoadedAndBlockUntilReady(int thread_id) {  // nn_interface.h:293-309
@@ -53,23 +63,40 @@ void NNInterfaceB200::SignalLoadedAndBlockUntilReady(int thread_id) {  // nn_int
     num_inferences_.fetch_add(1, std::memory_order_relaxed);
     return;
   }
-  ThreadInfo& t = thread_info_[thread_id];
+  Bank& bank = BankOf(thread_id);
+  ThreadInfo& t = bank.thread_info[thread_id - bank.first];
   {
-    std::lock_guard<std::mutex> l(mu_);
+    std::lock_guard<std::mutex> l(bank.mu);
     t.loaded_for_inference = true;
     t.res_ready.store(false, std::memory_order_relaxed);
   }
-  infer_cv_.notify_all();
-  std::unique_lock<std::mutex> l(mu_);
-  ready_cv_.wait(l, [&]() { return t.res_ready.load(std::memory_order_acquire); });
+  bank.infer_cv.notify_all();
+  std::unique_lock<std::mutex> l(bank.mu);
+  bank.ready_cv.wait(l, [&]() { return t.res_ready.load(std::memory_order_acquire); });
+}
+
+void NNInterfaceB200::EngineLoad(int thread_id, const GoFeatures& features, int sym, bool with_sym) {
+  if (num_banks_ > 1) {
+    b200_->LoadBatchBank(thread_id / slots_per_bank_, thread_id % slots_per_bank_, features, with_sym ? sym : 0);
+  } else if (with_sym) {
+    b200_->LoadBatchSym(thread_id, features, sym);
+  } else {
+    engine_->LoadBatch(thread_id, features);
+  }
+}
+
+void NNInterfaceB200::EngineGet(int thread_id, NNInferResult& result) {
+  if (num_banks_ > 1) b200_->GetBatchBank(thread_id / slots_per_bank_, thread_id % slots_per_bank_, result);
+  else engine_->GetBatch(thread_id, result);
 }
 
 NNInferResult NNInterfaceB200::LoadAndGetInference(int thread_id, const GoFeatures& features) {
-  engine_->LoadBatch(thread_id, features);  // no lock held (nn_interface.cc:276)
+  EngineLoad(thread_id, features, 0, false);  // no lock held (nn_interface.cc:276)
   SignalLoadedAndBlockUntilReady(thread_id);
   NNInferResult r;
-  engine_->GetBatch(thread_id, r);
-  thread_info_[thread_id].res_ready.store(false, std::memory_order_release);  // nn_interface.h:256-261
+  EngineGet(thread_id, r);
+  Bank& bank = BankOf(thread_id);
+  bank.thread_info[thread_id - bank.first].res_ready.store(false, std::memory_order_release);  // nn_interface.h:256-261
   return r;
 }
 
@@ -78,22 +105,23 @@ NNInferResult NNInterfaceB200::LoadAndGetInferenceSym(int thread_id, const GoFea
     std::fprintf(stderr, "NNInterfaceB200::LoadAndGetInferenceSym needs a B200Engine\n");
     std::abort();
   }
-  b200_->LoadBatchSym(thread_id, features, sym);
+  EngineLoad(thread_id, features, sym, true);
   SignalLoadedAndBlockUntilReady(thread_id);
   NNInferResult r;
-  engine_->GetBatch(thread_id, r);
-  thread_info_[thread_id].res_ready.store(false, std::memory_order_release);
+  EngineGet(thread_id, r);
+  Bank& bank = BankOf(thread_id);
+  bank.thread_info[thread_id - bank.first].res_ready.store(false, std::memory_order_release);
   return r;
 }
 
-void NNInterfaceB200::InferLoop() {
-  while (running_.load(std::memory_order_acquire)) Infer();
+void NNInterfaceB200::InferLoop(Bank* bank) {
+  while (running_.load(std::memory_order_acquire)) Infer(*bank);
 }
 
-bool NNInterfaceB200::ShouldInfer() const {  // kAuto branch of nn_interface.cc:373-400
+bool NNInterfaceB200::ShouldInfer(const Bank& bank) const {  // kAuto branch of nn_interface.cc:373-400
   if (!running_.load(std::memory_order_acquire)) return true;
   bool exists_pending = false;
-  for (const ThreadInfo& t : thread_info_) {
+  for (const ThreadInfo& t : bank.thread_info) {
     if (!t.registered) continue;
     if (!t.loaded_for_inference) return false;
     exists_pending = true;
@@ -101,37 +129,42 @@ bool NNInterfaceB200::ShouldInfer() const {  // kAuto branch of nn_interface.cc:
   return exists_pending;
 }
 
-void NNInterfaceB200::Infer() {  // nn_interface.cc:286-371
-  std::unique_lock<std::mutex> l(mu_);
+void NNInterfaceB200::Infer(Bank& bank) {  // nn_interface.cc:286-371
+  std::unique_lock<std::mutex> l(bank.mu);
   if (timeout_us_ > 0)
-    infer_cv_.wait_for(l, std::chrono::microseconds(timeout_us_), [this]() { return ShouldInfer(); });
+    bank.infer_cv.wait_for(l, std::chrono::microseconds(timeout_us_), [&]() { return ShouldInfer(bank); });
   else
-    infer_cv_.wait(l, [this]() { return ShouldInfer(); });
-  if (!running_.load(std::memory_order_acquire) || num_registered_threads_ == 0) return;
+    bank.infer_cv.wait(l, [&]() { return ShouldInfer(bank); });
+  if (!running_.load(std::memory_order_acquire) || bank.num_registered == 0) return;
   // never overwrite an unread result
-  for (const ThreadInfo& t : thread_info_)
+  for (const ThreadInfo& t : bank.thread_info)
     if (t.res_ready.load(std::memory_order_acquire)) return;
   bool any_loaded = false;
-  for (const ThreadInfo& t : thread_info_) any_loaded = any_loaded || t.loaded_for_inference;
+  for (const ThreadInfo& t : bank.thread_info) any_loaded = any_loaded || t.loaded_for_inference;
   if (!any_loaded) return;
   // Only the slots that are loaded NOW get this run's results: a slot whose worker is still inside LoadBatch (or loads
   // while the engine runs) is marked loaded later and waits for the next cycle (nn_interface.cc:355-369).  The reference
   // holds mu_ across RunInference; workers only need mu_ to mark themselves loaded, so releasing it here is equivalent for
   // them and lets them queue up for the next cycle while the GPU works.
-  std::vector<char> in_batch(num_threads_, 0);
-  for (int i = 0; i < num_threads_; ++i) in_batch[i] = thread_info_[i].registered && thread_info_[i].loaded_for_inference;
+  std::vector<char> in_batch(bank.size, 0);
+  for (int i = 0; i < bank.size; ++i) in_batch[i] = bank.thread_info[i].registered && bank.thread_info[i].loaded_for_inference;
   l.unlock();
-  engine_->RunInference();
+  if (num_banks_ > 1) {
+    b200_->Submit(bank.index);  // the other bank's step may be on the GPU: this one queues behind it, copies overlap
+    b200_->Wait(bank.index);
+  } else {
+    engine_->RunInference();
+  }
   num_inferences_.fetch_add(1, std::memory_order_relaxed);
   l.lock();
-  for (int i = 0; i < num_threads_; ++i) {
+  for (int i = 0; i < bank.size; ++i) {
     if (!in_batch[i]) continue;
-    ThreadInfo& t = thread_info_[i];
+    ThreadInfo& t = bank.thread_info[i];
     t.loaded_for_inference = false;
     t.res_ready.store(true, std::memory_order_release);
   }
   l.unlock();
-  ready_cv_.notify_all();
+  bank.ready_cv.notify_all();
 }
 
 }  // namespace nn
@@ -230,10 +263,13 @@ int p3_host_iface_sync_test(int threads, int millis, int timeout_us, long long* 
 // `threads` workers each evaluate `per_thread` positions through NNInterfaceB200 over a real B200 engine with `threads`
 // slots (1024 is fine: no kMaxNumThreads cap); thread t evaluates positions t, t + threads, ... and stores NNInferResult
 // records at results[position].  use_sym != 0: LoadAndGetInferenceSym with symmetry (position % 8).
-int p3_host_iface_run(const char* weights_path, int device, int threads, int version, int precision, const p3_go_features* positions,
-                      int n_positions, int use_sym, int timeout_us, p3_infer_result* results, long long* n_inferences) {
-  auto engine = nn::B200Engine::Create(weights_path, threads, version, device, precision);
-  nn::NNInterfaceB200 iface(threads, timeout_us, std::move(engine));
+// `banks` = 2: the double-buffered interface over an engine of batch threads / 2.
+int p3_host_iface_run_banks(const char* weights_path, int device, int threads, int version, int precision,
+                            const p3_go_features* positions, int n_positions, int use_sym, int timeout_us, int banks,
+                            p3_infer_result* results, long long* n_inferences, double* seconds) {
+  auto engine = nn::B200Engine::Create(weights_path, threads / banks, version, device, precision);
+  nn::NNInterfaceB200 iface(threads, timeout_us, std::move(engine), banks);
+  const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
   for (int tid = 0; tid < threads; ++tid)
     pool.emplace_back([&, tid]() {
@@ -242,8 +278,15 @@ int p3_host_iface_run(const char* weights_path, int device, int threads, int ver
       iface.UnregisterThread(tid);
     });
   for (auto& t : pool) t.join();
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (n_inferences) *n_inferences = static_cast<long long>(iface.num_inferences());
   return 0;
+}
+
+int p3_host_iface_run(const char* weights_path, int device, int threads, int version, int precision, const p3_go_features* positions,
+                      int n_positions, int use_sym, int timeout_us, p3_infer_result* results, long long* n_inferences) {
+  return p3_host_iface_run_banks(weights_path, device, threads, version, precision, positions, n_positions, use_sym, timeout_us, 1,
+                                 results, n_inferences, nullptr);
 }
 
 }  // extern "C"

@@ -8,6 +8,10 @@
 //     whatever is loaded; never while a result is still unread, never with nothing loaded; only the slots that were loaded
 //     before the run are marked ready (a slot loaded during the run waits for the next cycle);
 //   * Engine::GetBatch never overlaps RunInference; res_ready is cleared after GetBatch.
+// Double-buffered form: with `num_banks` = 2 over a B200Engine of batch num_threads / 2, the worker threads
+// are split into two slot banks (thread t -> bank t / (num_threads / 2)), each with its own lock, infer thread and the
+// protocol above; a bank's infer thread calls B200Engine::Submit + Wait instead of RunInference, so bank 1's workers load
+// and read their slots (and its copies run) while bank 0's step is on the GPU.  The invariants hold per bank.
 // What is NOT here: building GoFeatures from a game::Game (cc/game stays on the reference side of the boundary) and the
 // per-thread NN cache (cc/core/lru_cache.h, keyed on zobrist hashes of game::Board).
 #pragma once
@@ -28,7 +32,7 @@ class B200Engine;
 class NNInterfaceB200 {
  public:
   static constexpr int64_t kTimeoutUs = 400;  // nn_interface.h:205
-  NNInterfaceB200(int num_threads, int64_t timeout_us, std::unique_ptr<Engine> engine);
+  NNInterfaceB200(int num_threads, int64_t timeout_us, std::unique_ptr<Engine> engine, int num_banks = 1);
   ~NNInterfaceB200();
   NNInterfaceB200(const NNInterfaceB200&) = delete;
   NNInterfaceB200& operator=(const NNInterfaceB200&) = delete;
@@ -51,23 +55,34 @@ class NNInterfaceB200 {
     bool loaded_for_inference = false;
     std::atomic<bool> res_ready{false};
   };
+  // one slot bank: the reference NNInterface's state (nn_interface.h:329-345) for `size` consecutive thread ids
+  struct Bank {
+    explicit Bank(int index, int first, int size) : index(index), first(first), size(size), thread_info(size), num_registered(size) {}
+    const int index, first, size;
+    mutable std::mutex mu;
+    std::condition_variable infer_cv;  // workers -> infer thread ("a slot was loaded / a thread left")
+    std::condition_variable ready_cv;  // infer thread -> workers ("results are ready")
+    std::vector<ThreadInfo> thread_info;
+    int num_registered;
+    std::thread infer_thread;
+  };
+  Bank& BankOf(int thread_id) { return *banks_[thread_id / slots_per_bank_]; }
   void SignalLoadedAndBlockUntilReady(int thread_id);
-  void InferLoop();
-  void Infer();
-  bool ShouldInfer() const;  // mu_ held
+  void InferLoop(Bank* bank);
+  void Infer(Bank& bank);
+  bool ShouldInfer(const Bank& bank) const;  // bank.mu held
+  void EngineLoad(int thread_id, const GoFeatures& features, int sym, bool with_sym);
+  void EngineGet(int thread_id, NNInferResult& result);
 
   const int num_threads_;
   const int64_t timeout_us_;
   std::unique_ptr<Engine> engine_;
   B200Engine* b200_ = nullptr;
-  mutable std::mutex mu_;
-  std::condition_variable infer_cv_;   // workers -> infer thread ("a slot was loaded / a thread left")
-  std::condition_variable ready_cv_;   // infer thread -> workers ("results are ready")
-  std::vector<ThreadInfo> thread_info_;
-  int num_registered_threads_;
+  const int num_banks_;
+  const int slots_per_bank_;
+  std::vector<std::unique_ptr<Bank>> banks_;
   std::atomic<bool> running_{true};
   std::atomic<uint64_t> num_inferences_{0};
-  std::thread infer_thread_;
 };
 
 }  // namespace nn

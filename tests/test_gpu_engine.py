@@ -283,3 +283,44 @@ def test_symmetry_on_gpu_equals_host_symmetry(precision_name, weight_dir, golden
             assert np.array_equal(np.asarray(rh[field]), np.asarray(rd[field]))
     host.close()
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+def test_slot_banks_equal_serial_calls(precision_name, weight_dir, golden_positions):
+    """The pipelined form (p3_engine_submit / p3_engine_wait over two slot banks) returns, bit for bit, what
+    LoadBatch -> RunInference -> GetBatch returns for the same positions - with both banks in flight at once, over several
+    rounds, with the symmetry on the GPU, and a bank cannot be submitted twice without a wait."""
+    from p3achygo_b200 import engine as E
+    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B, rounds = 8, 3
+    feats = golden_positions["feats"][:2 * B * rounds]
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=prec)
+    want = []
+    for lo in range(0, len(feats), B):
+        for b in range(B):
+            eng.LoadBatchSym(b, feats[lo + b], (lo + b) % 8)
+        eng.RunInference()
+        want.append([eng.GetBatch(b).copy() for b in range(B)])
+    with pytest.raises(E.P3Error):
+        eng.Wait(0)                          # nothing submitted
+    for r in range(rounds):
+        for bank in (0, 1):
+            lo = (2 * r + bank) * B
+            for b in range(B):
+                eng.LoadBatchBank(bank, b, feats[lo + b], (lo + b) % 8)
+            eng.Submit(bank)                 # bank 0 and bank 1 are in flight together
+        with pytest.raises(E.P3Error):
+            eng.Submit(1)                    # not waited yet
+        for bank in (1, 0):                  # wait order is free
+            eng.Wait(bank)
+            for b in range(B):
+                assert _same(eng.GetBatchBank(bank, b), want[2 * r + bank][b]), (r, bank, b)
+    # the serial calls still work afterwards and share bank 0's slots
+    for b in range(B):
+        eng.LoadBatchSym(b, feats[b], b % 8)
+    eng.RunInference()
+    for b in range(B):
+        assert _same(eng.GetBatch(b), want[0][b])
+    eng.close()

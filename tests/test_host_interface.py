@@ -20,6 +20,9 @@ def _host():
     h.p3_host_iface_sync_test.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     h.p3_host_iface_run.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    h.p3_host_iface_run_banks.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)]
     return h
 
 
@@ -59,3 +62,26 @@ def test_interface_over_b200_engine(use_sym, weight_dir, golden_positions):
             for f in r.dtype.names:
                 assert np.array_equal(np.asarray(r[f]), np.asarray(results[lo + s][f])), (lo + s, f)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_sym", [0, 1])
+def test_double_buffered_interface_equals_single(use_sym, weight_dir, golden_positions):
+    """NNInterfaceB200 with two slot banks (256 workers over a 128-slot engine, each bank with its own infer thread calling
+    Submit + Wait) serves every worker the same bits as the single-bank interface."""
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200._lib import INFER_RESULT_DTYPE
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    threads, n = 256, 1024
+    feats = np.ascontiguousarray(np.resize(golden_positions["feats"], n))
+    out = {}
+    for banks in (1, 2):
+        results = np.zeros(n, dtype=INFER_RESULT_DTYPE)
+        ninf, secs = ctypes.c_longlong(0), ctypes.c_double(0)
+        _host().p3_host_iface_run_banks(path.encode(), 0, threads, 1, E.PRECISION_BF16, feats.ctypes.data_as(ctypes.c_void_p), n,
+                                        use_sym, 400, banks, results.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ninf),
+                                        ctypes.byref(secs))
+        assert ninf.value >= n // threads * banks
+        out[banks] = results
+    for f in INFER_RESULT_DTYPE.names:
+        assert np.array_equal(out[1][f], out[2][f]), f
