@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const p3_go_features* __res
   for (int i = threadIdx.x; i < kFeatWords; i += blockDim.x) s_raw[i] = src[i];
   __syncthreads();
   const p3_go_features& f = *reinterpret_cast<const p3_go_features*>(s_raw);
-  const int bsize = f.bsize;
+  const int bsize = min(max(f.bsize, 0), P3_BOARD_LEN);  // a torn / garbage record must not index outside the 361-entry grids
   const int8_t color = f.color;
   // ApplySymmetry (cc/game/symmetry.h:42-51): sym_grid[T(i)] = grid[i], i.e. output point p reads source point Tinv(p);
   // the caller hands over identity-orientation features when it gives a symmetry (NNInterface::LoadBatch, nn_interface.cc:245-277)

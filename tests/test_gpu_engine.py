@@ -324,3 +324,33 @@ def test_slot_banks_equal_serial_calls(precision_name, weight_dir, golden_positi
     for b in range(B):
         assert _same(eng.GetBatch(b), want[0][b])
     eng.close()
+
+
+@pytest.mark.gpu
+def test_garbage_slots_do_not_fault(weight_dir, golden_positions):
+    """LoadBatch may overlap RunInference (cc/nn/nn_interface.cc:276), so the H2D copy can pick up a half-written slot; the
+    reference just does not mark such a slot ready (nn_interface.cc:355-369).  Whatever bytes a slot holds, the step must run
+    to completion and leave the other slots' results untouched."""
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200._lib import GO_FEATURES_DTYPE
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 8
+    feats = golden_positions["feats"][:B]
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    for b in range(B):
+        eng.LoadBatch(b, feats[b])
+    eng.RunInference()
+    want = [eng.GetBatch(b).copy() for b in range(B)]
+    rng = np.random.default_rng(5)
+    junk = rng.integers(0, 256, size=(4, 1860), dtype=np.uint8).view(GO_FEATURES_DTYPE).reshape(-1)
+    for k, b in enumerate((1, 3, 4, 6)):
+        eng.LoadBatch(b, junk[k])
+    eng.RunInference()
+    for b in (0, 2, 5, 7):
+        assert _same(eng.GetBatch(b), want[b])
+    for b in (1, 3, 4, 6):
+        eng.LoadBatch(b, feats[b])
+    eng.RunInference()
+    for b in range(B):
+        assert _same(eng.GetBatch(b), want[b])
+    eng.close()

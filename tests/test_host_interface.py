@@ -73,7 +73,8 @@ def test_double_buffered_interface_equals_single(use_sym, weight_dir, golden_pos
     from p3achygo_b200._lib import INFER_RESULT_DTYPE
     path, cfg, tensors = weight_dir("b10c128btl3")
     threads, n = 256, 1024
-    feats = np.ascontiguousarray(np.resize(golden_positions["feats"], n))
+    feats = np.ascontiguousarray(golden_positions["feats"][:n])
+    assert len(feats) == n and feats.dtype.itemsize == 1860
     out = {}
     for banks in (1, 2):
         results = np.zeros(n, dtype=INFER_RESULT_DTYPE)
