@@ -217,6 +217,22 @@ int p3_board_liberties(int device, const int8_t* boards, int n, int8_t* out);
 int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const int8_t* forbidden,
                   int n, uint8_t* out);
 
+/* Rules from a game record, entirely on the GPU: for `n` games given as move lists
+ * (game::Game::moves(), cc/game/game.h; pad moves of game.cc:20 excluded), replay them from the empty board and return
+ *   boards   [n,361]  the position (Board::position(), +1 black / -1 white),
+ *   laddered [n,361]  Board::GetLadderedStones(), cc/game/board.cc:692-899 (what NNInterface::LoadBatch puts in
+ *                     GoFeatures::stones_laddered, cc/nn/nn_interface.cc:268-270),
+ *   legal    [n,362]  Game::IsValidMove for colors[b] over all encodings, cc/game/game.cc:45-51 -> Board::PlayMoveDry,
+ *                     cc/game/board.cc:595-644: occupied, pass-alive, self-capture AND positional superko,
+ *   status   [n]      0 = ok, bit 0 = the move list is not a legal game, bit 1 = candidate list overflow in the reader.
+ * moves [n,max_moves] int16: board point 0..360 or 361 = pass, + P3_MOVE_WHITE for a white move; entries beyond
+ * num_moves[b] are ignored.  `forbidden` (optional, [n,361], non-zero = prohibited): the reference's pass-alive regions
+ * (Benson, only populated after three passes, board.cc:587-590), which stay on the host as for p3_legal_mask.
+ * boards / laddered / legal may each be NULL (legal needs colors).  All pointers are HOST memory. */
+#define P3_MOVE_WHITE 512
+int p3_game_derive(int device, const int16_t* moves, const int32_t* num_moves, int max_moves, const int8_t* forbidden,
+                   const int8_t* colors, int n, int8_t* boards, int8_t* laddered, uint8_t* legal, int32_t* status);
+
 /* Gumbel root sampling, cc/mcts/gumbel.cc:283-321 with core::Probability::GumbelSample
  * (cc/core/probability.cc:12-30) over PCG32 (cc/core/rand.cc:32-71), for `n` independent roots.
  *   logits [n,362], legal [n,362] (0 = masked: logit -10000, no noise, no PRNG draw),

@@ -78,6 +78,8 @@ def ref():
         L.ref_game_laddered.argtypes = [vp, vp]
         L.ref_game_legal_mask.argtypes = [vp, ci, vp]
         L.ref_game_features.argtypes = [vp, ci, ci, vp]
+        L.ref_game_moves.argtypes = [vp, vp, ci]
+        L.ref_game_move_status.argtypes = [vp, ci, vp]
         L.ref_load_go_features.argtypes = [vp, ci, ci, vp, vp]
         L.ref_transform_index.argtypes = [ci, ci]
         L.ref_transform_inv.argtypes = [ci, ci]

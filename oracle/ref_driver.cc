@@ -77,6 +77,26 @@ void ref_game_legal_mask(void* gp, int color, uint8_t* out) {
     out[i] = g->IsValidMove(i, static_cast<Color>(color)) ? 1 : 0;
 }
 
+// Game::moves() without the kMoveOffset pad (cc/game/game.cc:20,30-32), encoded as include/p3_b200.h's p3_game_derive
+// expects: point 0..360 or 361 = pass, + 512 for WHITE.  Returns the number of moves.
+int ref_game_moves(void* gp, int16_t* out, int cap) {
+  Game& g = *static_cast<Game*>(gp);
+  const int n = std::min(g.num_moves(), cap);
+  for (int i = 0; i < n; ++i) {
+    const game::Move mv = g.move(i);
+    const int point = mv.loc == game::kPassLoc ? 361 : mv.loc.i * BOARD_LEN + mv.loc.j;
+    out[i] = static_cast<int16_t>(point + (mv.color == WHITE ? 512 : 0));
+  }
+  return g.num_moves();
+}
+// Board::PlayMoveDry(loc, color).status for every board point (cc/game/board.cc:595-644): 0 kValid, 3 kLocNotEmpty,
+// 4 kPassAliveRegion, 5 kSelfCapture, 6 kRepeatedPosition.
+void ref_game_move_status(void* gp, int color, uint8_t* out) {
+  const game::Board& b = static_cast<Game*>(gp)->board();
+  for (int p = 0; p < 361; ++p)
+    out[p] = static_cast<uint8_t>(b.PlayMoveDry(Loc{p / BOARD_LEN, p % BOARD_LEN}, static_cast<Color>(color)).status);
+}
+
 // NNInterface::LoadBatch restated (cc/nn/nn_interface.cc:245-277): gather the last five
 // moves oldest->newest (noop pad, pass kept untransformed), apply `sym` to the board and
 // the four derived grids, fill GoFeatures.

@@ -80,7 +80,7 @@ EXPORTS = [
     "p3_engine_load_batch_bank", "p3_engine_submit", "p3_engine_wait", "p3_engine_get_batch_bank",
     "p3_engine_get_ownership", "p3_engine_path", "p3_engine_batch_size", "p3_engine_get_planes", "p3_engine_get_aux",
     "p3_engine_run_device", "p3_engine_upload", "p3_engine_profile", "p3_engine_stage_ms", "p3_engine_launches_per_run", "p3_engine_flops_per_position",
-    "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_gumbel_topk",
+    "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_game_derive", "p3_gumbel_topk",
     "p3_conv_test", "p3_broadcast_test", "p3_block_boundary_test", "p3_last_error", "p3_version",
 ]
 
@@ -122,6 +122,7 @@ def _load() -> ctypes.CDLL:
     lib.p3_encode_features.argtypes = [ci, vp, ci, ci, vp, vp]
     lib.p3_board_liberties.argtypes = [ci, vp, ci, vp]
     lib.p3_legal_mask.argtypes = [ci, vp, vp, vp, ci, vp]
+    lib.p3_game_derive.argtypes = [ci, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp]
     lib.p3_gumbel_topk.argtypes = [ci, vp, vp, vp, ci, cf, ci, vp, vp, vp]
     lib.p3_conv_test.argtypes = [ci, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.p3_broadcast_test.argtypes = [ci, ci, vp, vp, vp, ci, ci, vp]

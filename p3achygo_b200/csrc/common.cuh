@@ -198,6 +198,9 @@ int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result
                  cudaStream_t stream, bool accurate = true, const int8_t* sym = nullptr);
 
 // ---- gumbel (gumbel.cu) --------------------------------------------------------------------------------------
+// ladder.cu: replay of move lists -> boards, laddered stones (board.cc:692-899), exact legal masks (board.cc:595-644); device pointers
+int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
+               int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream);
 int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
                   int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid, cudaStream_t stream);
 

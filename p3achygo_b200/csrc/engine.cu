@@ -1162,6 +1162,33 @@ int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const 
   return P3_OK;
 }
 
+int p3_game_derive(int device, const int16_t* moves, const int32_t* num_moves, int max_moves, const int8_t* forbidden,
+                   const int8_t* colors, int n, int8_t* boards, int8_t* laddered, uint8_t* legal, int32_t* status) {
+  if (!moves || !num_moves || max_moves <= 0 || n < 0 || !status || (legal && !colors))
+    return fail(P3_ERR_INVALID_ARG, "game_derive: bad argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return P3_OK;
+  DevBuf dm, dn, dfb, dc, db, dl, dlegal, dst;
+  if ((rc = upload(dm, moves, static_cast<size_t>(n) * max_moves * sizeof(int16_t))) ||
+      (rc = upload(dn, num_moves, static_cast<size_t>(n) * sizeof(int32_t))) || (rc = dst.alloc(static_cast<size_t>(n) * sizeof(int32_t))))
+    return rc;
+  if (forbidden && (rc = upload(dfb, forbidden, static_cast<size_t>(n) * 361))) return rc;
+  if (colors && (rc = upload(dc, colors, n))) return rc;
+  if (boards && (rc = db.alloc(static_cast<size_t>(n) * 361))) return rc;
+  if (laddered && (rc = dl.alloc(static_cast<size_t>(n) * 361))) return rc;
+  if (legal && (rc = dlegal.alloc(static_cast<size_t>(n) * 362))) return rc;
+  rc = ladder_run(dm.as<int16_t>(), dn.as<int32_t>(), max_moves, forbidden ? dfb.as<int8_t>() : nullptr,
+                  colors ? dc.as<int8_t>() : nullptr, n, boards ? db.as<int8_t>() : nullptr, laddered ? dl.as<int8_t>() : nullptr,
+                  legal ? dlegal.as<uint8_t>() : nullptr, dst.as<int32_t>(), 0);
+  if (rc) return rc;
+  if (boards) P3_CUDA(cudaMemcpy(boards, db.p, db.bytes, cudaMemcpyDeviceToHost));
+  if (laddered) P3_CUDA(cudaMemcpy(laddered, dl.p, dl.bytes, cudaMemcpyDeviceToHost));
+  if (legal) P3_CUDA(cudaMemcpy(legal, dlegal.p, dlegal.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(status, dst.p, dst.bytes, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
 int p3_gumbel_topk(int device, const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
                    int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid) {
   if (!logits || !legal || !prng_state || !out_moves || !out_scores || !out_kvalid || n < 0)

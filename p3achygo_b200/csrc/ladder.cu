@@ -1,0 +1,499 @@
+// Go rules on the GPU from a game's move list: position replay with positional-superko history, the ladder reader
+// (Board::GetLadderedStones, cc/game/board.cc:692-899) and the exact legal-move mask (Board::PlayMoveDry,
+// cc/game/board.cc:595-644), so the derived feature grids no longer have to come from the host.
+//
+// Representation: ONE WARP PER BOARD.  Lane r (0..18) holds row r of the black stones and of the white stones as 19-bit
+// masks in two registers; lanes 19..31 hold zeros.  Everything the rules need is then a handful of warp-uniform bit
+// operations:
+//   * the 4-neighbourhood of a point set is (x << 1 | x >> 1) within a row plus one shuffle up and one shuffle down;
+//   * a group is the fix point of  x |= nbrs(x) & colour  (flood), its liberties are nbrs(group) & empty;
+//   * the stones a move captures are the part of the adjacent opposing groups that cannot reach an empty point once the
+//     stone stands; a move without captures whose own group then has no liberty is self-capture
+//     (Board::IsSelfCapture, board.cc:901-915, is exactly that condition);
+//   * positional superko: a 64-bit Zobrist hash over (point, colour), updated by the played stone and the captured
+//     stones, looked up in the list of the game's earlier positions plus the hashes on the current search path
+//     (Board::seen_states_ travels with every Board copy the reference's Solve makes, board.cc:794-798).
+// The history list comes from replaying the game's moves from the empty board (the reference's hashes are clock-seeded
+// per process, so they could not be passed in anyway).  Points the reference prohibits as pass-alive regions (Benson,
+// only computed after three passes, board.cc:587-590) are supplied by the caller as a grid, as for p3_legal_mask.
+//
+// The reader itself is the reference's recursion turned into an explicit stack of frames in global memory (one stack per
+// resident warp, 301 frames = the reference's call_depth <= 300): an attacker node is an OR over the two liberties, a
+// defender node an AND over "extend at the liberty" and "capture an adjacent group in atari"; an illegal move loses for
+// its mover; results do not depend on the order children are tried (no depth-capped branch is reachable on 19 x 19), so
+// duplicate candidate points are tried once.  Searches (one per group in atari that passes the reference's quick reject,
+// board.cc:857-860) are handed to persistent warps through an atomic counter, since their lengths vary wildly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace p3 {
+namespace {
+
+constexpr uint32_t kRowFull = 0x7FFFFu;   // 19 columns
+constexpr int kMaxDepth = 301;            // frames 0..300 (Solve returns false beyond call_depth 300, board.cc:778-780)
+constexpr int kMaxCand = 40;              // candidate moves of one node (1 + adjacent groups in atari)
+constexpr int kWhiteBit = 512;            // move encoding: point (0..360) or 361 = pass, + 512 for WHITE
+constexpr unsigned kAll = 0xFFFFFFFFu;
+
+struct Board {
+  uint32_t bk, wh;  // this lane's row
+};
+
+__device__ __forceinline__ uint64_t zobrist(int point, int is_white) {  // splitmix64 of (point, colour)
+  uint64_t x = (static_cast<uint64_t>(point) * 2 + is_white + 1) * 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint32_t row_mask(int lane) { return lane < P3_BOARD_LEN ? kRowFull : 0u; }
+
+__device__ __forceinline__ uint32_t nbrs(uint32_t x, int lane) {
+  uint32_t up = __shfl_up_sync(kAll, x, 1);      // row above (lane - 1)
+  uint32_t dn = __shfl_down_sync(kAll, x, 1);    // row below (lane + 1); lanes >= 19 hold zeros
+  if (lane == 0) up = 0;
+  if (lane == 31) dn = 0;
+  return ((x << 1) | (x >> 1) | up | dn) & row_mask(lane);
+}
+
+// connected closure of `seed` inside `mask`
+__device__ __forceinline__ uint32_t flood(uint32_t seed, uint32_t mask, int lane) {
+  uint32_t x = seed & mask;
+  while (true) {
+    uint32_t y = x | (((x << 1) | (x >> 1)) & mask);   // two horizontal steps per vertical one: rows are cheap
+    y |= ((y << 1) | (y >> 1)) & mask;
+    y |= nbrs(y, lane) & mask;
+    const bool changed = __any_sync(kAll, y != x);
+    x = y;
+    if (!changed) break;
+  }
+  return x;
+}
+
+__device__ __forceinline__ int warp_count(uint32_t x) {
+  int c = __popc(x);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(kAll, c, o);
+  return c;
+}
+
+__device__ __forceinline__ uint64_t warp_xor64(uint64_t h) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) h ^= __shfl_xor_sync(kAll, h, o);
+  return h;
+}
+
+// first point (row-major) of a non-empty row-mask set, or -1; warp-uniform
+__device__ __forceinline__ int first_point(uint32_t x) {
+  const uint32_t b = __ballot_sync(kAll, x != 0);
+  if (!b) return -1;
+  const int src = __ffs(b) - 1;
+  const uint32_t row = __shfl_sync(kAll, x, src);
+  return src * P3_BOARD_LEN + (__ffs(row) - 1);
+}
+
+__device__ __forceinline__ uint32_t point_bit(int point, int lane) {
+  return lane == point / P3_BOARD_LEN ? 1u << (point % P3_BOARD_LEN) : 0u;
+}
+
+__device__ __forceinline__ uint64_t hash_of(uint32_t rows, int is_white, int lane) {
+  uint64_t h = 0;
+  while (rows) {
+    const int c = __ffs(rows) - 1;
+    rows &= rows - 1;
+    h ^= zobrist(lane * P3_BOARD_LEN + c, is_white);
+  }
+  return warp_xor64(h);
+}
+
+struct SeenSet {
+  const uint64_t* hist;  // hashes of the game's positions up to and including the current one
+  int n_hist;
+  const uint64_t* path;  // hashes of the search path's positions
+  int n_path;
+};
+
+__device__ __forceinline__ bool seen_contains(const SeenSet& s, uint64_t h, int lane) {
+  bool hit = false;
+  for (int i = lane; i < s.n_hist; i += 32) hit |= s.hist[i] == h;
+  for (int i = lane; i < s.n_path; i += 32) hit |= s.path[i] == h;
+  return __any_sync(kAll, hit);
+}
+
+// Board::PlayMove (board.cc:536-580) for a board point.  `check` = false replays a recorded (legal) move: captures only.
+// Returns false (board untouched) when the reference's PlayMoveDry would not return kValid.
+__device__ __forceinline__ bool play(Board& b, uint64_t& hash, int point, int color, bool check, uint32_t forbidden_row,
+                                     const SeenSet& seen, int lane) {
+  const uint32_t bit = point_bit(point, lane);
+  if (check && __any_sync(kAll, (bit & (b.bk | b.wh | forbidden_row)) != 0)) return false;  // kLocNotEmpty / kPassAliveRegion
+  const bool black = color == P3_BLACK;
+  uint32_t own = (black ? b.bk : b.wh) | bit;
+  uint32_t opp = black ? b.wh : b.bk;
+  uint32_t empty = ~(own | opp) & row_mask(lane);
+  uint32_t captured = 0;
+  const uint32_t seeds = nbrs(bit, lane) & opp;
+  if (__any_sync(kAll, seeds != 0)) {
+    const uint32_t touched = flood(seeds, opp, lane);                      // the adjacent opposing groups
+    const uint32_t alive = flood(nbrs(empty, lane) & touched, touched, lane);  // ... that still reach an empty point
+    captured = touched & ~alive;
+  }
+  const bool any_capture = __any_sync(kAll, captured != 0);
+  if (any_capture) {
+    opp &= ~captured;
+  } else if (check) {  // IsSelfCapture, board.cc:901-915
+    const uint32_t group = flood(bit, own, lane);
+    if (!__any_sync(kAll, (nbrs(group, lane) & empty) != 0)) return false;
+  }
+  uint64_t h = hash ^ zobrist(point, black ? 0 : 1);
+  if (any_capture) h ^= hash_of(captured, black ? 1 : 0, lane);
+  if (check && seen_contains(seen, h, lane)) return false;                 // kRepeatedPosition, board.cc:636-640
+  b.bk = black ? own : opp;
+  b.wh = black ? opp : own;
+  hash = h;
+  return true;
+}
+
+// ---- kernel 1: replay, atari groups, quick reject -> search tasks ------------------------------------------------------
+struct LadderTask {
+  int pos, root, liberty;
+};
+
+__global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__ moves, const int32_t* __restrict__ num_moves,
+                                                     int max_moves, const int8_t* __restrict__ forbidden, int n,
+                                                     uint32_t* __restrict__ rows,        // [n][3][32] black, white, forbidden
+                                                     uint64_t* __restrict__ hist,        // [n][max_moves + 1]
+                                                     int32_t* __restrict__ n_hist, int8_t* __restrict__ boards,
+                                                     int8_t* __restrict__ laddered, int32_t* __restrict__ status,
+                                                     LadderTask* __restrict__ tasks, int* __restrict__ n_tasks) {
+  const int lane = threadIdx.x & 31;
+  const int pos = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pos >= n) return;
+  Board b{0, 0};
+  uint64_t hash = 0;
+  uint64_t* my_hist = hist + static_cast<size_t>(pos) * (max_moves + 1);
+  int nh = 0;
+  if (lane == 0) my_hist[0] = 0;  // the empty board (Board::Board inserts its hash, board.cc:505-513)
+  nh = 1;
+  int st = 0;
+  const int nm = min(max(num_moves[pos], 0), max_moves);
+  const int16_t* mv = moves + static_cast<size_t>(pos) * max_moves;
+  const SeenSet none{nullptr, 0, nullptr, 0};
+  for (int m = 0; m < nm; ++m) {
+    const int code = mv[m];
+    const int point = code & (kWhiteBit - 1);
+    if (code < 0 || point >= P3_PASS_ENCODING) continue;  // pass (or padding): Board::Pass leaves seen_states_ alone
+    const int color = (code & kWhiteBit) ? P3_WHITE : P3_BLACK;
+    if (__any_sync(kAll, (point_bit(point, lane) & (b.bk | b.wh)) != 0)) {
+      st = 1;  // not a legal game record
+      break;
+    }
+    play(b, hash, point, color, false, 0, none, lane);
+    if (lane == 0) my_hist[nh] = hash;
+    ++nh;
+  }
+  // forbidden grid -> row masks
+  uint32_t fb = 0;
+  if (forbidden && lane < P3_BOARD_LEN) {
+    const int8_t* f = forbidden + static_cast<size_t>(pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
+    for (int c = 0; c < P3_BOARD_LEN; ++c) fb |= f[c] ? 1u << c : 0u;
+  }
+  uint32_t* r = rows + static_cast<size_t>(pos) * 96;
+  r[lane] = b.bk;
+  r[32 + lane] = b.wh;
+  r[64 + lane] = fb;
+  if (lane == 0) {
+    n_hist[pos] = nh;
+    status[pos] = st;
+  }
+  if (lane < P3_BOARD_LEN) {
+    const size_t at = static_cast<size_t>(pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
+    for (int c = 0; c < P3_BOARD_LEN; ++c) {
+      if (boards) boards[at + c] = (b.bk >> c) & 1 ? P3_BLACK : ((b.wh >> c) & 1 ? P3_WHITE : P3_EMPTY);
+      if (laddered) laddered[at + c] = 0;
+    }
+  }
+  if (!tasks) return;
+  // groups in atari (board.cc:874-882) that survive the quick reject (board.cc:857-860)
+  const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
+  // only groups next to an empty point with at most 2 empty neighbours can be laddered candidates; enumerate the
+  // groups touching any empty point's neighbourhood instead of all groups: every group has a liberty, so that is all of
+  // them - but visit each once
+  uint32_t todo = b.bk | b.wh;
+  while (true) {
+    const int s = first_point(todo);
+    if (s < 0) break;
+    const uint32_t sbit = point_bit(s, lane);
+    const bool is_black = __any_sync(kAll, (sbit & b.bk) != 0);
+    const uint32_t group = flood(sbit, is_black ? b.bk : b.wh, lane);
+    todo &= ~group;
+    const uint32_t libs = nbrs(group, lane) & empty;
+    if (warp_count(libs) != 1) continue;
+    const int liberty = first_point(libs);
+    if (warp_count(nbrs(point_bit(liberty, lane), lane) & empty) >= 3) continue;  // GroupTracker::LibertiesAt(liberty) >= 3
+    if (lane == 0) {
+      const int t = atomicAdd(n_tasks, 1);
+      tasks[t] = LadderTask{pos, s, liberty};
+    }
+  }
+}
+
+// ---- kernel 2: the reader ---------------------------------------------------------------------------------------------
+struct Frame {           // one Solve() activation whose children are being tried
+  uint64_t hash;         // of the position after this node's move (also this node's entry in the path's seen set)
+  int16_t cand[kMaxCand];
+  int16_t n_cand, next;
+  int16_t is_and;        // defender to move: AND over the candidates; attacker to move: OR
+  int16_t pad;
+};
+
+struct Scratch {         // per resident warp
+  uint32_t rows[kMaxDepth][2][32];
+  uint64_t path[kMaxDepth];
+  Frame frames[kMaxDepth];
+};
+
+__global__ void __launch_bounds__(128) ladder_kernel(const LadderTask* __restrict__ tasks, const int* __restrict__ n_tasks,
+                                                     int* __restrict__ next_task, const uint32_t* __restrict__ rows,
+                                                     const uint64_t* __restrict__ hist, const int32_t* __restrict__ n_hist,
+                                                     int max_moves, Scratch* __restrict__ scratch,
+                                                     int8_t* __restrict__ laddered, int32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  Scratch& S = scratch[warp];
+  const int total = *n_tasks;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(next_task, 1);
+    t = __shfl_sync(kAll, t, 0);
+    if (t >= total) break;
+    const LadderTask task = tasks[t];
+    const uint32_t* r = rows + static_cast<size_t>(task.pos) * 96;
+    const Board root_board{r[lane], r[32 + lane]};
+    const uint32_t fb = r[64 + lane];
+    const uint64_t* my_hist = hist + static_cast<size_t>(task.pos) * (max_moves + 1);
+    const int nh = n_hist[task.pos];
+    const uint32_t rootbit = point_bit(task.root, lane);
+    const int g_color = __any_sync(kAll, (rootbit & root_board.bk) != 0) ? P3_BLACK : P3_WHITE;
+
+    // Solve(board_copy, gid, g_color, OppositeColor(g_color), root, liberty, 0): the defender extends first (board.cc:863-866)
+    Board b = root_board;
+    uint64_t hash = my_hist[nh - 1];
+    int top = -1;            // index of the frame whose children are being tried; the call being entered has call_depth top + 1
+    int move = task.liberty;
+    int mover = g_color;
+    bool value = false;
+    bool overflow = false;
+    while (true) {
+      // ---- enter Solve(move by `mover`) from the position in (b, hash)
+      bool returned;
+      const int depth = top + 1;
+      if (depth > 300) {
+        value = false;
+        returned = true;
+      } else {
+        const SeenSet seen{my_hist, nh, S.path, depth};
+        if (!play(b, hash, move, mover, true, fb, seen, lane)) {
+          value = mover == g_color;  // board.cc:782-786: an illegal move loses for its mover
+          returned = true;
+        } else {
+          const int to_move = -mover;
+          const uint32_t own = g_color == P3_BLACK ? b.bk : b.wh;
+          const uint32_t opp = g_color == P3_BLACK ? b.wh : b.bk;
+          const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
+          const uint32_t group = flood(rootbit, own, lane);   // the group of group_root (board.cc:788-792)
+          uint32_t libs = nbrs(group, lane) & empty;
+          const int n_libs = warp_count(libs);
+          returned = true;
+          if (to_move != g_color) {          // attacker to move (board.cc:800-812)
+            if (n_libs > 2) value = false;
+            else if (n_libs <= 1) value = true;
+            else returned = false;
+          } else {                           // defender to move (board.cc:813-839)
+            if (n_libs > 1) value = false;
+            else if (n_libs == 0) value = true;  // unreachable after a legal attacker move (the reference CHECK-fails)
+            else returned = false;
+          }
+          if (!returned) {
+            Frame& f = S.frames[depth];
+            int nc = 0;
+            while (true) {                   // the group's liberties: two (attacker) or one (defender)
+              const int p = first_point(libs);
+              if (p < 0) break;
+              libs &= ~point_bit(p, lane);
+              if (lane == 0) f.cand[nc] = static_cast<int16_t>(p);
+              ++nc;
+            }
+            if (to_move == g_color) {        // FindSurroundingStonesInAtari + FindLiberty (board.cc:744-770, 827-835)
+              const int own_liberty = __shfl_sync(kAll, lane == 0 ? static_cast<int>(f.cand[0]) : 0, 0);
+              uint32_t around = nbrs(group, lane) & opp;
+              uint32_t tried = point_bit(own_liberty, lane);
+              while (true) {
+                const int s = first_point(around);
+                if (s < 0) break;
+                const uint32_t g2 = flood(point_bit(s, lane), opp, lane);
+                around &= ~g2;
+                uint32_t l2 = nbrs(g2, lane) & empty;
+                if (warp_count(l2) != 1) continue;
+                if (__any_sync(kAll, (l2 & tried) != 0)) continue;  // same point, same position: same answer
+                tried |= l2;
+                if (nc >= kMaxCand) {
+                  overflow = true;
+                  break;
+                }
+                const int p = first_point(l2);
+                if (lane == 0) f.cand[nc] = static_cast<int16_t>(p);
+                ++nc;
+              }
+            }
+            if (lane == 0) {
+              f.hash = hash;
+              f.n_cand = static_cast<int16_t>(nc);
+              f.next = 0;
+              f.is_and = to_move == g_color ? 1 : 0;
+              S.path[depth] = hash;
+            }
+            S.rows[depth][0][lane] = b.bk;
+            S.rows[depth][1][lane] = b.wh;
+            __syncwarp();
+            top = depth;
+            mover = to_move;
+            move = __shfl_sync(kAll, lane == 0 ? static_cast<int>(f.cand[0]) : 0, 0);
+            continue;  // enter the first child from this position
+          }
+        }
+      }
+      // ---- a call returned `value`: unwind
+      bool done = false;
+      while (true) {
+        if (top < 0) {
+          done = true;
+          break;
+        }
+        Frame& f = S.frames[top];
+        int is_and = 0, n_cand = 0, next = 0;
+        if (lane == 0) {
+          is_and = f.is_and;
+          n_cand = f.n_cand;
+          next = f.next + 1;
+        }
+        is_and = __shfl_sync(kAll, is_and, 0);
+        n_cand = __shfl_sync(kAll, n_cand, 0);
+        next = __shfl_sync(kAll, next, 0);
+        const bool decided = is_and ? !value : value;    // AND stops at the first false, OR at the first true
+        if (decided || next >= n_cand) {                  // exhausted: AND -> true (all true), OR -> false (all false) == value
+          --top;
+          continue;
+        }
+        // next child from this frame's position
+        int mv2 = 0;
+        if (lane == 0) {
+          f.next = static_cast<int16_t>(next);
+          mv2 = f.cand[next];
+        }
+        move = __shfl_sync(kAll, mv2, 0);
+        b.bk = S.rows[top][0][lane];
+        b.wh = S.rows[top][1][lane];
+        hash = S.path[top];
+        mover = is_and ? g_color : -g_color;
+        break;
+      }
+      if (done) break;
+    }
+    if (overflow && lane == 0) atomicOr(&status[task.pos], 2);
+    if (value) {
+      const uint32_t group = flood(rootbit, g_color == P3_BLACK ? root_board.bk : root_board.wh, lane);
+      if (lane < P3_BOARD_LEN) {
+        int8_t* l = laddered + static_cast<size_t>(task.pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
+        for (int c = 0; c < P3_BOARD_LEN; ++c)
+          if ((group >> c) & 1) l[c] = static_cast<int8_t>(g_color);
+      }
+    }
+  }
+}
+
+// ---- kernel 3: exact legal mask (Game::IsValidMove over all 362 encodings, cc/game/game.cc:45-51) ----------------------
+constexpr int kLegalSplit = 8;  // warps per position
+
+__global__ void __launch_bounds__(256) legal_exact_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ hist,
+                                                          const int32_t* __restrict__ n_hist, int max_moves,
+                                                          const int8_t* __restrict__ colors, int n, uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int pos = blockIdx.x;
+  const uint32_t* r = rows + static_cast<size_t>(pos) * 96;
+  const Board root{r[lane], r[32 + lane]};
+  const uint32_t fb = r[64 + lane];
+  const uint64_t* my_hist = hist + static_cast<size_t>(pos) * (max_moves + 1);
+  const int nh = n_hist[pos];
+  const SeenSet seen{my_hist, nh, nullptr, 0};
+  const uint64_t root_hash = my_hist[nh - 1];
+  const int color = colors[pos];
+  uint8_t* o = out + static_cast<size_t>(pos) * P3_MAX_MOVES;
+  for (int p = part; p < P3_NUM_BOARD_LOCS; p += kLegalSplit) {
+    Board b = root;
+    uint64_t h = root_hash;
+    const bool ok = play(b, h, p, color, true, fb, seen, lane);
+    if (lane == 0) o[p] = ok ? 1 : 0;
+  }
+  if (threadIdx.x == 0) o[P3_NUM_BOARD_LOCS] = 1;  // pass (board.cc:516-518)
+}
+
+}  // namespace
+
+// Host entry: all buffers are device pointers except where noted; scratch is allocated per call.
+int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
+               int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream) {
+  if (n <= 0) return P3_OK;
+  uint32_t* rows = nullptr;
+  uint64_t* hist = nullptr;
+  int32_t* n_hist = nullptr;
+  LadderTask* tasks = nullptr;
+  int* counters = nullptr;
+  Scratch* scratch = nullptr;
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int warps_per_block = 4;
+  const int blocks = sms * 4;                      // 16 resident warps per SM, each with its own frame stack
+  const int n_warps = blocks * warps_per_block;
+  int rc = P3_OK;
+  auto cleanup = [&]() {
+    cudaFree(rows), cudaFree(hist), cudaFree(n_hist), cudaFree(tasks), cudaFree(counters), cudaFree(scratch);
+  };
+#define P3_TRY(call)                                                                                     \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      cleanup();                                                                                         \
+      return fail(P3_ERR_CUDA, std::string(#call) + " -> " + cudaGetErrorString(_e) + " (ladder.cu)");   \
+    }                                                                                                    \
+  } while (0)
+  P3_TRY(cudaMalloc(&rows, static_cast<size_t>(n) * 96 * sizeof(uint32_t)));
+  P3_TRY(cudaMalloc(&hist, static_cast<size_t>(n) * (max_moves + 1) * sizeof(uint64_t)));
+  P3_TRY(cudaMalloc(&n_hist, static_cast<size_t>(n) * sizeof(int32_t)));
+  P3_TRY(cudaMalloc(&tasks, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS / 2 * sizeof(LadderTask)));
+  P3_TRY(cudaMalloc(&counters, 2 * sizeof(int)));
+  P3_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
+  const bool want_ladder = d_laddered != nullptr;
+  replay_kernel<<<(n + 3) / 4, 128, 0, stream>>>(d_moves, d_num_moves, max_moves, d_forbidden, n, rows, hist, n_hist, d_boards,
+                                                 d_laddered, d_status, want_ladder ? tasks : nullptr, counters);
+  P3_TRY(cudaGetLastError());
+  if (want_ladder) {
+    P3_TRY(cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(Scratch)));
+    ladder_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(tasks, counters, counters + 1, rows, hist, n_hist, max_moves, scratch,
+                                                               d_laddered, d_status);
+    P3_TRY(cudaGetLastError());
+  }
+  if (d_legal && d_colors) {
+    legal_exact_kernel<<<n, kLegalSplit * 32, 0, stream>>>(rows, hist, n_hist, max_moves, d_colors, n, d_legal);
+    P3_TRY(cudaGetLastError());
+  }
+  P3_TRY(cudaStreamSynchronize(stream));
+#undef P3_TRY
+  cleanup();
+  return rc;
+}
+
+}  // namespace p3

@@ -232,6 +232,28 @@ def legal_mask(boards: np.ndarray, colors: np.ndarray, forbidden: Optional[np.nd
     return out
 
 
+MOVE_WHITE = 512
+
+
+def game_derive(moves: np.ndarray, num_moves: np.ndarray, colors: Optional[np.ndarray] = None, forbidden: Optional[np.ndarray] = None,
+                want_ladder: bool = True, device: int = 0):
+    """Replay move lists on the GPU -> (boards [n,361] i8, laddered [n,361] i8 | None, legal [n,362] u8 | None, status [n] i32).
+    Board::GetLadderedStones (cc/game/board.cc:692-899) and Game::IsValidMove incl. superko (board.cc:595-644)."""
+    moves = np.ascontiguousarray(moves, dtype=np.int16)
+    n, max_moves = moves.shape
+    num_moves = np.ascontiguousarray(num_moves, dtype=np.int32)
+    boards = np.zeros((n, NUM_LOCS), dtype=np.int8)
+    laddered = np.zeros((n, NUM_LOCS), dtype=np.int8) if want_ladder else None
+    legal = np.zeros((n, 362), dtype=np.uint8) if colors is not None else None
+    status = np.zeros(n, dtype=np.int32)
+    cols = np.ascontiguousarray(colors, dtype=np.int8) if colors is not None else None
+    fb = np.ascontiguousarray(forbidden, dtype=np.int8) if forbidden is not None else None
+    check(lib.p3_game_derive(device, ptr(moves), ptr(num_moves), max_moves, ptr(fb) if fb is not None else None,
+                             ptr(cols) if cols is not None else None, n, ptr(boards), ptr(laddered) if want_ladder else None,
+                             ptr(legal) if legal is not None else None, ptr(status)))
+    return boards, laddered, legal, status
+
+
 def gumbel_topk(logits: np.ndarray, legal: np.ndarray, prng_state: np.ndarray, noise_scaling: float, k: int,
                 device: int = 0):
     """cc/mcts/gumbel.cc:283-321 for n roots; ``prng_state`` (uint64[n]) is updated in place."""
