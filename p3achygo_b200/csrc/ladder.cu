@@ -26,6 +26,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace p3 {
@@ -72,17 +76,12 @@ __device__ __forceinline__ uint32_t flood(uint32_t seed, uint32_t mask, int lane
   return x;
 }
 
-__device__ __forceinline__ int warp_count(uint32_t x) {
-  int c = __popc(x);
-#pragma unroll
-  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(kAll, c, o);
-  return c;
-}
+__device__ __forceinline__ int warp_count(uint32_t x) { return static_cast<int>(__reduce_add_sync(kAll, static_cast<unsigned>(__popc(x)))); }
 
 __device__ __forceinline__ uint64_t warp_xor64(uint64_t h) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) h ^= __shfl_xor_sync(kAll, h, o);
-  return h;
+  const uint32_t lo = __reduce_xor_sync(kAll, static_cast<uint32_t>(h));
+  const uint32_t hi = __reduce_xor_sync(kAll, static_cast<uint32_t>(h >> 32));
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
 // first point (row-major) of a non-empty row-mask set, or -1; warp-uniform
@@ -240,28 +239,82 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
 }
 
 // ---- kernel 2: the reader ---------------------------------------------------------------------------------------------
-struct Frame {           // one Solve() activation whose children are being tried
-  uint64_t hash;         // of the position after this node's move (also this node's entry in the path's seen set)
-  int16_t cand[kMaxCand];
-  int16_t n_cand, next;
-  int16_t is_and;        // defender to move: AND over the candidates; attacker to move: OR
-  int16_t pad;
+// Per resident warp, in shared memory: the game's position hashes (superko look-ups), the hashes on the search path, and
+// the first kSmemFrames frames of the explicit stack; deeper frames live in a global scratch area.  A frame is three
+// 32-word rows: [0] black rows in lanes 0..18, candidate moves packed two per word in lanes 19..31; [1] white rows, lane
+// 31 = n_cand | next << 8; [2] the rows of the hunted group at this node (it only grows along a path, so the flood
+// after a move starts from it and converges in a step or two).  A node's kind needs no storage: the defender moves at
+// even call depths, so frame d is an AND node iff d is odd.
+constexpr int kSmemFrames = 40;
+constexpr int kHistSmem = 608;
+constexpr int kReaderWarps = 4;
+constexpr int kFrameWords = 96;
+constexpr int kMaxCandPacked = 26;
+constexpr size_t kWarpSmemBytes = kHistSmem * 8 + kMaxDepth * 8 + kSmemFrames * kFrameWords * 4;
+static_assert(kMaxCandPacked <= kMaxCand, "candidate capacity");
+
+struct DeepFrames {  // per resident warp: frames kSmemFrames .. kMaxDepth-1
+  uint32_t w[kMaxDepth - kSmemFrames][kFrameWords];
 };
 
-struct Scratch {         // per resident warp
-  uint32_t rows[kMaxDepth][2][32];
-  uint64_t path[kMaxDepth];
-  Frame frames[kMaxDepth];
-};
+// like play() for the searched moves, with the cheap exits that make most nodes flood-free: a neighbouring opposing stone
+// with an empty neighbour of its own cannot be captured, and a stone with an empty neighbour (or next to a friendly stone
+// that has one) is not self-capture.
+__device__ __forceinline__ bool play_checked(Board& b, uint64_t& hash, int point, int color, uint32_t forbidden_row,
+                                             const uint64_t* hist_s, int n_hist_s, const uint64_t* hist_g, int n_hist,
+                                             const uint64_t* path_s, int n_path, int lane) {
+  const uint32_t bit = point_bit(point, lane);
+  if (__any_sync(kAll, (bit & (b.bk | b.wh | forbidden_row)) != 0)) return false;  // kLocNotEmpty / kPassAliveRegion
+  const bool black = color == P3_BLACK;
+  const uint32_t own_prev = black ? b.bk : b.wh;
+  const uint32_t own = own_prev | bit;
+  uint32_t opp = black ? b.wh : b.bk;
+  const uint32_t empty = ~(own | opp) & row_mask(lane);
+  const uint32_t near_empty = nbrs(empty, lane);     // points with an empty neighbour
+  const uint32_t around = nbrs(bit, lane);
+  uint32_t captured = 0;
+  bool any_capture = false;
+  const uint32_t seeds = around & opp & ~near_empty;  // adjacent opposing stones without a liberty of their own
+  if (__any_sync(kAll, seeds != 0)) {
+    const uint32_t touched = flood(seeds, opp, lane);
+    const uint32_t alive = flood(near_empty & touched, touched, lane);
+    captured = touched & ~alive;
+    any_capture = __any_sync(kAll, captured != 0);
+  }
+  if (any_capture) {
+    opp &= ~captured;
+  } else if (!__any_sync(kAll, ((around & empty) | (around & own_prev & near_empty)) != 0)) {  // IsSelfCapture, board.cc:901-915
+    const uint32_t group = flood(bit, own, lane);
+    if (!__any_sync(kAll, (nbrs(group, lane) & empty) != 0)) return false;
+  }
+  uint64_t h = hash ^ zobrist(point, black ? 0 : 1);
+  if (any_capture) h ^= hash_of(captured, black ? 1 : 0, lane);
+  bool hit = false;                                   // kRepeatedPosition, board.cc:636-640
+  for (int i = lane; i < n_hist_s; i += 32) hit |= hist_s[i] == h;
+  for (int i = n_hist_s + lane; i < n_hist; i += 32) hit |= hist_g[i] == h;
+  for (int i = lane; i < n_path; i += 32) hit |= path_s[i] == h;
+  if (__any_sync(kAll, hit)) return false;
+  b.bk = black ? own : opp;
+  b.wh = black ? opp : own;
+  hash = h;
+  return true;
+}
 
-__global__ void __launch_bounds__(128) ladder_kernel(const LadderTask* __restrict__ tasks, const int* __restrict__ n_tasks,
-                                                     int* __restrict__ next_task, const uint32_t* __restrict__ rows,
-                                                     const uint64_t* __restrict__ hist, const int32_t* __restrict__ n_hist,
-                                                     int max_moves, Scratch* __restrict__ scratch,
-                                                     int8_t* __restrict__ laddered, int32_t* __restrict__ status) {
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  Scratch& S = scratch[warp];
+__global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderTask* __restrict__ tasks, const int* __restrict__ n_tasks,
+                                                                   int* __restrict__ next_task, const uint32_t* __restrict__ rows,
+                                                                   const uint64_t* __restrict__ hist, const int32_t* __restrict__ n_hist,
+                                                                   int max_moves, DeepFrames* __restrict__ deep,
+                                                                   int8_t* __restrict__ laddered, int32_t* __restrict__ status,
+                                                                   long long* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * kReaderWarps + wib;
+  unsigned char* base = smem_raw + wib * kWarpSmemBytes;
+  uint64_t* hist_s = reinterpret_cast<uint64_t*>(base);
+  uint64_t* path_s = hist_s + kHistSmem;
+  uint32_t* frames_s = reinterpret_cast<uint32_t*>(path_s + kMaxDepth);
+  DeepFrames& D = deep[warp];
+  auto frame = [&](int d) -> uint32_t* { return d < kSmemFrames ? frames_s + d * kFrameWords : D.w[d - kSmemFrames]; };
   const int total = *n_tasks;
   while (true) {
     int t = 0;
@@ -274,94 +327,106 @@ __global__ void __launch_bounds__(128) ladder_kernel(const LadderTask* __restric
     const uint32_t fb = r[64 + lane];
     const uint64_t* my_hist = hist + static_cast<size_t>(task.pos) * (max_moves + 1);
     const int nh = n_hist[task.pos];
+    const int nh_s = min(nh, kHistSmem);
+    __syncwarp();
+    for (int i = lane; i < nh_s; i += 32) hist_s[i] = my_hist[i];
+    __syncwarp();
     const uint32_t rootbit = point_bit(task.root, lane);
     const int g_color = __any_sync(kAll, (rootbit & root_board.bk) != 0) ? P3_BLACK : P3_WHITE;
+    const uint32_t root_group = flood(rootbit, g_color == P3_BLACK ? root_board.bk : root_board.wh, lane);
 
     // Solve(board_copy, gid, g_color, OppositeColor(g_color), root, liberty, 0): the defender extends first (board.cc:863-866)
     Board b = root_board;
+    uint32_t grp = root_group;
     uint64_t hash = my_hist[nh - 1];
     int top = -1;            // index of the frame whose children are being tried; the call being entered has call_depth top + 1
     int move = task.liberty;
     int mover = g_color;
     bool value = false;
     bool overflow = false;
+    long long nodes = 0;
+    const long long c0 = stats ? clock64() : 0;
     while (true) {
+      ++nodes;
       // ---- enter Solve(move by `mover`) from the position in (b, hash)
-      bool returned;
+      bool returned = true;
       const int depth = top + 1;
       if (depth > 300) {
         value = false;
-        returned = true;
+      } else if (!play_checked(b, hash, move, mover, fb, hist_s, nh_s, my_hist, nh, path_s, depth, lane)) {
+        value = mover == g_color;  // board.cc:782-786: an illegal move loses for its mover
       } else {
-        const SeenSet seen{my_hist, nh, S.path, depth};
-        if (!play(b, hash, move, mover, true, fb, seen, lane)) {
-          value = mover == g_color;  // board.cc:782-786: an illegal move loses for its mover
-          returned = true;
-        } else {
-          const int to_move = -mover;
-          const uint32_t own = g_color == P3_BLACK ? b.bk : b.wh;
-          const uint32_t opp = g_color == P3_BLACK ? b.wh : b.bk;
-          const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
-          const uint32_t group = flood(rootbit, own, lane);   // the group of group_root (board.cc:788-792)
-          uint32_t libs = nbrs(group, lane) & empty;
-          const int n_libs = warp_count(libs);
-          returned = true;
-          if (to_move != g_color) {          // attacker to move (board.cc:800-812)
-            if (n_libs > 2) value = false;
-            else if (n_libs <= 1) value = true;
-            else returned = false;
-          } else {                           // defender to move (board.cc:813-839)
-            if (n_libs > 1) value = false;
-            else if (n_libs == 0) value = true;  // unreachable after a legal attacker move (the reference CHECK-fails)
-            else returned = false;
+        const int to_move = -mover;
+        const uint32_t own = g_color == P3_BLACK ? b.bk : b.wh;
+        const uint32_t opp = g_color == P3_BLACK ? b.wh : b.bk;
+        const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
+        if (mover == g_color) {  // the group of group_root after the defender's stone (board.cc:788-792)
+          const uint32_t mbit = point_bit(move, lane);
+          if (__any_sync(kAll, (nbrs(mbit, lane) & grp) != 0)) {        // the stone joins the group ...
+            grp |= mbit;
+            if (__any_sync(kAll, (nbrs(mbit, lane) & own & ~grp) != 0)) grp = flood(grp, own, lane);  // ... and brings others along
           }
-          if (!returned) {
-            Frame& f = S.frames[depth];
-            int nc = 0;
-            while (true) {                   // the group's liberties: two (attacker) or one (defender)
-              const int p = first_point(libs);
-              if (p < 0) break;
-              libs &= ~point_bit(p, lane);
-              if (lane == 0) f.cand[nc] = static_cast<int16_t>(p);
+        }
+        uint32_t libs = nbrs(grp, lane) & empty;
+        const int n_libs = warp_count(libs);
+        if (to_move != g_color) {          // attacker to move (board.cc:800-812)
+          if (n_libs > 2) value = false;
+          else if (n_libs <= 1) value = true;
+          else returned = false;
+        } else {                           // defender to move (board.cc:813-839)
+          if (n_libs > 1) value = false;
+          else if (n_libs == 0) value = true;  // unreachable after a legal attacker move (the reference CHECK-fails)
+          else returned = false;
+        }
+        if (!returned) {
+          int nc = 0;
+          uint32_t cand_reg = 0;           // lanes 19..31: two packed candidate points each
+          int first = -1;
+          while (true) {                   // the group's liberties: two (attacker) or one (defender)
+            const int p = first_point(libs);
+            if (p < 0) break;
+            libs &= ~point_bit(p, lane);
+            if (nc == 0) first = p;
+            if (lane == 19 + (nc >> 1)) cand_reg |= static_cast<uint32_t>(p) << ((nc & 1) * 16);
+            ++nc;
+          }
+          if (to_move == g_color) {        // FindSurroundingStonesInAtari + FindLiberty (board.cc:744-770, 827-835)
+            // a stone with two empty neighbours of its own is not in atari: skip the flood for it
+            uint32_t eu = __shfl_up_sync(kAll, empty, 1), ed = __shfl_down_sync(kAll, empty, 1);
+            if (lane == 0) eu = 0;
+            if (lane == 31) ed = 0;
+            const uint32_t el = empty << 1, er = empty >> 1;
+            const uint32_t two = (el & er) | (el & eu) | (el & ed) | (er & eu) | (er & ed) | (eu & ed);
+            uint32_t around = nbrs(grp, lane) & opp & ~two;
+            uint32_t tried = point_bit(first, lane);
+            while (true) {
+              const int s = first_point(around);
+              if (s < 0) break;
+              const uint32_t g2 = flood(point_bit(s, lane), opp, lane);
+              around &= ~g2;
+              const uint32_t l2 = nbrs(g2, lane) & empty;
+              if (warp_count(l2) != 1) continue;
+              if (__any_sync(kAll, (l2 & tried) != 0)) continue;  // same point, same position: same answer
+              tried |= l2;
+              if (nc >= kMaxCandPacked) {
+                overflow = true;
+                break;
+              }
+              const int p = first_point(l2);
+              if (lane == 19 + (nc >> 1)) cand_reg |= static_cast<uint32_t>(p) << ((nc & 1) * 16);
               ++nc;
             }
-            if (to_move == g_color) {        // FindSurroundingStonesInAtari + FindLiberty (board.cc:744-770, 827-835)
-              const int own_liberty = __shfl_sync(kAll, lane == 0 ? static_cast<int>(f.cand[0]) : 0, 0);
-              uint32_t around = nbrs(group, lane) & opp;
-              uint32_t tried = point_bit(own_liberty, lane);
-              while (true) {
-                const int s = first_point(around);
-                if (s < 0) break;
-                const uint32_t g2 = flood(point_bit(s, lane), opp, lane);
-                around &= ~g2;
-                uint32_t l2 = nbrs(g2, lane) & empty;
-                if (warp_count(l2) != 1) continue;
-                if (__any_sync(kAll, (l2 & tried) != 0)) continue;  // same point, same position: same answer
-                tried |= l2;
-                if (nc >= kMaxCand) {
-                  overflow = true;
-                  break;
-                }
-                const int p = first_point(l2);
-                if (lane == 0) f.cand[nc] = static_cast<int16_t>(p);
-                ++nc;
-              }
-            }
-            if (lane == 0) {
-              f.hash = hash;
-              f.n_cand = static_cast<int16_t>(nc);
-              f.next = 0;
-              f.is_and = to_move == g_color ? 1 : 0;
-              S.path[depth] = hash;
-            }
-            S.rows[depth][0][lane] = b.bk;
-            S.rows[depth][1][lane] = b.wh;
-            __syncwarp();
-            top = depth;
-            mover = to_move;
-            move = __shfl_sync(kAll, lane == 0 ? static_cast<int>(f.cand[0]) : 0, 0);
-            continue;  // enter the first child from this position
           }
+          uint32_t* f = frame(depth);
+          f[lane] = lane < P3_BOARD_LEN ? b.bk : cand_reg;
+          f[32 + lane] = lane == 31 ? static_cast<uint32_t>(nc) : b.wh;   // next = 0
+          f[64 + lane] = grp;
+          if (lane == 0) path_s[depth] = hash;
+          __syncwarp();
+          top = depth;
+          mover = to_move;
+          move = first;
+          continue;  // enter the first child from this position
         }
       }
       // ---- a call returned `value`: unwind
@@ -371,44 +436,38 @@ __global__ void __launch_bounds__(128) ladder_kernel(const LadderTask* __restric
           done = true;
           break;
         }
-        Frame& f = S.frames[top];
-        int is_and = 0, n_cand = 0, next = 0;
-        if (lane == 0) {
-          is_and = f.is_and;
-          n_cand = f.n_cand;
-          next = f.next + 1;
-        }
-        is_and = __shfl_sync(kAll, is_and, 0);
-        n_cand = __shfl_sync(kAll, n_cand, 0);
-        next = __shfl_sync(kAll, next, 0);
+        uint32_t* f = frame(top);
+        const uint32_t meta = f[32 + 31];
+        const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8) + 1;
+        const bool is_and = top & 1;                     // frame d was pushed after the move at call depth d; defender moves at even depths
         const bool decided = is_and ? !value : value;    // AND stops at the first false, OR at the first true
         if (decided || next >= n_cand) {                  // exhausted: AND -> true (all true), OR -> false (all false) == value
           --top;
           continue;
         }
-        // next child from this frame's position
-        int mv2 = 0;
-        if (lane == 0) {
-          f.next = static_cast<int16_t>(next);
-          mv2 = f.cand[next];
-        }
-        move = __shfl_sync(kAll, mv2, 0);
-        b.bk = S.rows[top][0][lane];
-        b.wh = S.rows[top][1][lane];
-        hash = S.path[top];
+        const uint32_t packed = f[19 + (next >> 1)];
+        move = (packed >> ((next & 1) * 16)) & 0xFFFF;
+        __syncwarp();
+        if (lane == 31) f[32 + 31] = static_cast<uint32_t>(n_cand) | (static_cast<uint32_t>(next) << 8);
+        b.bk = lane < P3_BOARD_LEN ? f[lane] : 0u;
+        b.wh = lane < P3_BOARD_LEN ? f[32 + lane] : 0u;
+        grp = f[64 + lane];
+        hash = path_s[top];
         mover = is_and ? g_color : -g_color;
+        __syncwarp();
         break;
       }
       if (done) break;
     }
+    if (stats && lane == 0) {
+      stats[2 * t] = nodes;
+      stats[2 * t + 1] = clock64() - c0;
+    }
     if (overflow && lane == 0) atomicOr(&status[task.pos], 2);
-    if (value) {
-      const uint32_t group = flood(rootbit, g_color == P3_BLACK ? root_board.bk : root_board.wh, lane);
-      if (lane < P3_BOARD_LEN) {
-        int8_t* l = laddered + static_cast<size_t>(task.pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
-        for (int c = 0; c < P3_BOARD_LEN; ++c)
-          if ((group >> c) & 1) l[c] = static_cast<int8_t>(g_color);
-      }
+    if (value && lane < P3_BOARD_LEN) {
+      int8_t* l = laddered + static_cast<size_t>(task.pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
+      for (int c = 0; c < P3_BOARD_LEN; ++c)
+        if ((root_group >> c) & 1) l[c] = static_cast<int8_t>(g_color);
     }
   }
 }
@@ -450,14 +509,15 @@ int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves
   int32_t* n_hist = nullptr;
   LadderTask* tasks = nullptr;
   int* counters = nullptr;
-  Scratch* scratch = nullptr;
+  DeepFrames* scratch = nullptr;
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int warps_per_block = 4;
-  const int blocks = sms * 4;                      // 16 resident warps per SM, each with its own frame stack
+  const int warps_per_block = kReaderWarps;
+  const int blocks = sms * 2;                      // 8 resident warps per SM, each with its own frame stack in shared memory
   const int n_warps = blocks * warps_per_block;
+  const size_t reader_smem = kReaderWarps * kWarpSmemBytes;
   int rc = P3_OK;
   auto cleanup = [&]() {
     cudaFree(rows), cudaFree(hist), cudaFree(n_hist), cudaFree(tasks), cudaFree(counters), cudaFree(scratch);
@@ -477,20 +537,56 @@ int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves
   P3_TRY(cudaMalloc(&counters, 2 * sizeof(int)));
   P3_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
   const bool want_ladder = d_laddered != nullptr;
+  const bool trace = std::getenv("P3_LADDER_TRACE") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long* d_stats = nullptr;
+  if (trace) {
+    cudaMalloc(&d_stats, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS * sizeof(long long));
+    cudaMemset(d_stats, 0, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS * sizeof(long long));
+    for (auto& e : ev) cudaEventCreate(&e);
+    if (want_ladder) cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(DeepFrames));
+    cudaEventRecord(ev[0], stream);
+  }
   replay_kernel<<<(n + 3) / 4, 128, 0, stream>>>(d_moves, d_num_moves, max_moves, d_forbidden, n, rows, hist, n_hist, d_boards,
                                                  d_laddered, d_status, want_ladder ? tasks : nullptr, counters);
   P3_TRY(cudaGetLastError());
+  if (trace) cudaEventRecord(ev[1], stream);
   if (want_ladder) {
-    P3_TRY(cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(Scratch)));
-    ladder_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(tasks, counters, counters + 1, rows, hist, n_hist, max_moves, scratch,
-                                                               d_laddered, d_status);
+    if (!scratch) P3_TRY(cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(DeepFrames)));
+    P3_TRY(cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(reader_smem)));
+    ladder_kernel<<<blocks, warps_per_block * 32, reader_smem, stream>>>(tasks, counters, counters + 1, rows, hist, n_hist, max_moves, scratch,
+                                                               d_laddered, d_status, d_stats);
     P3_TRY(cudaGetLastError());
   }
+  if (trace) cudaEventRecord(ev[2], stream);
   if (d_legal && d_colors) {
     legal_exact_kernel<<<n, kLegalSplit * 32, 0, stream>>>(rows, hist, n_hist, max_moves, d_colors, n, d_legal);
     P3_TRY(cudaGetLastError());
   }
+  if (trace) cudaEventRecord(ev[3], stream);
   P3_TRY(cudaStreamSynchronize(stream));
+  if (trace) {
+    float a = 0, b = 0, c = 0;
+    int h_counters[2] = {0, 0};
+    cudaMemcpy(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost);
+    cudaEventElapsedTime(&a, ev[0], ev[1]), cudaEventElapsedTime(&b, ev[1], ev[2]), cudaEventElapsedTime(&c, ev[2], ev[3]);
+    std::fprintf(stderr, "[p3 ladder] n %d  replay+tasks %.3f ms  reader %.3f ms (%d searches)  exact legal %.3f ms\n", n, a, b,
+                 h_counters[0], c);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (want_ladder && h_counters[0] > 0) {
+      std::vector<long long> st(2 * static_cast<size_t>(h_counters[0]));
+      cudaMemcpy(st.data(), d_stats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long tot = 0, mx = 0, cyc = 0, mxc = 0;
+      for (int i = 0; i < h_counters[0]; ++i) {
+        tot += st[2 * i], cyc += st[2 * i + 1];
+        if (st[2 * i] > mx) mx = st[2 * i];
+        if (st[2 * i + 1] > mxc) mxc = st[2 * i + 1];
+      }
+      std::fprintf(stderr, "[p3 ladder] nodes total %lld  max per search %lld  cycles per node %.0f  longest search %lld cycles\n", tot, mx,
+                   tot ? static_cast<double>(cyc) / tot : 0.0, mxc);
+    }
+    cudaFree(d_stats);
+  }
 #undef P3_TRY
   cleanup();
   return rc;
