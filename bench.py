@@ -45,6 +45,47 @@ def load_positions():
     return np.ascontiguousarray(z["feats"]).view(GO_FEATURES_DTYPE).reshape(-1)
 
 
+def game_record_leg(device: int):
+    """Rules from game records on the GPU (p3_game_derive: replay -> ladder reader -> exact legal mask), 1024 of the fixture
+    games of tests/golden/ladder_games.npz, host buffers in and out; the compiled reference timed beside it when present."""
+    from p3achygo_b200 import engine as E
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ladder_games.npz"))
+    sel = slice(17, 17 + 1024)
+    mv, nm, col, fb = z["moves"][sel], z["num_moves"][sel], z["colors"][sel], z["forbidden"][sel]
+    E.game_derive(mv, nm, colors=col, forbidden=fb, device=device)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        boards, lad, legal, status = E.game_derive(mv, nm, colors=col, forbidden=fb, device=device)
+    dt = (time.perf_counter() - t0) / reps
+    ok = bool(np.array_equal(lad, z["ladder"][sel]) and np.array_equal(legal, z["legal"][sel]) and not status.any())
+    out = {"positions": 1024, "ms_per_batch": dt * 1e3, "positions_per_s": 1024 / dt, "bit_exact_vs_reference_fixture": ok,
+           "what": "p3_game_derive: move lists -> boards, Board::GetLadderedStones, Game::IsValidMove (superko) for 1024 "
+                   "random-playout game records, wall time incl. H2D / D2H and per-call scratch allocation"}
+    try:
+        from oracle import oracle_lib
+        from oracle.oracle_lib import P
+        R = oracle_lib.ref()
+    except Exception:
+        R = None
+    if R is not None and hasattr(R, "ref_game_move_status"):
+        lad1 = np.zeros(361, dtype=np.int8)
+        mask = np.zeros(362, dtype=np.uint8)
+        tl = tm = 0.0
+        n_cpu = 128
+        for k in range(17, 17 + n_cpu):
+            g = R.ref_game_new(7.5, 1)
+            for code in z["moves"][k][: z["num_moves"][k]]:
+                pnt, c = int(code) & 511, (-1 if int(code) & 512 else 1)
+                R.ref_game_play(g, 19 if pnt == 361 else pnt // 19, 0 if pnt == 361 else pnt % 19, c)
+            t0 = time.perf_counter(); R.ref_game_laddered(g, P(lad1)); tl += time.perf_counter() - t0
+            t0 = time.perf_counter(); R.ref_game_legal_mask(g, int(z["colors"][k]), P(mask)); tm += time.perf_counter() - t0
+            R.ref_game_free(g)
+        out["reference_cpu"] = {"kind": "reference", "cores": 1, "sample": f"{n_cpu} of the same game records",
+                                "laddered_us_per_position": tl / n_cpu * 1e6, "legal_mask_us_per_position": tm / n_cpu * 1e6}
+    return out
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -268,6 +309,23 @@ def main():
     total_ms = reduce_max(float(np.sum(ms_steps)))
     value = world * B * args.steps / (total_ms * 1e-3)
 
+    # ---- the same step replayed back to back (no host staging between steps): what a saturated evaluator sustains.
+    # The board power limit, not the kernels, sets this number: NVML reports sw_power_cap and lower SM clocks here.
+    n_sus = int(os.environ.get("P3_SUSTAINED_STEPS", "150"))
+    sampler2 = ClockSampler(local)
+    for _ in range(10):
+        eng.RunDevice()
+    barrier()
+    sampler2.start()
+    sus_ms = [eng.RunDevice() for _ in range(n_sus)]
+    barrier()
+    clocks2 = sampler2.stop()
+    sus_tail = float(np.mean(sus_ms[n_sus // 2:]))
+    sus_tail = reduce_max(sus_tail)
+    sustained = {"value": world * B / (sus_tail * 1e-3), "unit": "positions/s", "ms_per_step": sus_tail, "steps": n_sus,
+                 "note": "back-to-back steps, mean of the second half; the device-resident `value` above has the host's "
+                         "staging of the next batch between steps", "clocks": clocks2}
+
     # ---- per-kernel-class device times (eager pass, an event around every launch), averaged over a few passes
     prof = {}
     n_prof = 3
@@ -356,8 +414,11 @@ def main():
                            "path": "the reference's own cycle, nothing overlapped: LoadBatch x B -> RunInference -> GetBatch x B "
                                    "(cc/nn/engine/benchmark_engine.cc:77-109 shape)"}},
         "gpu_launches": None,
+        "sustained": sustained,
         "roofline": roofline,
     }
+    if rank == 0:
+        line["game_records"] = game_record_leg(local)
     line["gpu_launches"] = int(sum(v[1] for v in prof.values())) * args.steps
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
