@@ -309,23 +309,6 @@ def main():
     total_ms = reduce_max(float(np.sum(ms_steps)))
     value = world * B * args.steps / (total_ms * 1e-3)
 
-    # ---- the same step replayed back to back (no host staging between steps): what a saturated evaluator sustains.
-    # The board power limit, not the kernels, sets this number: NVML reports sw_power_cap and lower SM clocks here.
-    n_sus = int(os.environ.get("P3_SUSTAINED_STEPS", "150"))
-    sampler2 = ClockSampler(local)
-    for _ in range(10):
-        eng.RunDevice()
-    barrier()
-    sampler2.start()
-    sus_ms = [eng.RunDevice() for _ in range(n_sus)]
-    barrier()
-    clocks2 = sampler2.stop()
-    sus_tail = float(np.mean(sus_ms[n_sus // 2:]))
-    sus_tail = reduce_max(sus_tail)
-    sustained = {"value": world * B / (sus_tail * 1e-3), "unit": "positions/s", "ms_per_step": sus_tail, "steps": n_sus,
-                 "note": "back-to-back steps, mean of the second half; the device-resident `value` above has the host's "
-                         "staging of the next batch between steps", "clocks": clocks2}
-
     # ---- per-kernel-class device times (eager pass, an event around every launch), averaged over a few passes
     prof = {}
     n_prof = 3
@@ -373,7 +356,6 @@ def main():
     host = ctypes.CDLL(os.path.join(ROOT, "p3achygo_b200", "libp3host.so"))
     host.p3_host_benchmark.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
-    eng.close()
     out = np.zeros(5, dtype=np.float64)
     threads = min(8, os.cpu_count() or 1)
     barrier()
@@ -393,6 +375,25 @@ def main():
     barrier()
     pipe_us = reduce_max(float(outp[0]))
     e2e_value = world * B / (pipe_us * 1e-6)
+
+    # ---- the same step replayed back to back (no host staging between steps): what a saturated evaluator sustains.
+    # The board power limit, not the kernels, sets this number: NVML reports sw_power_cap and lower SM clocks here.
+    n_sus = int(os.environ.get("P3_SUSTAINED_STEPS", "150"))
+    sampler2 = ClockSampler(local)
+    for _ in range(10):
+        eng.RunDevice()
+    barrier()
+    sampler2.start()
+    sus_ms = [eng.RunDevice() for _ in range(n_sus)]
+    barrier()
+    clocks2 = sampler2.stop()
+    sus_tail = float(np.mean(sus_ms[n_sus // 2:]))
+    sus_tail = reduce_max(sus_tail)
+    sustained = {"value": world * B / (sus_tail * 1e-3), "unit": "positions/s", "ms_per_step": sus_tail, "steps": n_sus,
+                 "note": "back-to-back steps, mean of the second half; the device-resident `value` above has the host's "
+                         "staging of the next batch between steps", "clocks": clocks2}
+
+    eng.close()
 
     line = {
         "metric": "leaf evals/sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,

@@ -414,6 +414,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   if ((rc = e.d_scalars.alloc(sizeof(float) * B * e.nscalars))) return rc;
   if ((rc = e.d_masks.alloc(sizeof(uint16_t) * B * 361))) return rc;
   if ((rc = e.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
+  P3_CUDA(cudaMemset(e.d_results.p, 0, e.d_results.bytes));  // struct padding travels with the D2H copies
   if ((rc = e.d_aux.alloc(sizeof(p3_aux_result) * B))) return rc;
   for (int k = 0; k < P3_NUM_BANKS; ++k) {
     p3_engine::Bank& bk = e.banks[k];
