@@ -168,6 +168,16 @@ int p3_engine_submit(p3_engine* e, int bank);
 int p3_engine_wait(p3_engine* e, int bank);
 int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result);
 
+/* NNInterface::LoadBatch from the game record itself (cc/nn/nn_interface.cc:245-277): instead of a filled GoFeatures the
+ * slot receives the game's move list (encoding of p3_game_derive below), the colour to move, komi, the optional pass-alive
+ * grid and the symmetry; the next run of that bank replays the game on the GPU and derives the board, the liberty grids
+ * (Board::GetStonesWithLiberties), the laddered stones (Board::GetLadderedStones) and the last five moves before the encode
+ * kernel runs.  Results are bit-identical to loading the GoFeatures the reference would have built.  Works with both
+ * p3_engine_run_inference (bank 0) and p3_engine_submit; slots of either kind can be mixed in one batch. */
+#define P3_MAX_GAME_MOVES 1024
+int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi,
+                             const int8_t* forbidden, int sym);
+
 /* nn::Engine::kind()/path(), cc/nn/engine/engine.h:33-34. */
 const char* p3_engine_path(const p3_engine* e);
 int p3_engine_batch_size(const p3_engine* e);

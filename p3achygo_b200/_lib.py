@@ -77,7 +77,7 @@ assert ctypes.sizeof(GoFeatures) == 1860 and GO_FEATURES_DTYPE.itemsize == 1860
 # every symbol include/p3_b200.h declares
 EXPORTS = [
     "p3_engine_create", "p3_engine_destroy", "p3_engine_load_batch", "p3_engine_load_batch_sym", "p3_engine_run_inference", "p3_engine_get_batch",
-    "p3_engine_load_batch_bank", "p3_engine_submit", "p3_engine_wait", "p3_engine_get_batch_bank",
+    "p3_engine_load_batch_bank", "p3_engine_submit", "p3_engine_wait", "p3_engine_get_batch_bank", "p3_engine_load_game_bank",
     "p3_engine_get_ownership", "p3_engine_path", "p3_engine_batch_size", "p3_engine_get_planes", "p3_engine_get_aux",
     "p3_engine_run_device", "p3_engine_upload", "p3_engine_profile", "p3_engine_stage_ms", "p3_engine_launches_per_run", "p3_engine_flops_per_position",
     "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_game_derive", "p3_gumbel_topk",
@@ -102,6 +102,7 @@ def _load() -> ctypes.CDLL:
     lib.p3_engine_run_inference.argtypes = [vp]
     lib.p3_engine_get_batch.argtypes = [vp, ci, vp]
     lib.p3_engine_load_batch_bank.argtypes = [vp, ci, ci, vp, ci]
+    lib.p3_engine_load_game_bank.argtypes = [vp, ci, ci, vp, ci, ci, cf, vp, ci]
     lib.p3_engine_submit.argtypes = [vp, ci]
     lib.p3_engine_wait.argtypes = [vp, ci]
     lib.p3_engine_get_batch_bank.argtypes = [vp, ci, ci, vp]

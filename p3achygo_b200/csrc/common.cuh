@@ -201,6 +201,16 @@ int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result
 // ladder.cu: replay of move lists -> boards, laddered stones (board.cc:692-899), exact legal masks (board.cc:595-644); device pointers
 int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
                int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream);
+struct LadderWorkspace;   // preallocated buffers of the game-record kernels for batches up to n, move lists up to max_moves
+int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out);
+void ladder_workspace_destroy(LadderWorkspace* w);
+// asynchronous form of ladder_run on a workspace; ev (optional) = 4 events recorded around the three kernels
+int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_num_moves, const int8_t* d_forbidden,
+                   const int8_t* d_colors, int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status,
+                   cudaStream_t stream, cudaEvent_t* ev);
+// derived grids + move list -> the GoFeatures records of the slots whose num_moves >= 0 (NNInterface::LoadBatch, nn_interface.cc:245-277)
+int assemble_features_launch(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_boards, const int8_t* d_libs,
+                             const int8_t* d_laddered, int n, p3_go_features* d_feats, cudaStream_t stream);
 int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
                   int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid, cudaStream_t stream);
 

@@ -180,11 +180,19 @@ struct p3_engine {
     int8_t* h_sym = nullptr;
     bool owns_host = false;
     DevBuf d_feats, d_sym, d_results;
+    // slots loaded as game records (p3_engine_load_game_bank): move lists, move counts (-1 = the slot holds GoFeatures), pass-alive grids
+    int16_t* h_moves = nullptr;
+    int32_t* h_nmoves = nullptr;
+    int8_t* h_forbidden = nullptr;
+    DevBuf d_moves, d_nmoves, d_forbidden;
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
     std::atomic<int> in_flight{0};
   };
   Bank banks[P3_NUM_BANKS];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  // rules from game records (ladder.cu), allocated at the first run that has a game-record slot
+  LadderWorkspace* ladder_ws = nullptr;
+  DevBuf g_boards, g_laddered, g_libs, g_status;
   std::mutex submit_mu;  // one bank's enqueue sequence at a time (two infer threads may submit concurrently)
 
   ~p3_engine() {
@@ -201,12 +209,16 @@ struct p3_engine {
       if (b.ev_h2d) cudaEventDestroy(b.ev_h2d);
       if (b.ev_done) cudaEventDestroy(b.ev_done);
       if (b.ev_d2h) cudaEventDestroy(b.ev_d2h);
+      if (b.h_moves) cudaFreeHost(b.h_moves);
+      if (b.h_nmoves) cudaFreeHost(b.h_nmoves);
+      if (b.h_forbidden) cudaFreeHost(b.h_forbidden);
       if (b.owns_host) {
         if (b.h_feats) cudaFreeHost(b.h_feats);
         if (b.h_results) cudaFreeHost(b.h_results);
         if (b.h_sym) cudaFreeHost(b.h_sym);
       }
     }
+    if (ladder_ws) ladder_workspace_destroy(ladder_ws);
     if (h2d_stream) cudaStreamDestroy(h2d_stream);
     if (d2h_stream) cudaStreamDestroy(d2h_stream);
     if (stream) cudaStreamDestroy(stream);
@@ -272,6 +284,39 @@ struct p3_engine {
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
     return P3_OK;
+  }
+
+  // Slots of `bk` that were loaded as game records: move lists -> board, liberty grids, laddered stones, last moves, written
+  // into the step's GoFeatures buffer (d_feats) on `stream`; `copy_stream` carries the H2D of the lists.  No-op without such slots.
+  int enqueue_game_records(Bank& bk, cudaStream_t copy_stream, cudaEvent_t copied) {
+    bool any = false;
+    for (int b = 0; b < batch && !any; ++b) any = bk.h_nmoves[b] >= 0;
+    if (!any) return P3_OK;
+    int rc;
+    if (!ladder_ws) {
+      if ((rc = ladder_workspace_create(batch, P3_MAX_GAME_MOVES, &ladder_ws))) return rc;
+      if ((rc = g_boards.alloc(static_cast<size_t>(361) * batch)) || (rc = g_laddered.alloc(static_cast<size_t>(361) * batch)) ||
+          (rc = g_libs.alloc(static_cast<size_t>(3 * 361) * batch)) || (rc = g_status.alloc(sizeof(int32_t) * batch)))
+        return rc;
+    }
+    if (!bk.d_moves.p) {
+      if ((rc = bk.d_moves.alloc(sizeof(int16_t) * P3_MAX_GAME_MOVES * batch)) || (rc = bk.d_nmoves.alloc(sizeof(int32_t) * batch)) ||
+          (rc = bk.d_forbidden.alloc(static_cast<size_t>(361) * batch)))
+        return rc;
+    }
+    P3_CUDA(cudaMemcpyAsync(bk.d_moves.p, bk.h_moves, bk.d_moves.bytes, cudaMemcpyHostToDevice, copy_stream));
+    P3_CUDA(cudaMemcpyAsync(bk.d_nmoves.p, bk.h_nmoves, bk.d_nmoves.bytes, cudaMemcpyHostToDevice, copy_stream));
+    P3_CUDA(cudaMemcpyAsync(bk.d_forbidden.p, bk.h_forbidden, bk.d_forbidden.bytes, cudaMemcpyHostToDevice, copy_stream));
+    if (copy_stream != stream) {
+      P3_CUDA(cudaEventRecord(copied, copy_stream));
+      P3_CUDA(cudaStreamWaitEvent(stream, copied, 0));
+    }
+    rc = ladder_enqueue(ladder_ws, bk.d_moves.as<int16_t>(), bk.d_nmoves.as<int32_t>(), bk.d_forbidden.as<int8_t>(), nullptr, batch,
+                        g_boards.as<int8_t>(), g_laddered.as<int8_t>(), nullptr, g_status.as<int32_t>(), stream, nullptr);
+    if (rc) return rc;
+    if ((rc = liberties_launch(g_boards.as<int8_t>(), batch, g_libs.as<int8_t>(), stream))) return rc;
+    return assemble_features_launch(bk.d_moves.as<int16_t>(), bk.d_nmoves.as<int32_t>(), P3_MAX_GAME_MOVES, g_boards.as<int8_t>(),
+                                    g_libs.as<int8_t>(), g_laddered.as<int8_t>(), batch, d_feats.as<p3_go_features>(), stream);
   }
 
   int ensure_graph(bool to_host = false) {
@@ -429,6 +474,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       std::memset(bk.h_results, 0, sizeof(p3_infer_result) * B);
       std::memset(bk.h_sym, 0, B);
     }
+    P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_moves), sizeof(int16_t) * P3_MAX_GAME_MOVES * B));
+    P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_nmoves), sizeof(int32_t) * B));
+    P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_forbidden), static_cast<size_t>(361) * B));
+    for (int b = 0; b < B; ++b) bk.h_nmoves[b] = -1;
+    std::memset(bk.h_forbidden, 0, static_cast<size_t>(361) * B);
     if ((rc = bk.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
     if ((rc = bk.d_sym.alloc(B))) return rc;
     if ((rc = bk.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
@@ -883,6 +933,7 @@ int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* featu
   if (!e || !features || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "load_batch: bad argument");
   std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
   e->h_sym[batch_id] = 0;
+  e->banks[0].h_nmoves[batch_id] = -1;
   return P3_OK;
 }
 
@@ -891,6 +942,7 @@ int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* f
     return fail(P3_ERR_INVALID_ARG, "load_batch_sym: bad argument");
   std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
   e->h_sym[batch_id] = static_cast<int8_t>(sym);
+  e->banks[0].h_nmoves[batch_id] = -1;
   return P3_OK;
 }
 
@@ -901,8 +953,10 @@ int p3_engine_run_inference(p3_engine* e) {
   if (trace) P3_CUDA(cudaEventRecord(e->ev[0], e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_sym.p, e->h_sym, e->batch, cudaMemcpyHostToDevice, e->stream));
+  int rc = e->enqueue_game_records(e->banks[0], e->stream, nullptr);
+  if (rc) return rc;
   if (trace) P3_CUDA(cudaEventRecord(e->ev[1], e->stream));
-  int rc = e->enqueue_device_maybe_graph(e->results_to_host);
+  rc = e->enqueue_device_maybe_graph(e->results_to_host);
   if (rc) return rc;
   if (trace) P3_CUDA(cudaEventRecord(e->ev[2], e->stream));
   if (!e->results_to_host)
@@ -933,6 +987,25 @@ int p3_engine_load_batch_bank(p3_engine* e, int bank, int batch_id, const p3_go_
   p3_engine::Bank& bk = e->banks[bank];
   std::memcpy(&bk.h_feats[batch_id], features, sizeof(p3_go_features));
   bk.h_sym[batch_id] = static_cast<int8_t>(sym);
+  bk.h_nmoves[batch_id] = -1;
+  return P3_OK;
+}
+
+int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi,
+                             const int8_t* forbidden, int sym) {
+  if (!e || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch || sym < 0 || sym > 7 || num_moves < 0 ||
+      num_moves > P3_MAX_GAME_MOVES || (num_moves > 0 && !moves) || (color != P3_BLACK && color != P3_WHITE))
+    return fail(P3_ERR_INVALID_ARG, "load_game_bank: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  std::memcpy(bk.h_moves + static_cast<size_t>(batch_id) * P3_MAX_GAME_MOVES, moves, sizeof(int16_t) * num_moves);
+  if (forbidden) std::memcpy(bk.h_forbidden + static_cast<size_t>(batch_id) * 361, forbidden, 361);
+  else std::memset(bk.h_forbidden + static_cast<size_t>(batch_id) * 361, 0, 361);
+  p3_go_features& f = bk.h_feats[batch_id];   // colour, komi, bsize travel in the record; the grids and last moves are derived on the GPU
+  f.bsize = P3_BOARD_LEN;
+  f.color = static_cast<int8_t>(color);
+  f.komi = komi;
+  bk.h_sym[batch_id] = static_cast<int8_t>(sym);
+  bk.h_nmoves[batch_id] = num_moves;
   return P3_OK;
 }
 
@@ -952,7 +1025,9 @@ int p3_engine_submit(p3_engine* e, int bank) {
   P3_CUDA(cudaStreamWaitEvent(e->stream, bk.ev_h2d, 0));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, bk.d_feats.p, fbytes, cudaMemcpyDeviceToDevice, e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_sym.p, bk.d_sym.p, e->batch, cudaMemcpyDeviceToDevice, e->stream));
-  int rc = e->enqueue_device_maybe_graph(false);
+  int rc = e->enqueue_game_records(bk, e->h2d_stream, bk.ev_h2d);
+  if (rc) return rc;
+  rc = e->enqueue_device_maybe_graph(false);
   if (rc) return rc;
   P3_CUDA(cudaMemcpyAsync(bk.d_results.p, e->d_results.p, rbytes, cudaMemcpyDeviceToDevice, e->stream));
   P3_CUDA(cudaEventRecord(bk.ev_done, e->stream));

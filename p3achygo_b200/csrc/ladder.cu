@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -250,7 +251,8 @@ constexpr int kHistSmem = 608;
 constexpr int kReaderWarps = 4;
 constexpr int kFrameWords = 96;
 constexpr int kMaxCandPacked = 26;
-constexpr size_t kWarpSmemBytes = kHistSmem * 8 + kMaxDepth * 8 + kSmemFrames * kFrameWords * 4;
+constexpr size_t kWarpSmemBytes = kHistSmem * 8 + kMaxDepth * 8 + kSmemFrames * kFrameWords * 4 + (kMaxDepth + 3) * 2;
+static_assert(kWarpSmemBytes % 8 == 0, "per-warp shared memory slices stay 8-byte aligned");
 static_assert(kMaxCandPacked <= kMaxCand, "candidate capacity");
 
 struct DeepFrames {  // per resident warp: frames kSmemFrames .. kMaxDepth-1
@@ -300,28 +302,158 @@ __device__ __forceinline__ bool play_checked(Board& b, uint64_t& hash, int point
   return true;
 }
 
-__global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderTask* __restrict__ tasks, const int* __restrict__ n_tasks,
-                                                                   int* __restrict__ next_task, const uint32_t* __restrict__ rows,
-                                                                   const uint64_t* __restrict__ hist, const int32_t* __restrict__ n_hist,
-                                                                   int max_moves, DeepFrames* __restrict__ deep,
-                                                                   int8_t* __restrict__ laddered, int32_t* __restrict__ status,
-                                                                   long long* __restrict__ stats) {
+// A long search is split among warps.  Work items are sub-searches: "the value of Solve() entered with this move after
+// this path from the search root".  A warp runs an item as a plain depth-first search; when the item has cost kSplitNodes
+// nodes it stops, turns its live stack into nodes of an AND/OR tree (one per frame; the untried sibling moves of every
+// frame become new items, replayed from the root by whichever warp picks them up) and goes back to the queue.  A finished
+// item reports its value to its parent node: a deciding value (false under AND, true under OR) settles the parent at once,
+// otherwise the parent's pending count drops and the last child settles it with the neutral value; settled nodes report
+// upwards, a settled root writes the task's answer.  Items whose ancestors are already settled are dropped unrun.  Every
+// sub-search is a pure function of (position, path), so the answer is the sequential one; only the order differs.
+constexpr int kSplitNodesDefault = 16;   // measured: 10.6 ms unsplit, 2.2 ms at 96, 1.4 ms at 32, 0.98 ms at 16 (1024 random-playout positions)
+constexpr unsigned kDecided = 0x80000000u, kValTrue = 0x40000000u, kIsAnd = 0x20000000u, kPendMask = 0xFFFFu;
+
+struct TreeNode {
+  int parent;        // -1: the root of a task's search
+  unsigned state;    // kDecided | kValTrue | kIsAnd | pending children
+};
+
+struct Item {
+  int task, node, n_moves;
+  int moves_at;      // offset into the move pool: moves[0..n_moves-2] the path from the search root (known legal), moves[n_moves-1] the move to enter
+};
+
+struct Queue {
+  int n_tasks;       // written by replay_kernel (atomic counter)
+  int tail;          // items reserved
+  int head;          // items claimed
+  int outstanding;   // items queued or running
+  int n_nodes;       // tree nodes allocated
+  int dropped;       // items skipped because an ancestor was settled
+  int splits;        // successful splits
+  int full;          // splits refused for lack of room (the item then just keeps searching)
+  int pool_used;     // int16 entries of the move pool handed out
+  int pad;
+  long long nodes;   // Solve() activations over all items
+};
+
+__global__ void seed_items_kernel(const LadderTask* __restrict__ tasks, Queue* q, TreeNode* nodes, Item* items, int16_t* pool,
+                                  int* ready) {
+  const int n = q->n_tasks;   // <= the capacities by construction (ladder_run sizes them from the batch)
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    nodes[t] = TreeNode{-1, 0u};
+    items[t] = Item{t, t, 1, t};
+    pool[t] = static_cast<int16_t>(tasks[t].liberty);
+    __threadfence();
+    ready[t] = 1;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q->tail = n;
+    q->outstanding = n;
+    q->n_nodes = n;
+    q->pool_used = n;
+  }
+}
+
+// lane 0 only: child of `parent` finished with `v`; returns true when that settled the task's root (value in *root_value)
+__device__ __forceinline__ bool report_up(TreeNode* nodes, int parent, bool v, bool* root_value) {
+  while (true) {
+    if (parent < 0) {
+      *root_value = v;
+      return true;
+    }
+    unsigned* st = &nodes[parent].state;
+    bool settled = false;
+    while (true) {
+      const unsigned s = *reinterpret_cast<volatile unsigned*>(st);
+      if (s & kDecided) return false;            // somebody else settled it: this report is moot
+      const bool is_and = s & kIsAnd;
+      const bool deciding = is_and ? !v : v;
+      unsigned ns;
+      if (deciding || (s & kPendMask) == 1) {
+        ns = (s & ~kPendMask) | kDecided | (v ? kValTrue : 0u);   // the last non-deciding child carries the neutral value
+        settled = true;
+      } else {
+        ns = s - 1;
+        settled = false;
+      }
+      if (atomicCAS(st, s, ns) == s) break;
+    }
+    if (!settled) return false;
+    parent = nodes[parent].parent;               // the parent's value is v: carry it upwards
+  }
+}
+
+__global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderTask* __restrict__ tasks, Queue* q, TreeNode* nodes,
+                                                                   int node_cap, Item* items, int16_t* pool, int pool_cap,
+                                                                   int* ready, int item_cap,
+                                                                   const uint32_t* __restrict__ rows, const uint64_t* __restrict__ hist,
+                                                                   const int32_t* __restrict__ n_hist, int max_moves,
+                                                                   DeepFrames* __restrict__ deep, int8_t* __restrict__ laddered,
+                                                                   int32_t* __restrict__ status, int split_nodes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = blockIdx.x * kReaderWarps + wib;
-  unsigned char* base = smem_raw + wib * kWarpSmemBytes;
-  uint64_t* hist_s = reinterpret_cast<uint64_t*>(base);
+  unsigned char* base_ptr = smem_raw + wib * kWarpSmemBytes;
+  uint64_t* hist_s = reinterpret_cast<uint64_t*>(base_ptr);
   uint64_t* path_s = hist_s + kHistSmem;
   uint32_t* frames_s = reinterpret_cast<uint32_t*>(path_s + kMaxDepth);
+  int16_t* pmove = reinterpret_cast<int16_t*>(frames_s + kSmemFrames * kFrameWords);   // move entered at each call depth
   DeepFrames& D = deep[warp];
   auto frame = [&](int d) -> uint32_t* { return d < kSmemFrames ? frames_s + d * kFrameWords : D.w[d - kSmemFrames]; };
-  const int total = *n_tasks;
+  volatile int* v_ready = ready;
+  volatile int* v_out = &q->outstanding;
+  long long my_nodes = 0;
   while (true) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(next_task, 1);
-    t = __shfl_sync(kAll, t, 0);
-    if (t >= total) break;
-    const LadderTask task = tasks[t];
+    // ---- claim the next item; wait until it is published or nothing is left anywhere
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&q->head, 1);
+    idx = __shfl_sync(kAll, idx, 0);
+    bool have = false;
+    while (true) {
+      int r = 0, out = 1;
+      if (lane == 0) {
+        r = idx < item_cap ? v_ready[idx] : 0;
+        out = *v_out;
+      }
+      r = __shfl_sync(kAll, r, 0);
+      out = __shfl_sync(kAll, out, 0);
+      if (r) {
+        have = true;
+        break;
+      }
+      if (out == 0) break;
+      __nanosleep(200);
+    }
+    if (!have) break;
+    __threadfence();
+    const Item it = items[idx];
+    const int task_id = it.task, node_id = it.node, n_moves = it.n_moves;
+    if (task_id < 0) {  // a reserved slot that was given back
+      if (lane == 0) atomicSub(&q->outstanding, 1);
+      continue;
+    }
+    // dropped if an ancestor is already settled
+    int cancelled = 0;
+    if (lane == 0) {
+      int nd = nodes[node_id].parent;
+      while (nd >= 0) {
+        if (*reinterpret_cast<volatile unsigned*>(&nodes[nd].state) & kDecided) {
+          cancelled = 1;
+          break;
+        }
+        nd = nodes[nd].parent;
+      }
+    }
+    cancelled = __shfl_sync(kAll, cancelled, 0);
+    if (cancelled) {
+      if (lane == 0) {
+        atomicAdd(&q->dropped, 1);
+        atomicSub(&q->outstanding, 1);
+      }
+      continue;
+    }
+    const LadderTask task = tasks[task_id];
     const uint32_t* r = rows + static_cast<size_t>(task.pos) * 96;
     const Board root_board{r[lane], r[32 + lane]};
     const uint32_t fb = r[64 + lane];
@@ -330,24 +462,122 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
     const int nh_s = min(nh, kHistSmem);
     __syncwarp();
     for (int i = lane; i < nh_s; i += 32) hist_s[i] = my_hist[i];
+    for (int i = lane; i < n_moves; i += 32) pmove[i] = pool[it.moves_at + i];
     __syncwarp();
     const uint32_t rootbit = point_bit(task.root, lane);
     const int g_color = __any_sync(kAll, (rootbit & root_board.bk) != 0) ? P3_BLACK : P3_WHITE;
     const uint32_t root_group = flood(rootbit, g_color == P3_BLACK ? root_board.bk : root_board.wh, lane);
 
-    // Solve(board_copy, gid, g_color, OppositeColor(g_color), root, liberty, 0): the defender extends first (board.cc:863-866)
     Board b = root_board;
     uint32_t grp = root_group;
     uint64_t hash = my_hist[nh - 1];
-    int top = -1;            // index of the frame whose children are being tried; the call being entered has call_depth top + 1
-    int move = task.liberty;
-    int mover = g_color;
+    bool bad = false;
+    // the defender's group after one of his stones (board.cc:788-792): it only grows
+    auto grow = [&](int mv) {
+      const uint32_t own = g_color == P3_BLACK ? b.bk : b.wh;
+      const uint32_t mbit = point_bit(mv, lane);
+      if (__any_sync(kAll, (nbrs(mbit, lane) & grp) != 0)) {        // the stone joins the group ...
+        grp |= mbit;
+        if (__any_sync(kAll, (nbrs(mbit, lane) & own & ~grp) != 0)) grp = flood(grp, own, lane);  // ... and brings others along
+      }
+    };
+    // ---- replay the path to this item's position (moves at call depths 0 .. base-1, all legal when they were searched)
+    const int base = n_moves - 1;
+    for (int j = 0; j < base; ++j) {
+      const int mv = pmove[j];
+      const int who = (j & 1) ? -g_color : g_color;   // Solve(..., liberty, 0) is the defender's move (board.cc:863-866)
+      if (!play_checked(b, hash, mv, who, fb, hist_s, nh_s, my_hist, nh, path_s, j, lane)) bad = true;
+      if (who == g_color) grow(mv);
+      if (lane == 0) path_s[j] = hash;
+      __syncwarp();
+    }
+    int top = base - 1;      // index of the frame whose children are being tried; the call being entered has call_depth top + 1
+    int move = pmove[base];
+    int mover = (base & 1) ? -g_color : g_color;
     bool value = false;
-    bool overflow = false;
-    long long nodes = 0;
-    const long long c0 = stats ? clock64() : 0;
+    bool overflow = false, split_done = false, may_split = true;
+    int nodes_here = 0;
     while (true) {
-      ++nodes;
+      // ---- over budget: hand the untried parts of the stack to other warps
+      if (nodes_here >= split_nodes && top >= base && may_split) {
+        int n_items = 0;
+        for (int j = base; j <= top; ++j) {
+          const uint32_t meta = frame(j)[32 + 31];
+          const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8);
+          n_items += j < top ? n_cand - next - 1 : n_cand - next;
+        }
+        const int n_inner = top - base;
+        int n_pool = 0;
+        for (int j = base; j <= top; ++j) {
+          const uint32_t meta = frame(j)[32 + 31];
+          const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8);
+          n_pool += (j < top ? n_cand - next - 1 : n_cand - next) * (j + 2);
+        }
+        int node0 = 0, item0 = 0, pool0 = 0, ok = 0;
+        if (lane == 0) {
+          node0 = atomicAdd(&q->n_nodes, n_inner + n_items);
+          item0 = atomicAdd(&q->tail, n_items);
+          pool0 = atomicAdd(&q->pool_used, n_pool);
+          ok = node0 + n_inner + n_items <= node_cap && item0 + n_items <= item_cap && pool0 + n_pool <= pool_cap;
+          atomicAdd(&q->outstanding, n_items);   // before anything is published
+          if (!ok) atomicAdd(&q->full, 1);
+        }
+        node0 = __shfl_sync(kAll, node0, 0);
+        item0 = __shfl_sync(kAll, item0, 0);
+        pool0 = __shfl_sync(kAll, pool0, 0);
+        ok = __shfl_sync(kAll, ok, 0);
+        if (!ok) {
+          // no room: give the reserved queue slots back as no-ops so that nobody waits on them, and keep searching alone
+          if (lane == 0) {
+            int given = 0;
+            for (int k = 0; k < n_items; ++k)
+              if (item0 + k < item_cap) {
+                items[item0 + k].task = -1;
+                ++given;
+              }
+            __threadfence();
+            for (int k = 0; k < n_items; ++k)
+              if (item0 + k < item_cap) v_ready[item0 + k] = 1;
+            atomicSub(&q->outstanding, n_items - given);
+          }
+          may_split = false;
+        } else {
+          if (lane == 0) atomicAdd(&q->splits, 1);
+          int leaf = node0 + n_inner, slot = item0, at = pool0;
+          for (int j = base; j <= top; ++j) {
+            const uint32_t* f = frame(j);
+            const uint32_t meta = f[32 + 31];
+            const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8);
+            const int first = j < top ? next + 1 : next;                      // frame top's next move has not been entered yet
+            const int my_node = j == base ? node_id : node0 + (j - base - 1); // the item's own node turns from a leaf into an inner node
+            const int pending = (n_cand - first) + (j < top ? 1 : 0);         // untried siblings + the child in progress (frame j + 1)
+            if (lane == 0) {
+              if (j > base) nodes[my_node].parent = j - 1 == base ? node_id : my_node - 1;
+              atomicExch(&nodes[my_node].state, ((j & 1) ? kIsAnd : 0u) | static_cast<unsigned>(pending));
+            }
+            for (int c = first; c < n_cand; ++c) {
+              const uint32_t packed = f[19 + (c >> 1)];
+              const int mv = (packed >> ((c & 1) * 16)) & 0xFFFF;
+              for (int i = lane; i <= j; i += 32) pool[at + i] = pmove[i];
+              if (lane == 0) {
+                pool[at + j + 1] = static_cast<int16_t>(mv);
+                items[slot] = Item{task_id, leaf, j + 2, at};
+                nodes[leaf] = TreeNode{my_node, 0u};
+              }
+              at += j + 2;
+              ++leaf;
+              ++slot;
+            }
+          }
+          __threadfence();
+          __syncwarp();
+          if (lane == 0)
+            for (int k = 0; k < n_items; ++k) v_ready[item0 + k] = 1;
+          split_done = true;
+          break;
+        }
+      }
+      ++nodes_here;
       // ---- enter Solve(move by `mover`) from the position in (b, hash)
       bool returned = true;
       const int depth = top + 1;
@@ -357,16 +587,9 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
         value = mover == g_color;  // board.cc:782-786: an illegal move loses for its mover
       } else {
         const int to_move = -mover;
-        const uint32_t own = g_color == P3_BLACK ? b.bk : b.wh;
         const uint32_t opp = g_color == P3_BLACK ? b.wh : b.bk;
         const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
-        if (mover == g_color) {  // the group of group_root after the defender's stone (board.cc:788-792)
-          const uint32_t mbit = point_bit(move, lane);
-          if (__any_sync(kAll, (nbrs(mbit, lane) & grp) != 0)) {        // the stone joins the group ...
-            grp |= mbit;
-            if (__any_sync(kAll, (nbrs(mbit, lane) & own & ~grp) != 0)) grp = flood(grp, own, lane);  // ... and brings others along
-          }
-        }
+        if (mover == g_color) grow(move);
         uint32_t libs = nbrs(grp, lane) & empty;
         const int n_libs = warp_count(libs);
         if (to_move != g_color) {          // attacker to move (board.cc:800-812)
@@ -421,7 +644,10 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
           f[lane] = lane < P3_BOARD_LEN ? b.bk : cand_reg;
           f[32 + lane] = lane == 31 ? static_cast<uint32_t>(nc) : b.wh;   // next = 0
           f[64 + lane] = grp;
-          if (lane == 0) path_s[depth] = hash;
+          if (lane == 0) {
+            path_s[depth] = hash;
+            pmove[depth] = static_cast<int16_t>(move);
+          }
           __syncwarp();
           top = depth;
           mover = to_move;
@@ -432,14 +658,14 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
       // ---- a call returned `value`: unwind
       bool done = false;
       while (true) {
-        if (top < 0) {
+        if (top < base) {
           done = true;
           break;
         }
         uint32_t* f = frame(top);
         const uint32_t meta = f[32 + 31];
         const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8) + 1;
-        const bool is_and = top & 1;                     // frame d was pushed after the move at call depth d; defender moves at even depths
+        const bool is_and = top & 1;                     // frame d was pushed after the move at call depth d; the defender moves at even depths
         const bool decided = is_and ? !value : value;    // AND stops at the first false, OR at the first true
         if (decided || next >= n_cand) {                  // exhausted: AND -> true (all true), OR -> false (all false) == value
           --top;
@@ -459,17 +685,30 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
       }
       if (done) break;
     }
-    if (stats && lane == 0) {
-      stats[2 * t] = nodes;
-      stats[2 * t + 1] = clock64() - c0;
+    my_nodes += nodes_here;
+    if ((overflow || bad) && lane == 0) atomicOr(&status[task.pos], overflow ? 2 : 4);
+    if (!split_done) {
+      int root_done = 0, root_val = 0;
+      if (lane == 0) {
+        bool rv = false;
+        root_done = report_up(nodes, nodes[node_id].parent, value, &rv) ? 1 : 0;
+        root_val = rv ? 1 : 0;
+      }
+      root_done = __shfl_sync(kAll, root_done, 0);
+      root_val = __shfl_sync(kAll, root_val, 0);
+      if (root_done && root_val && lane < P3_BOARD_LEN) {
+        int8_t* l = laddered + static_cast<size_t>(task.pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
+        for (int c = 0; c < P3_BOARD_LEN; ++c)
+          if ((root_group >> c) & 1) l[c] = static_cast<int8_t>(g_color);
+      }
     }
-    if (overflow && lane == 0) atomicOr(&status[task.pos], 2);
-    if (value && lane < P3_BOARD_LEN) {
-      int8_t* l = laddered + static_cast<size_t>(task.pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
-      for (int c = 0; c < P3_BOARD_LEN; ++c)
-        if ((root_group >> c) & 1) l[c] = static_cast<int8_t>(g_color);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicSub(&q->outstanding, 1);
     }
   }
+  if (lane == 0 && my_nodes) atomicAdd(reinterpret_cast<unsigned long long*>(&q->nodes), static_cast<unsigned long long>(my_nodes));
 }
 
 // ---- kernel 3: exact legal mask (Game::IsValidMove over all 362 encodings, cc/game/game.cc:45-51) ----------------------
@@ -501,95 +740,162 @@ __global__ void __launch_bounds__(256) legal_exact_kernel(const uint32_t* __rest
 }  // namespace
 
 // Host entry: all buffers are device pointers except where noted; scratch is allocated per call.
-int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
-               int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream) {
-  if (n <= 0) return P3_OK;
+struct LadderWorkspace {
+  int n = 0, max_moves = 0, blocks = 0, item_cap = 0, node_cap = 0, pool_cap = 0, split_nodes = kSplitNodesDefault, sms = 148;
   uint32_t* rows = nullptr;
   uint64_t* hist = nullptr;
   int32_t* n_hist = nullptr;
   LadderTask* tasks = nullptr;
-  int* counters = nullptr;
+  Queue* queue = nullptr;
+  TreeNode* nodes = nullptr;
+  Item* items = nullptr;
+  int16_t* pool = nullptr;
+  int* ready = nullptr;
   DeepFrames* scratch = nullptr;
-  int sms = 148;
+};
+
+void ladder_workspace_destroy(LadderWorkspace* w) {
+  if (!w) return;
+  cudaFree(w->rows), cudaFree(w->hist), cudaFree(w->n_hist), cudaFree(w->tasks), cudaFree(w->queue), cudaFree(w->nodes), cudaFree(w->items),
+      cudaFree(w->pool), cudaFree(w->ready), cudaFree(w->scratch);
+  delete w;
+}
+
+int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out) {
+  LadderWorkspace* w = new LadderWorkspace();
+  w->n = n, w->max_moves = max_moves;
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int warps_per_block = kReaderWarps;
-  const int blocks = sms * 2;                      // 8 resident warps per SM, each with its own frame stack in shared memory
-  const int n_warps = blocks * warps_per_block;
-  const size_t reader_smem = kReaderWarps * kWarpSmemBytes;
-  int rc = P3_OK;
-  auto cleanup = [&]() {
-    cudaFree(rows), cudaFree(hist), cudaFree(n_hist), cudaFree(tasks), cudaFree(counters), cudaFree(scratch);
-  };
+  cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, dev);
+  w->blocks = w->sms * 2;                                  // 8 resident warps per SM, each with its own frame stack in shared memory
+  const int max_tasks = n * (P3_NUM_BOARD_LOCS / 2);       // groups in atari per position
+  w->item_cap = max_tasks + (1 << 17);
+  w->node_cap = max_tasks + (1 << 19);
+  w->pool_cap = max_tasks + (1 << 24);
+  if (const char* sn = std::getenv("P3_LADDER_SPLIT")) w->split_nodes = std::max(1, std::atoi(sn));
 #define P3_TRY(call)                                                                                     \
   do {                                                                                                   \
     cudaError_t _e = (call);                                                                             \
     if (_e != cudaSuccess) {                                                                             \
-      cleanup();                                                                                         \
+      ladder_workspace_destroy(w);                                                                       \
       return fail(P3_ERR_CUDA, std::string(#call) + " -> " + cudaGetErrorString(_e) + " (ladder.cu)");   \
     }                                                                                                    \
   } while (0)
-  P3_TRY(cudaMalloc(&rows, static_cast<size_t>(n) * 96 * sizeof(uint32_t)));
-  P3_TRY(cudaMalloc(&hist, static_cast<size_t>(n) * (max_moves + 1) * sizeof(uint64_t)));
-  P3_TRY(cudaMalloc(&n_hist, static_cast<size_t>(n) * sizeof(int32_t)));
-  P3_TRY(cudaMalloc(&tasks, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS / 2 * sizeof(LadderTask)));
-  P3_TRY(cudaMalloc(&counters, 2 * sizeof(int)));
-  P3_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
+  P3_TRY(cudaMalloc(&w->rows, static_cast<size_t>(n) * 96 * sizeof(uint32_t)));
+  P3_TRY(cudaMalloc(&w->hist, static_cast<size_t>(n) * (max_moves + 1) * sizeof(uint64_t)));
+  P3_TRY(cudaMalloc(&w->n_hist, static_cast<size_t>(n) * sizeof(int32_t)));
+  P3_TRY(cudaMalloc(&w->queue, sizeof(Queue)));
+  P3_TRY(cudaMalloc(&w->tasks, static_cast<size_t>(max_tasks) * sizeof(LadderTask)));
+  P3_TRY(cudaMalloc(&w->nodes, static_cast<size_t>(w->node_cap) * sizeof(TreeNode)));
+  P3_TRY(cudaMalloc(&w->items, static_cast<size_t>(w->item_cap) * sizeof(Item)));
+  P3_TRY(cudaMalloc(&w->pool, static_cast<size_t>(w->pool_cap) * sizeof(int16_t)));
+  P3_TRY(cudaMalloc(&w->ready, static_cast<size_t>(w->item_cap) * sizeof(int)));
+  P3_TRY(cudaMalloc(&w->scratch, static_cast<size_t>(w->blocks) * kReaderWarps * sizeof(DeepFrames)));
+  P3_TRY(cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kReaderWarps * kWarpSmemBytes)));
+#undef P3_TRY
+  *out = w;
+  return P3_OK;
+}
+
+// Asynchronous: replay -> (reader) -> (exact legal mask) on `stream`; device pointers; n <= the workspace's capacity.
+int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_num_moves, const int8_t* d_forbidden,
+                   const int8_t* d_colors, int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status,
+                   cudaStream_t stream, cudaEvent_t* ev) {
+  if (n <= 0) return P3_OK;
+  if (n > w->n) return fail(P3_ERR_INVALID_ARG, "ladder_enqueue: batch exceeds the workspace");
   const bool want_ladder = d_laddered != nullptr;
+  P3_CUDA(cudaMemsetAsync(w->queue, 0, sizeof(Queue), stream));
+  if (want_ladder) P3_CUDA(cudaMemsetAsync(w->ready, 0, static_cast<size_t>(w->item_cap) * sizeof(int), stream));
+  if (ev) cudaEventRecord(ev[0], stream);
+  replay_kernel<<<(n + 3) / 4, 128, 0, stream>>>(d_moves, d_num_moves, w->max_moves, d_forbidden, n, w->rows, w->hist, w->n_hist, d_boards,
+                                                 d_laddered, d_status, want_ladder ? w->tasks : nullptr, &w->queue->n_tasks);
+  P3_CUDA(cudaGetLastError());
+  if (ev) cudaEventRecord(ev[1], stream);
+  if (want_ladder) {
+    seed_items_kernel<<<w->sms, 256, 0, stream>>>(w->tasks, w->queue, w->nodes, w->items, w->pool, w->ready);
+    P3_CUDA(cudaGetLastError());
+    ladder_kernel<<<w->blocks, kReaderWarps * 32, kReaderWarps * kWarpSmemBytes, stream>>>(
+        w->tasks, w->queue, w->nodes, w->node_cap, w->items, w->pool, w->pool_cap, w->ready, w->item_cap, w->rows, w->hist, w->n_hist,
+        w->max_moves, w->scratch, d_laddered, d_status, w->split_nodes);
+    P3_CUDA(cudaGetLastError());
+  }
+  if (ev) cudaEventRecord(ev[2], stream);
+  if (d_legal && d_colors) {
+    legal_exact_kernel<<<n, kLegalSplit * 32, 0, stream>>>(w->rows, w->hist, w->n_hist, w->max_moves, d_colors, n, d_legal);
+    P3_CUDA(cudaGetLastError());
+  }
+  if (ev) cudaEventRecord(ev[3], stream);
+  return P3_OK;
+}
+
+int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
+               int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream) {
+  if (n <= 0) return P3_OK;
+  LadderWorkspace* w = nullptr;
+  int rc = ladder_workspace_create(n, max_moves, &w);
+  if (rc) return rc;
   const bool trace = std::getenv("P3_LADDER_TRACE") != nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  long long* d_stats = nullptr;
-  if (trace) {
-    cudaMalloc(&d_stats, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS * sizeof(long long));
-    cudaMemset(d_stats, 0, static_cast<size_t>(n) * P3_NUM_BOARD_LOCS * sizeof(long long));
+  if (trace)
     for (auto& e : ev) cudaEventCreate(&e);
-    if (want_ladder) cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(DeepFrames));
-    cudaEventRecord(ev[0], stream);
-  }
-  replay_kernel<<<(n + 3) / 4, 128, 0, stream>>>(d_moves, d_num_moves, max_moves, d_forbidden, n, rows, hist, n_hist, d_boards,
-                                                 d_laddered, d_status, want_ladder ? tasks : nullptr, counters);
-  P3_TRY(cudaGetLastError());
-  if (trace) cudaEventRecord(ev[1], stream);
-  if (want_ladder) {
-    if (!scratch) P3_TRY(cudaMalloc(&scratch, static_cast<size_t>(n_warps) * sizeof(DeepFrames)));
-    P3_TRY(cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(reader_smem)));
-    ladder_kernel<<<blocks, warps_per_block * 32, reader_smem, stream>>>(tasks, counters, counters + 1, rows, hist, n_hist, max_moves, scratch,
-                                                               d_laddered, d_status, d_stats);
-    P3_TRY(cudaGetLastError());
-  }
-  if (trace) cudaEventRecord(ev[2], stream);
-  if (d_legal && d_colors) {
-    legal_exact_kernel<<<n, kLegalSplit * 32, 0, stream>>>(rows, hist, n_hist, max_moves, d_colors, n, d_legal);
-    P3_TRY(cudaGetLastError());
-  }
-  if (trace) cudaEventRecord(ev[3], stream);
-  P3_TRY(cudaStreamSynchronize(stream));
-  if (trace) {
+  rc = ladder_enqueue(w, d_moves, d_num_moves, d_forbidden, d_colors, n, d_boards, d_laddered, d_legal, d_status, stream,
+                      trace ? ev : nullptr);
+  cudaError_t se = cudaStreamSynchronize(stream);
+  if (!rc && se != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("ladder_run: ") + cudaGetErrorString(se));
+  if (trace && !rc) {
     float a = 0, b = 0, c = 0;
-    int h_counters[2] = {0, 0};
-    cudaMemcpy(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost);
+    Queue h{};
+    cudaMemcpy(&h, w->queue, sizeof(h), cudaMemcpyDeviceToHost);
     cudaEventElapsedTime(&a, ev[0], ev[1]), cudaEventElapsedTime(&b, ev[1], ev[2]), cudaEventElapsedTime(&c, ev[2], ev[3]);
-    std::fprintf(stderr, "[p3 ladder] n %d  replay+tasks %.3f ms  reader %.3f ms (%d searches)  exact legal %.3f ms\n", n, a, b,
-                 h_counters[0], c);
-    for (auto& e : ev) cudaEventDestroy(e);
-    if (want_ladder && h_counters[0] > 0) {
-      std::vector<long long> st(2 * static_cast<size_t>(h_counters[0]));
-      cudaMemcpy(st.data(), d_stats, st.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-      long long tot = 0, mx = 0, cyc = 0, mxc = 0;
-      for (int i = 0; i < h_counters[0]; ++i) {
-        tot += st[2 * i], cyc += st[2 * i + 1];
-        if (st[2 * i] > mx) mx = st[2 * i];
-        if (st[2 * i + 1] > mxc) mxc = st[2 * i + 1];
-      }
-      std::fprintf(stderr, "[p3 ladder] nodes total %lld  max per search %lld  cycles per node %.0f  longest search %lld cycles\n", tot, mx,
-                   tot ? static_cast<double>(cyc) / tot : 0.0, mxc);
-    }
-    cudaFree(d_stats);
+    std::fprintf(stderr,
+                 "[p3 ladder] n %d  replay+tasks %.3f ms  reader %.3f ms (%d searches, %lld nodes, %d items, %d splits, %d dropped, "
+                 "%d refused)  exact legal %.3f ms\n",
+                 n, a, b, h.n_tasks, h.nodes, h.tail, h.splits, h.dropped, h.full, c);
   }
-#undef P3_TRY
-  cleanup();
+  if (trace)
+    for (auto& e : ev) cudaEventDestroy(e);
+  ladder_workspace_destroy(w);
   return rc;
+}
+
+// ---- GoFeatures from the derived grids (NNInterface::LoadBatch, cc/nn/nn_interface.cc:245-277, in identity orientation) --------
+__global__ void __launch_bounds__(128) assemble_features_kernel(const int16_t* __restrict__ moves, const int32_t* __restrict__ num_moves,
+                                                                int max_moves, const int8_t* __restrict__ boards,
+                                                                const int8_t* __restrict__ libs, const int8_t* __restrict__ laddered, int n,
+                                                                p3_go_features* __restrict__ feats) {
+  const int b = blockIdx.x;
+  const int nm = num_moves[b];
+  if (nm < 0) return;  // this slot was loaded as GoFeatures
+  p3_go_features& f = feats[b];
+  const size_t at = static_cast<size_t>(b) * P3_NUM_BOARD_LOCS;
+  for (int p = threadIdx.x; p < P3_NUM_BOARD_LOCS; p += blockDim.x) {
+    f.board[p] = boards[at + p];
+    f.stones_atari[p] = libs[at * 3 + p];
+    f.stones_two_liberties[p] = libs[at * 3 + P3_NUM_BOARD_LOCS + p];
+    f.stones_three_liberties[p] = libs[at * 3 + 2 * P3_NUM_BOARD_LOCS + p];
+    f.stones_laddered[p] = laddered[at + p];
+  }
+  if (threadIdx.x < P3_NUM_LAST_MOVES) {  // the last five moves, oldest first; kNoopLoc pad, kPassLoc for passes (nn_interface.cc:249-257)
+    const int k = threadIdx.x;
+    const int count = min(nm, max_moves);
+    const int off = count - P3_NUM_LAST_MOVES + k;
+    p3_loc loc{-1, -1};
+    if (off >= 0) {
+      const int code = moves[static_cast<size_t>(b) * max_moves + off];
+      const int point = code & (kWhiteBit - 1);
+      if (code >= 0) loc = point >= P3_PASS_ENCODING ? p3_loc{19, 0} : p3_loc{point / P3_BOARD_LEN, point % P3_BOARD_LEN};
+    }
+    f.last_moves[k] = loc;
+  }
+  if (threadIdx.x == 0) f.bsize = P3_BOARD_LEN;
+}
+
+int assemble_features_launch(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_boards, const int8_t* d_libs,
+                             const int8_t* d_laddered, int n, p3_go_features* d_feats, cudaStream_t stream) {
+  if (n <= 0) return P3_OK;
+  assemble_features_kernel<<<n, 128, 0, stream>>>(d_moves, d_num_moves, max_moves, d_boards, d_libs, d_laddered, n, d_feats);
+  P3_CUDA(cudaGetLastError());
+  return P3_OK;
 }
 
 }  // namespace p3

@@ -117,6 +117,13 @@ class B200Engine:
         arr = np.ascontiguousarray(np.asarray(features, dtype=GO_FEATURES_DTYPE).reshape(1))
         check(lib.p3_engine_load_batch_bank(self._h, bank, batch_id, ptr(arr), int(sym)))
 
+    def LoadGameBank(self, bank: int, batch_id: int, moves: np.ndarray, color: int, komi: float, forbidden=None, sym: int = 0) -> None:
+        """NNInterface::LoadBatch from the game record (nn_interface.cc:245-277): the derived grids are computed on the GPU."""
+        mv = np.ascontiguousarray(moves, dtype=np.int16)
+        fb = np.ascontiguousarray(forbidden, dtype=np.int8) if forbidden is not None else None
+        check(lib.p3_engine_load_game_bank(self._h, bank, batch_id, ptr(mv), len(mv), int(color), float(komi),
+                                           ptr(fb) if fb is not None else None, int(sym)))
+
     def Submit(self, bank: int) -> None:
         """Asynchronous half of RunInference for one bank (H2D -> step -> D2H on copy streams); returns at once."""
         check(lib.p3_engine_submit(self._h, bank))

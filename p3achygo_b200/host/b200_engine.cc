@@ -41,6 +41,10 @@ void B200Engine::GetBatch(int batch_id, NNInferResult& result) { P3_CHECK(p3_eng
 void B200Engine::LoadBatchBank(int bank, int batch_id, const GoFeatures& features, int sym) {
   P3_CHECK(p3_engine_load_batch_bank(engine_, bank, batch_id, &features, sym));
 }
+void B200Engine::LoadGameBank(int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi,
+                              const int8_t* forbidden, int sym) {
+  P3_CHECK(p3_engine_load_game_bank(engine_, bank, batch_id, moves, num_moves, color, komi, forbidden, sym));
+}
 void B200Engine::Submit(int bank) { P3_CHECK(p3_engine_submit(engine_, bank)); }
 void B200Engine::Wait(int bank) { P3_CHECK(p3_engine_wait(engine_, bank)); }
 void B200Engine::GetBatchBank(int bank, int batch_id, NNInferResult& result) {

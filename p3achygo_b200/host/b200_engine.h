@@ -27,6 +27,9 @@ class B200Engine final : public Engine {
   // RunInference() == Submit(0) + Wait(0) in effect; results are identical.
   static constexpr int kNumBanks = P3_NUM_BANKS;
   void LoadBatchBank(int bank, int batch_id, const GoFeatures& features, int sym = 0);
+  // NNInterface::LoadBatch from the game record (nn_interface.cc:245-277): moves as p3_game_derive encodes them; the board, the
+  // liberty grids, the laddered stones and the last moves are derived on the GPU by the next run of that bank.
+  void LoadGameBank(int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi, const int8_t* forbidden, int sym);
   void Submit(int bank);
   void Wait(int bank);
   void GetBatchBank(int bank, int batch_id, NNInferResult& result);

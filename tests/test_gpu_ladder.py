@@ -134,3 +134,72 @@ def test_game_derive_matches_live_reference():
     assert not status.any() and len(recs) > 100
     assert np.array_equal(lad, np.stack([r[3] for r in recs]))
     assert np.array_equal(legal, np.stack([r[4] for r in recs]))
+
+
+def _features_from_fixture(games, idx, komi=7.5):
+    """The GoFeatures NNInterface::LoadBatch would build (identity orientation) from the reference's own outputs in the fixture."""
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200._lib import GO_FEATURES_DTYPE
+    boards = games["boards"][idx]
+    libs = E.board_liberties(boards)            # bit-exact vs Board::GetStonesWithLiberties (tests/test_gpu_features.py)
+    feats = np.zeros(len(idx), dtype=GO_FEATURES_DTYPE)
+    feats["bsize"] = 19
+    feats["color"] = games["colors"][idx]
+    feats["komi"] = komi
+    feats["board"] = boards
+    feats["stones_atari"] = libs[:, 0]
+    feats["stones_two_liberties"] = libs[:, 1]
+    feats["stones_three_liberties"] = libs[:, 2]
+    feats["stones_laddered"] = games["ladder"][idx]
+    for k, g in enumerate(idx):
+        nm = int(games["num_moves"][g])
+        for j in range(5):
+            off = nm - 5 + j
+            if off < 0:
+                feats["last_moves"][k, j] = (-1, -1)
+            else:
+                p = int(games["moves"][g, off]) & 511
+                feats["last_moves"][k, j] = (19, 0) if p == 361 else (p // 19, p % 19)
+    return feats
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_engine_game_record_slots_equal_feature_slots(pipelined, games, weight_dir):
+    """p3_engine_load_game_bank: a slot loaded as a game record gives, bit for bit, the planes and the NNInferResult of the
+    same position loaded as the GoFeatures the reference builds - all symmetries, mixed with feature slots in one batch."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 64
+    idx = np.concatenate([np.arange(0, 17), np.arange(100, 100 + 2 * B - 17)])   # the reference's ladder tests + playouts
+    feats = _features_from_fixture(games, idx)
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    for half in range(2):
+        sel = idx[half * B:(half + 1) * B]
+        for b in range(B):
+            eng.LoadBatchSym(b, feats[half * B + b], b % 8)
+        eng.RunInference()
+        want = [eng.GetBatch(b).copy() for b in range(B)]
+        want_planes = [eng.GetPlanes(b) for b in range(B)]
+        for b in range(B):
+            g = sel[b]
+            if b % 5 == 4:   # some slots stay GoFeatures slots
+                if pipelined:
+                    eng.LoadBatchBank(1, b, feats[half * B + b], b % 8)
+                else:
+                    eng.LoadBatchSym(b, feats[half * B + b], b % 8)
+                continue
+            mv = games["moves"][g][: games["num_moves"][g]]
+            eng.LoadGameBank(1 if pipelined else 0, b, mv, int(games["colors"][g]), 7.5, games["forbidden"][g], b % 8)
+        if pipelined:
+            eng.Submit(1)
+            eng.Wait(1)
+        else:
+            eng.RunInference()
+        for b in range(B):
+            got = eng.GetBatchBank(1, b) if pipelined else eng.GetBatch(b)
+            for f in got.dtype.names:
+                assert np.array_equal(got[f], want[b][f]), (half, b, f)
+            pl, sc = eng.GetPlanes(b)
+            assert np.array_equal(pl, want_planes[b][0]) and np.array_equal(sc, want_planes[b][1]), (half, b)
+    eng.close()
