@@ -376,6 +376,26 @@ def main():
     pipe_us = reduce_max(float(outp[0]))
     e2e_value = world * B / (pipe_us * 1e-6)
 
+    # ---- the same pipelined cycle with the slots loaded as GAME RECORDS (move lists): board, liberty grids, laddered stones and last
+    # moves are derived on the GPU inside the step (p3_engine_load_game_bank) - the work NNInterface::LoadBatch does on the host
+    gz = np.load(os.path.join(ROOT, "tests", "golden", "ladder_games.npz"))
+    g_moves = np.ascontiguousarray(gz["moves"][17:], dtype=np.int16)
+    g_num = np.ascontiguousarray(gz["num_moves"][17:], dtype=np.int32)
+    g_col = np.ascontiguousarray(gz["colors"][17:], dtype=np.int8)
+    host.p3_host_benchmark_games.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_void_p]
+    outg = np.zeros(5, dtype=np.float64)
+    barrier()
+    host.p3_host_benchmark_games(wpath.encode(), local, B, 1, precision, _lib.ptr(g_moves), _lib.ptr(g_num), _lib.ptr(g_col),
+                                 g_moves.shape[1], len(g_moves), args.warmup, args.steps, threads, _lib.ptr(outg))
+    barrier()
+    games_us = reduce_max(float(outg[0]))
+    e2e_games = {"value": world * B / (games_us * 1e-6), "unit": "positions/s", "cycle_us": games_us,
+                 "h2d_bytes_per_step": int((1860 + 2 * 1024 + 4 + 361 + 1) * B), "d2h_bytes_per_step": D2H_PER_POS * B,
+                 "path": "LoadGameBank x B (move lists of 1280 random-playout game records, cycled) -> Submit | Wait -> GetBatchBank x B; "
+                         "replay + ladder reader + liberties + feature assembly run on the GPU in front of the encode kernel"}
+
     # ---- the same step replayed back to back (no host staging between steps): what a saturated evaluator sustains.
     # The board power limit, not the kernels, sets this number: NVML reports sw_power_cap and lower SM clocks here.
     n_sus = int(os.environ.get("P3_SUSTAINED_STEPS", "150"))
@@ -415,6 +435,7 @@ def main():
                            "path": "the reference's own cycle, nothing overlapped: LoadBatch x B -> RunInference -> GetBatch x B "
                                    "(cc/nn/engine/benchmark_engine.cc:77-109 shape)"}},
         "gpu_launches": None,
+        "e2e_from_game_records": e2e_games,
         "sustained": sustained,
         "roofline": roofline,
     }

@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -831,9 +832,20 @@ int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_
 int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_forbidden, const int8_t* d_colors,
                int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status, cudaStream_t stream) {
   if (n <= 0) return P3_OK;
-  LadderWorkspace* w = nullptr;
-  int rc = ladder_workspace_create(n, max_moves, &w);
-  if (rc) return rc;
+  // the stand-alone entry keeps one workspace per device between calls (its ~170 MB of scratch cost more to allocate than the
+  // kernels take to run); calls are serialised on it
+  static std::mutex mu;
+  static LadderWorkspace* cached[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  LadderWorkspace*& w = cached[dev & 63];
+  int rc = P3_OK;
+  if (!w || w->n < n || w->max_moves != max_moves) {
+    ladder_workspace_destroy(w);
+    w = nullptr;
+    if ((rc = ladder_workspace_create(n, max_moves, &w))) return rc;
+  }
   const bool trace = std::getenv("P3_LADDER_TRACE") != nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (trace)
@@ -854,7 +866,6 @@ int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves
   }
   if (trace)
     for (auto& e : ev) cudaEventDestroy(e);
-  ladder_workspace_destroy(w);
   return rc;
 }
 

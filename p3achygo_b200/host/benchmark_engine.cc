@@ -129,8 +129,28 @@ int p3_host_benchmark(const char* weights_path, int device, int batch, int versi
 // still loaded from host memory, evaluated, and read back into a caller-owned NNInferResult inside the timed region.
 //   out[0] whole cycle per batch (us, total wall time / steps)   out[1] LoadBatch x B   out[2] GetBatch x B
 //   out[3] Wait (time the host blocked on the GPU)               out[4] checksum of value_probs
+// games != nullptr: the slots are loaded as game records instead (LoadGameBank: n_positions move lists of max_moves int16 codes,
+// num_moves, colours; komi 7.5), so the board, the liberty grids and the laddered stones are derived on the GPU inside the step.
+static int pipelined_cycle(const char* weights_path, int device, int batch, int version, int precision,
+                           const p3_go_features* positions, const int16_t* games, const int32_t* num_moves, const int8_t* colors,
+                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out);
+
 int p3_host_benchmark_pipelined(const char* weights_path, int device, int batch, int version, int precision,
                                 const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
+  return pipelined_cycle(weights_path, device, batch, version, precision, positions, nullptr, nullptr, nullptr, 0, n_positions, warmup,
+                         steps, threads, out);
+}
+
+int p3_host_benchmark_games(const char* weights_path, int device, int batch, int version, int precision, const int16_t* games,
+                            const int32_t* num_moves, const int8_t* colors, int max_moves, int n_games, int warmup, int steps,
+                            int threads, double* out) {
+  return pipelined_cycle(weights_path, device, batch, version, precision, nullptr, games, num_moves, colors, max_moves, n_games, warmup,
+                         steps, threads, out);
+}
+
+static int pipelined_cycle(const char* weights_path, int device, int batch, int version, int precision,
+                           const p3_go_features* positions, const int16_t* games, const int32_t* num_moves, const int8_t* colors,
+                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out) {
   auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
   std::vector<nn::NNInferResult> results(batch);
   WorkerPool pool(threads);
@@ -140,7 +160,13 @@ int p3_host_benchmark_pipelined(const char* weights_path, int device, int batch,
   auto load = [&](int bank) {
     const int base = cursor;
     cursor = (cursor + batch) % n_positions;
-    pool.run(batch, [&](int b) { engine->LoadBatchBank(bank, b, positions[(base + b) % n_positions]); });
+    if (games)
+      pool.run(batch, [&](int b) {
+        const int g = (base + b) % n_positions;
+        engine->LoadGameBank(bank, b, games + static_cast<size_t>(g) * max_moves, num_moves[g], colors[g], 7.5f, nullptr, g % 8);
+      });
+    else
+      pool.run(batch, [&](int b) { engine->LoadBatchBank(bank, b, positions[(base + b) % n_positions]); });
   };
   Clock::time_point t_start = Clock::now();
   load(0);
