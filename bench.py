@@ -270,6 +270,10 @@ def main():
         run_reference_arm(args)
         return
 
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local, reduce_max, barrier = dist_setup(args.gpus)
     from p3achygo_b200 import engine as E
     from p3achygo_b200 import weights as W
@@ -452,7 +456,8 @@ def main():
                                 "sample": f"{n_sample} positions of the same workload in {dt:.1f} s; features: C restatement of "
                                           "go_features.cc, net: PyTorch-CPU restatement of python/model.py (TensorFlow absent)"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
