@@ -2,7 +2,8 @@
  * TEST INFRASTRUCTURE — NOT PRODUCT CODE.
  *
  * CPU restatement (plain C) of the integer / byte / PRNG algorithms on p3achygo's
- * leaf-evaluation hot path.  Each function cites the reference file:line it follows.
+ * leaf-evaluation hot path (feature fill, symmetry, liberties, legality, PCG32 / Gumbel, softmax, leaf statistics, and the
+ * rules from a game record: replay, ladder reader, exact legal mask).  Each function cites the reference file:line it follows.
  * It is the checker the CUDA kernels are compared with on the GPU box (where
  * /root/reference does not exist).  PARITY PINNED: tests/test_oracle_vs_ref.py checks every
  * function here bit-for-bit against the reference's own sources compiled unmodified
@@ -274,4 +275,200 @@ void orc_init_fields(const float* value_probs, const float* score_probs, float* 
   out3[0] = value_probs[0] * -1 + value_probs[1] * 1;
   out3[1] = score_est;
   out3[2] = score_sq_est - score_est * score_est;
+}
+
+/* ==== rules from a game record: replay, superko history, ladder reader, exact legal mask ====================
+ * Restates Board::PlayMove / PlayMoveDry (cc/game/board.cc:536-644), Board::IsSelfCapture (:901-915) and
+ * Board::GetLadderedStones with its Solver (:692-899) on plain arrays, with the recursion and the Board copies of the
+ * reference kept as they are.  PARITY PINNED: tests/test_oracle_golden.py compares it with tests/golden/ladder_games.npz
+ * (outputs of the compiled reference for 1297 game records, among them the positions of the reference's own ladder tests,
+ * cc/game/__tests__/board_test.cc "LadderTest") and tests/test_oracle_vs_ref.py with the compiled reference directly.
+ * Hashes: any injective-in-practice position hash reproduces seen_states_ membership; the reference's Zobrist table is
+ * seeded from the clock (cc/game/zobrist.cc), so a splitmix64 table is used here. */
+#define ORC_MAX_SEEN 2048
+#define ORC_WHITE_BIT 512
+
+typedef struct {
+  int8_t at[NLOCS];
+  uint64_t hash;
+  uint64_t seen[ORC_MAX_SEEN]; /* Board::seen_states_ (board.h:372): copied with the board, as the reference does */
+  int n_seen;
+} orc_board;
+
+static uint64_t orc_zobrist(int p, int is_white) {
+  uint64_t x = ((uint64_t)p * 2 + (uint64_t)is_white + 1) * 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+static int orc_adjacent(int p, int out[4]) {
+  int n = 0, i = p / BOARD_LEN, j = p % BOARD_LEN;
+  if (i > 0) out[n++] = p - BOARD_LEN;
+  if (i < BOARD_LEN - 1) out[n++] = p + BOARD_LEN;
+  if (j > 0) out[n++] = p - 1;
+  if (j < BOARD_LEN - 1) out[n++] = p + 1;
+  return n;
+}
+
+/* GroupTracker::ExpandGroup + LibertiesForGroup (board.cc:150-168): stones of p's group, its distinct liberties */
+static int orc_group(const int8_t* at, int p, int* stones, int* n_stones, int* libs) {
+  uint8_t mark[NLOCS];
+  int stack[NLOCS], sp = 0, ns = 0, nl = 0, nb[4];
+  memset(mark, 0, sizeof mark);
+  const int8_t c = at[p];
+  stack[sp++] = p;
+  mark[p] = 1;
+  while (sp) {
+    const int q = stack[--sp];
+    stones[ns++] = q;
+    const int k = orc_adjacent(q, nb);
+    for (int t = 0; t < k; ++t) {
+      const int r = nb[t];
+      if (mark[r]) continue;
+      if (at[r] == c) {
+        mark[r] = 1;
+        stack[sp++] = r;
+      } else if (at[r] == 0) {
+        mark[r] = 1;
+        if (libs) libs[nl] = r;
+        ++nl;
+      }
+    }
+  }
+  *n_stones = ns;
+  return nl;
+}
+
+/* Board::PlayMoveDry + PlayMove for a board point (board.cc:536-580, 595-644).  check = 0: replay of a recorded move. */
+static int orc_play(orc_board* b, int p, int8_t color, int check, const int8_t* forbidden) {
+  int nb[4], stones[NLOCS], ns, captured[NLOCS], nc = 0;
+  if (check && (b->at[p] != 0 || (forbidden && forbidden[p]))) return 0; /* kLocNotEmpty / kPassAliveRegion */
+  const int k = orc_adjacent(p, nb);
+  b->at[p] = color;
+  for (int t = 0; t < k; ++t) { /* GetCapturedGroups: opposing neighbours whose only liberty was p */
+    const int q = nb[t];
+    if (b->at[q] != -color) continue;
+    int dup = 0;
+    for (int c = 0; c < nc; ++c) dup |= captured[c] == q;
+    if (dup) continue;
+    if (orc_group(b->at, q, stones, &ns, NULL) == 0)
+      for (int s = 0; s < ns; ++s) captured[nc++] = stones[s];
+  }
+  if (nc == 0 && check && orc_group(b->at, p, stones, &ns, NULL) == 0) { /* IsSelfCapture, board.cc:901-915 */
+    b->at[p] = 0;
+    return 0;
+  }
+  uint64_t h = b->hash ^ orc_zobrist(p, color < 0);
+  for (int c = 0; c < nc; ++c) h ^= orc_zobrist(captured[c], -color < 0);
+  if (check)
+    for (int s = 0; s < b->n_seen; ++s)
+      if (b->seen[s] == h) { /* kRepeatedPosition, board.cc:636-640 */
+        b->at[p] = 0;
+        return 0;
+      }
+  for (int c = 0; c < nc; ++c) b->at[captured[c]] = 0;
+  b->hash = h;
+  if (b->n_seen < ORC_MAX_SEEN) b->seen[b->n_seen++] = h;
+  return 1;
+}
+
+/* Solver::Solve, board.cc:776-840.  `board` is this call's own copy. */
+static int orc_solve(orc_board* board, int8_t g_color, int8_t color_to_move, int group_root, int last_move, int call_depth,
+                     const int8_t* forbidden) {
+  if (call_depth > 300) return 0;
+  if (!orc_play(board, last_move, (int8_t)-color_to_move, 1, forbidden)) return g_color != color_to_move;
+  int stones[NLOCS], ns, libs[NLOCS];
+  const int liberties = orc_group(board->at, group_root, stones, &ns, libs);
+  orc_board* copy = (orc_board*)malloc(sizeof(orc_board));
+  int result;
+  if (g_color != color_to_move) { /* try to capture (:800-812) */
+    if (liberties > 2) result = 0;
+    else if (liberties <= 1) result = 1;
+    else {
+      *copy = *board;
+      result = orc_solve(copy, g_color, (int8_t)-color_to_move, group_root, libs[0], call_depth + 1, forbidden);
+      if (!result) {
+        *copy = *board;
+        result = orc_solve(copy, g_color, (int8_t)-color_to_move, group_root, libs[1], call_depth + 1, forbidden);
+      }
+    }
+  } else { /* try to refute (:813-839) */
+    if (liberties > 1) result = 0;
+    else {
+      *copy = *board;
+      if (!orc_solve(copy, g_color, (int8_t)-color_to_move, group_root, libs[0], call_depth + 1, forbidden)) {
+        result = 0;
+      } else {
+        result = 1;
+        /* FindSurroundingStonesInAtari (:744-770): opposing groups next to the group with one liberty; capture them */
+        uint8_t done[NLOCS];
+        memset(done, 0, sizeof done);
+        int nb[4], s2[NLOCS], n2, l2[NLOCS];
+        for (int s = 0; s < ns && result; ++s) {
+          const int k = orc_adjacent(stones[s], nb);
+          for (int t = 0; t < k && result; ++t) {
+            const int q = nb[t];
+            if (board->at[q] != -g_color || done[q]) continue;
+            const int nl = orc_group(board->at, q, s2, &n2, l2);
+            for (int u = 0; u < n2; ++u) done[s2[u]] = 1;
+            if (nl != 1) continue;
+            *copy = *board;
+            if (!orc_solve(copy, g_color, (int8_t)-color_to_move, group_root, l2[0], call_depth + 1, forbidden)) result = 0;
+          }
+        }
+      }
+    }
+  }
+  free(copy);
+  return result;
+}
+
+/* Replays `moves` (codes: point 0..360 or 361 = pass, + 512 for WHITE; Game::moves()) from the empty board and returns
+ * board [361], laddered [361] (Board::GetLadderedStones, board.cc:842-899) and, when legal != NULL, Game::IsValidMove for
+ * `color` over all 362 encodings (game.cc:45-51).  forbidden: pass-alive points (optional).  Returns 0, or 1 for an
+ * impossible record. */
+int orc_game_derive(const int16_t* moves, int num_moves, const int8_t* forbidden, int8_t color, int8_t* board, int8_t* laddered,
+                    uint8_t* legal) {
+  orc_board* b = (orc_board*)calloc(1, sizeof(orc_board));
+  orc_board* copy = (orc_board*)malloc(sizeof(orc_board));
+  b->seen[b->n_seen++] = 0; /* the empty board (board.cc:505-513) */
+  int rc = 0;
+  for (int m = 0; m < num_moves && !rc; ++m) {
+    const int code = moves[m], p = code & (ORC_WHITE_BIT - 1);
+    if (code < 0 || p >= NLOCS) continue; /* Board::Pass leaves seen_states_ alone (board.cc:582-593) */
+    if (b->at[p] != 0) rc = 1;
+    else orc_play(b, p, (code & ORC_WHITE_BIT) ? -1 : 1, 0, NULL);
+  }
+  memcpy(board, b->at, NLOCS);
+  if (laddered) {
+    memset(laddered, 0, NLOCS);
+    uint8_t visited[NLOCS];
+    memset(visited, 0, sizeof visited);
+    int stones[NLOCS], ns, libs[NLOCS], nb[4];
+    for (int p = 0; p < NLOCS && !rc; ++p) { /* groups in atari (:874-882) */
+      if (b->at[p] == 0 || visited[p]) continue;
+      const int nl = orc_group(b->at, p, stones, &ns, libs);
+      for (int s = 0; s < ns; ++s) visited[stones[s]] = 1;
+      if (nl != 1) continue;
+      int empties = 0; /* IsLaddered's quick reject: GroupTracker::LibertiesAt(liberty) >= 3 (:857-860) */
+      const int k = orc_adjacent(libs[0], nb);
+      for (int t = 0; t < k; ++t) empties += b->at[nb[t]] == 0;
+      if (empties >= 3) continue;
+      const int8_t g_color = b->at[p];
+      *copy = *b;
+      if (orc_solve(copy, g_color, (int8_t)-g_color, p, libs[0], 0, forbidden))
+        for (int s = 0; s < ns; ++s) laddered[stones[s]] = g_color;
+    }
+  }
+  if (legal) {
+    for (int p = 0; p < NLOCS; ++p) {
+      *copy = *b;
+      legal[p] = (uint8_t)orc_play(copy, p, color, 1, forbidden);
+    }
+    legal[NLOCS] = 1; /* pass (board.cc:516-518) */
+  }
+  free(copy);
+  free(b);
+  return rc;
 }

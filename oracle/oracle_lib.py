@@ -52,6 +52,7 @@ def oracle() -> ctypes.CDLL:
         L.orc_gumbel_topk.argtypes = [u64p, vp, vp, cf, ci, vp, vp]
         L.orc_softmax.argtypes = [ci, vp, vp]
         L.orc_init_fields.argtypes = [vp, vp, vp]
+        L.orc_game_derive.argtypes = [vp, ci, vp, ctypes.c_int8, vp, vp, vp]
         _ORACLE = L
     return _ORACLE
 
@@ -141,3 +142,19 @@ def gumbel_topk(state: int, logits: np.ndarray, legal: np.ndarray, noise_scaling
     legal = np.ascontiguousarray(legal, dtype=np.uint8)
     kv = oracle().orc_gumbel_topk(ctypes.byref(st), P(logits), P(legal), noise_scaling, k, P(moves), P(scores))
     return moves, scores, kv, st.value
+
+
+def game_derive(moves: np.ndarray, num_moves: np.ndarray, colors: np.ndarray, forbidden=None, want_legal: bool = True):
+    """oracle/features_oracle.c::orc_game_derive over a batch: (boards, laddered, legal | None, status)."""
+    L = oracle()
+    moves = np.ascontiguousarray(moves, dtype=np.int16)
+    n = len(moves)
+    boards = np.zeros((n, 361), dtype=np.int8)
+    lad = np.zeros((n, 361), dtype=np.int8)
+    legal = np.zeros((n, 362), dtype=np.uint8) if want_legal else None
+    status = np.zeros(n, dtype=np.int32)
+    for b in range(n):
+        fb = np.ascontiguousarray(forbidden[b], dtype=np.int8) if forbidden is not None else None
+        status[b] = L.orc_game_derive(P(moves[b]), int(num_moves[b]), P(fb) if fb is not None else None, int(colors[b]),
+                                      P(boards[b]), P(lad[b]), P(legal[b]) if want_legal else None)
+    return boards, lad, legal, status

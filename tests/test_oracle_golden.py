@@ -2,6 +2,7 @@
 reference's own sources (tests/golden/make_golden.py) — the files the GPU parity tests then trust."""
 import ctypes
 import hashlib
+import os
 
 import numpy as np
 
@@ -143,3 +144,19 @@ def test_init_fields_matches_formula():
     assert abs(out[0] - 0.4) < 1e-6
     assert abs(out[1] - float((p * s).sum())) < 1e-2
     assert abs(out[2] - float((p * s * s).sum() - (p * s).sum() ** 2)) < 1.0
+
+
+def test_oracle_game_rules_match_reference_fixture():
+    """oracle/features_oracle.c::orc_game_derive (replay, ladder reader, exact legal mask) against the compiled reference's
+    outputs for 1297 game records (tests/golden/ladder_games.npz), among them the reference's own 17 ladder test positions with
+    the values cc/game/__tests__/board_test.cc asserts."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ladder_games.npz"))
+    boards, lad, legal, status = oracle_lib.game_derive(z["moves"], z["num_moves"], z["colors"], z["forbidden"])
+    assert not status.any()
+    assert np.array_equal(boards, z["boards"])
+    assert np.array_equal(lad, z["ladder"])
+    assert np.array_equal(legal, z["legal"])
+    for t in range(int(z["n_reftest"])):
+        for i, j, c in z["reftest_expect"][t]:
+            if c != -9:
+                assert lad[t, i * 19 + j] == c, (str(z["reftest_names"][t]), i, j)

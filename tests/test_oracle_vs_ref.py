@@ -111,3 +111,29 @@ def test_symmetry_prng_softmax_gumbel_direct():
         R.ref_prob_free(p)
         om, osc, okv, _ = oracle_lib.gumbel_topk(L.orc_prng_seed(17), logits, legal, 1.0, k)
         assert kv == okv and np.array_equal(rm[:min(k, kv)], om[:min(k, kv)]) and np.array_equal(rsc[:min(k, kv)], osc[:min(k, kv)])
+
+
+def test_game_rules_on_fresh_games():
+    """orc_game_derive against Board::GetLadderedStones / Game::IsValidMove of the compiled reference on fresh games."""
+    rng = np.random.default_rng(31337)
+    recs = []
+    for _ in range(40):
+        g, color = _playout(rng, int(rng.integers(30, 320)))
+        moves = np.full(448, -1, dtype=np.int16)
+        n = R.ref_game_moves(g, P(moves), 448)
+        lad = np.zeros(361, dtype=np.int8)
+        legal = np.zeros(362, dtype=np.uint8)
+        st = np.zeros(361, dtype=np.uint8)
+        board = np.zeros(361, dtype=np.int8)
+        R.ref_game_board(g, P(board))
+        R.ref_game_laddered(g, P(lad))
+        R.ref_game_legal_mask(g, color, P(legal))
+        R.ref_game_move_status(g, color, P(st))
+        recs.append((moves, n, color, board, lad, legal, (st == 4).astype(np.int8)))
+        R.ref_game_free(g)
+    boards, lad, legal, status = oracle_lib.game_derive(np.stack([r[0] for r in recs]), np.array([r[1] for r in recs]),
+                                                        np.array([r[2] for r in recs], dtype=np.int8), np.stack([r[6] for r in recs]))
+    assert not status.any()
+    assert np.array_equal(boards, np.stack([r[3] for r in recs]))
+    assert np.array_equal(lad, np.stack([r[4] for r in recs]))
+    assert np.array_equal(legal, np.stack([r[5] for r in recs]))
