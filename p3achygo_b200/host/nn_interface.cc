@@ -114,6 +114,21 @@ NNInferResult NNInterfaceB200::LoadAndGetInferenceSym(int thread_id, const GoFea
   return r;
 }
 
+NNInferResult NNInterfaceB200::LoadAndGetInferenceGame(int thread_id, const int16_t* moves, int num_moves, int color, float komi,
+                                                       const int8_t* forbidden, int sym) {
+  if (!b200_) {
+    std::fprintf(stderr, "NNInterfaceB200::LoadAndGetInferenceGame needs a B200Engine\n");
+    std::abort();
+  }
+  b200_->LoadGameBank(thread_id / slots_per_bank_, thread_id % slots_per_bank_, moves, num_moves, color, komi, forbidden, sym);
+  SignalLoadedAndBlockUntilReady(thread_id);
+  NNInferResult r;
+  EngineGet(thread_id, r);
+  Bank& bank = BankOf(thread_id);
+  bank.thread_info[thread_id - bank.first].res_ready.store(false, std::memory_order_release);
+  return r;
+}
+
 void NNInterfaceB200::InferLoop(Bank* bank) {
   while (running_.load(std::memory_order_acquire)) Infer(*bank);
 }
@@ -279,6 +294,25 @@ int p3_host_iface_run_banks(const char* weights_path, int device, int threads, i
     });
   for (auto& t : pool) t.join();
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (n_inferences) *n_inferences = static_cast<long long>(iface.num_inferences());
+  return 0;
+}
+
+// As p3_host_iface_run_banks, with every position given as a game record (n_positions move lists of max_moves codes).
+int p3_host_iface_run_games(const char* weights_path, int device, int threads, int version, int precision, const int16_t* games,
+                            const int32_t* num_moves, const int8_t* colors, const int8_t* forbidden, int max_moves, int n_positions,
+                            int timeout_us, int banks, p3_infer_result* results, long long* n_inferences) {
+  auto engine = nn::B200Engine::Create(weights_path, threads / banks, version, device, precision);
+  nn::NNInterfaceB200 iface(threads, timeout_us, std::move(engine), banks);
+  std::vector<std::thread> pool;
+  for (int tid = 0; tid < threads; ++tid)
+    pool.emplace_back([&, tid]() {
+      for (int p = tid; p < n_positions; p += threads)
+        results[p] = iface.LoadAndGetInferenceGame(tid, games + static_cast<size_t>(p) * max_moves, num_moves[p], colors[p], 7.5f,
+                                                   forbidden ? forbidden + static_cast<size_t>(p) * 361 : nullptr, p % 8);
+      iface.UnregisterThread(tid);
+    });
+  for (auto& t : pool) t.join();
   if (n_inferences) *n_inferences = static_cast<long long>(iface.num_inferences());
   return 0;
 }

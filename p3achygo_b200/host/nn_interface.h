@@ -46,6 +46,11 @@ class NNInterfaceB200 {
   // Same with the symmetry applied / un-applied on the GPU (engine must be a B200Engine; p3_engine_load_batch_sym).
   NNInferResult LoadAndGetInferenceSym(int thread_id, const GoFeatures& features, int sym);
 
+  // NNInterface::LoadBatch from the game record itself (nn_interface.cc:245-277): the worker hands over Game::moves() (codes of
+  // p3_game_derive), colour to move, komi, optional pass-alive grid and the symmetry; the engine derives every grid on the GPU.
+  NNInferResult LoadAndGetInferenceGame(int thread_id, const int16_t* moves, int num_moves, int color, float komi,
+                                        const int8_t* forbidden, int sym);
+
   uint64_t num_inferences() const { return num_inferences_.load(std::memory_order_relaxed); }
   Engine* engine() { return engine_.get(); }
 

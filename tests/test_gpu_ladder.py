@@ -203,3 +203,75 @@ def test_engine_game_record_slots_equal_feature_slots(pipelined, games, weight_d
             pl, sc = eng.GetPlanes(b)
             assert np.array_equal(pl, want_planes[b][0]) and np.array_equal(sc, want_planes[b][1]), (half, b)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_game_derive_matches_oracle_on_fresh_games():
+    """GPU against the CPU restatement (oracle/features_oracle.c::orc_game_derive) on fresh seeded games that neither the fixture
+    nor the reference has seen: the games are played with the oracle's own exact legality (no /root/reference needed)."""
+    from oracle import oracle_lib
+    from p3achygo_b200 import engine as E
+    rng = np.random.default_rng(777001)
+    recs = []
+    for game in range(10):
+        moves = np.full(448, -1, dtype=np.int16)
+        n, color = 0, 1
+        length = int(rng.integers(60, 300))
+        while n < length:
+            _, _, legal, st = oracle_lib.game_derive(moves[None], np.array([n]), np.array([color], dtype=np.int8))
+            cand = np.flatnonzero(legal[0, :361])
+            if len(cand) == 0 or rng.random() < 0.02:
+                moves[n] = 361 + (E.MOVE_WHITE if color < 0 else 0)
+            else:
+                near = cand if n < 6 or rng.random() < 0.3 else cand[np.argsort(rng.random(len(cand)))[: max(8, len(cand) // 6)]]
+                moves[n] = int(rng.choice(near)) + (E.MOVE_WHITE if color < 0 else 0)
+            n += 1
+            color = -color
+            if n % 37 == 0 or n == length:
+                recs.append((moves.copy(), n, color))
+    mv = np.stack([r[0] for r in recs])
+    nm = np.array([r[1] for r in recs], dtype=np.int32)
+    col = np.array([r[2] for r in recs], dtype=np.int8)
+    want = oracle_lib.game_derive(mv, nm, col)
+    got = E.game_derive(mv, nm, colors=col)
+    assert not got[3].any() and not want[3].any() and len(recs) > 40
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert int((want[1] != 0).sum()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("banks", [1, 2])
+def test_interface_from_game_records(banks, games, weight_dir):
+    """NNInterfaceB200::LoadAndGetInferenceGame: 128 workers hand game records to the interface (one or two slot banks); every
+    result equals the engine's answer for the GoFeatures the reference builds for that position."""
+    import ctypes
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200._lib import INFER_RESULT_DTYPE
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    host = ctypes.CDLL(os.path.join(ROOT, "p3achygo_b200", "libp3host.so"))
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    host.p3_host_iface_run_games.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp,
+                                             ctypes.POINTER(ctypes.c_longlong)]
+    threads, n = 128, 256
+    idx = np.arange(0, n)
+    mv = np.ascontiguousarray(games["moves"][idx])
+    nm = np.ascontiguousarray(games["num_moves"][idx])
+    col = np.ascontiguousarray(games["colors"][idx])
+    fb = np.ascontiguousarray(games["forbidden"][idx])
+    results = np.zeros(n, dtype=INFER_RESULT_DTYPE)
+    ninf = ctypes.c_longlong(0)
+    host.p3_host_iface_run_games(path.encode(), 0, threads, 1, E.PRECISION_BF16, mv.ctypes.data_as(vp), nm.ctypes.data_as(vp),
+                                 col.ctypes.data_as(vp), fb.ctypes.data_as(vp), mv.shape[1], n, 400, banks,
+                                 results.ctypes.data_as(vp), ctypes.byref(ninf))
+    assert ninf.value >= n // threads
+    feats = _features_from_fixture(games, idx)
+    eng = E.CreateEngine(E.Kind.kB200, path, 64, 1, precision=E.PRECISION_BF16)
+    for lo in range(0, n, 64):
+        for s in range(64):
+            eng.LoadBatchSym(s, feats[lo + s], (lo + s) % 8)
+        eng.RunInference()
+        for s in range(64):
+            r = eng.GetBatch(s)
+            for f in r.dtype.names:
+                assert np.array_equal(np.asarray(r[f]), np.asarray(results[lo + s][f])), (lo + s, f)
+    eng.close()
