@@ -236,8 +236,9 @@ int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const 
  *                     cc/game/board.cc:595-644: occupied, pass-alive, self-capture AND positional superko,
  *   status   [n]      0 = ok, bit 0 = the move list is not a legal game, bit 1 = candidate list overflow in the reader.
  * moves [n,max_moves] int16: board point 0..360 or 361 = pass, + P3_MOVE_WHITE for a white move; entries beyond
- * num_moves[b] are ignored.  `forbidden` (optional, [n,361], non-zero = prohibited): the reference's pass-alive regions
- * (Benson, only populated after three passes, board.cc:587-590), which stay on the host as for p3_legal_mask.
+ * num_moves[b] are ignored.  The reference's pass-alive regions (GroupTracker::BensonSolver, board.cc:246-462, computed at
+ * every pass from the game's third on, board.cc:582-593, and prohibited for both colours, :607) are derived from the record
+ * as well; `forbidden` (optional, [n,361], non-zero = prohibited) adds caller-known prohibited points on top.
  * boards / laddered / legal may each be NULL (legal needs colors).  All pointers are HOST memory. */
 #define P3_MOVE_WHITE 512
 int p3_game_derive(int device, const int16_t* moves, const int32_t* num_moves, int max_moves, const int8_t* forbidden,

@@ -424,6 +424,80 @@ static int orc_solve(orc_board* board, int8_t g_color, int8_t color_to_move, int
   return result;
 }
 
+/* GroupTracker::BensonSolver::CalculatePassAliveRegionForColor, board.cc:246-462, on plain arrays: marks pass_alive[p] = color
+ * for the stones of the surviving groups and every point of the surviving small regions. */
+static void orc_benson_color(const int8_t* at, int8_t color, int8_t* pass_alive) {
+  int gid[NLOCS], rid[NLOCS], stones[NLOCS], ns, nb[4];
+  int n_groups = 0, n_regions = 0;
+  static _Thread_local uint8_t vital[NLOCS][NLOCS], adj[NLOCS][NLOCS]; /* [region][group] */
+  int g_alive[NLOCS], r_alive[NLOCS], g_vital[NLOCS];
+  for (int p = 0; p < NLOCS; ++p) gid[p] = rid[p] = -1;
+  for (int p = 0; p < NLOCS; ++p) { /* GetGroupMap (:278-296) */
+    if (at[p] != color || gid[p] >= 0) continue;
+    orc_group(at, p, stones, &ns, NULL);
+    for (int s = 0; s < ns; ++s) gid[stones[s]] = n_groups;
+    ++n_groups;
+  }
+  for (int p = 0; p < NLOCS; ++p) { /* GetRegionMap (:298-357): flood over empty / opposing points from every unseen empty point */
+    if (at[p] != 0 || rid[p] != -1) continue;
+    int stack[NLOCS], sp = 0, members[NLOCS], nm = 0, small = 1;
+    stack[sp++] = p;
+    rid[p] = -2;
+    while (sp) {
+      const int q = stack[--sp];
+      members[nm++] = q;
+      int is_liberty = at[q] != 0;
+      const int k = orc_adjacent(q, nb);
+      for (int t = 0; t < k; ++t) {
+        if (at[nb[t]] == color) {
+          if (at[q] == 0) is_liberty = 1;
+          continue;
+        }
+        if (rid[nb[t]] == -1) {
+          rid[nb[t]] = -2;
+          stack[sp++] = nb[t];
+        }
+      }
+      if (!is_liberty) small = 0;
+    }
+    for (int m = 0; m < nm; ++m) rid[members[m]] = small ? n_regions : -3; /* -3: seen, not small */
+    if (small) ++n_regions;
+  }
+  for (int r = 0; r < n_regions; ++r)
+    for (int g = 0; g < n_groups; ++g) vital[r][g] = 1, adj[r][g] = 0;
+  for (int p = 0; p < NLOCS; ++p) { /* PopulateAdjacentRegions (:359-374), PopulateVitalRegions (:376-418) */
+    if (rid[p] < 0) continue;
+    uint8_t touches[NLOCS];
+    memset(touches, 0, (size_t)n_groups);
+    const int k = orc_adjacent(p, nb);
+    for (int t = 0; t < k; ++t)
+      if (gid[nb[t]] >= 0) touches[gid[nb[t]]] = 1, adj[rid[p]][gid[nb[t]]] = 1;
+    if (at[p] == 0)
+      for (int g = 0; g < n_groups; ++g)
+        if (!touches[g]) vital[rid[p]][g] = 0;
+  }
+  for (int g = 0; g < n_groups; ++g) g_alive[g] = 1, g_vital[g] = 0;
+  for (int r = 0; r < n_regions; ++r) {
+    r_alive[r] = 1;
+    for (int g = 0; g < n_groups; ++g) g_vital[g] += vital[r][g];
+  }
+  for (int changed = 1; changed;) { /* RunBenson (:420-462) */
+    changed = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      if (!g_alive[g] || g_vital[g] >= 2) continue;
+      changed = 1;
+      g_alive[g] = 0;
+      for (int r = 0; r < n_regions; ++r) {
+        if (!r_alive[r] || !adj[r][g]) continue;
+        r_alive[r] = 0;
+        for (int v = 0; v < n_groups; ++v) g_vital[v] -= vital[r][v];
+      }
+    }
+  }
+  for (int p = 0; p < NLOCS; ++p)
+    if ((gid[p] >= 0 && g_alive[gid[p]]) || (rid[p] >= 0 && r_alive[rid[p]])) pass_alive[p] = color;
+}
+
 /* Replays `moves` (codes: point 0..360 or 361 = pass, + 512 for WHITE; Game::moves()) from the empty board and returns
  * board [361], laddered [361] (Board::GetLadderedStones, board.cc:842-899) and, when legal != NULL, Game::IsValidMove for
  * `color` over all 362 encodings (game.cc:45-51).  forbidden: pass-alive points (optional).  Returns 0, or 1 for an
@@ -433,14 +507,33 @@ int orc_game_derive(const int16_t* moves, int num_moves, const int8_t* forbidden
   orc_board* b = (orc_board*)calloc(1, sizeof(orc_board));
   orc_board* copy = (orc_board*)malloc(sizeof(orc_board));
   b->seen[b->n_seen++] = 0; /* the empty board (board.cc:505-513) */
-  int rc = 0;
+  int rc = 0, passes = 0, consecutive = 0, have_snapshot = 0;
+  int8_t snapshot[NLOCS], fb[NLOCS];
   for (int m = 0; m < num_moves && !rc; ++m) {
     const int code = moves[m], p = code & (ORC_WHITE_BIT - 1);
-    if (code < 0 || p >= NLOCS) continue; /* Board::Pass leaves seen_states_ alone (board.cc:582-593) */
+    if (code < 0) continue;
+    if (p >= NLOCS) { /* Board::Pass (board.cc:582-593): seen_states_ untouched; Benson from the third pass on unless the game ends */
+      ++passes;
+      ++consecutive;
+      if (consecutive != 2 && passes >= 3) {
+        memcpy(snapshot, b->at, NLOCS);
+        have_snapshot = 1;
+      }
+      continue;
+    }
+    consecutive = 0;
     if (b->at[p] != 0) rc = 1;
     else orc_play(b, p, (code & ORC_WHITE_BIT) ? -1 : 1, 0, NULL);
   }
   memcpy(board, b->at, NLOCS);
+  /* pass-alive points: the caller's grid and / or GroupTracker::CalculatePassAliveRegions (board.cc:223-233) at the last such pass */
+  memset(fb, 0, NLOCS);
+  if (forbidden) memcpy(fb, forbidden, NLOCS);
+  if (have_snapshot) {
+    orc_benson_color(snapshot, 1, fb);
+    orc_benson_color(snapshot, -1, fb);
+  }
+  forbidden = fb;
   if (laddered) {
     memset(laddered, 0, NLOCS);
     uint8_t visited[NLOCS];

@@ -156,6 +156,50 @@ __device__ __forceinline__ bool play(Board& b, uint64_t& hash, int point, int co
   return true;
 }
 
+// Pass-alive regions of one colour (GroupTracker::BensonSolver, cc/game/board.cc:246-462) on the board (bk, wh): the stones of
+// the surviving groups and every point (empty or opposing stone) of the surviving small regions.
+//   region  = connected set of non-`color` points (the reference's visitor walks empties and opposing stones, :318-340);
+//   small   = every EMPTY point of it touches a `color` stone (:325-343);
+//   vital to a group = every empty point of the region is a liberty of that group (:376-418);
+//   a group with fewer than two vital regions goes, together with every small region it touches (:420-462), until nothing
+//   changes.  Removal order does not matter (greatest fixed point), so groups are dropped as they are found.
+__device__ __forceinline__ uint32_t benson_color(uint32_t bk, uint32_t wh, bool black, int lane) {
+  const uint32_t mine = black ? bk : wh;
+  const uint32_t empty = ~(bk | wh) & row_mask(lane);
+  const uint32_t other = ~mine & row_mask(lane);                       // empty or opposing
+  const uint32_t lonely = empty & ~nbrs(mine, lane);                   // empty points that touch no stone of `color`
+  uint32_t regions = other & ~flood(lonely, other, lane);              // union of the small regions
+  uint32_t groups = mine;                                              // union of the surviving groups
+  while (true) {
+    bool changed = false;
+    uint32_t todo = groups;
+    while (true) {
+      const int s = first_point(todo);
+      if (s < 0) break;
+      const uint32_t g = flood(point_bit(s, lane), mine, lane);
+      todo &= ~g;
+      const uint32_t reach = nbrs(g, lane);
+      uint32_t touching = regions & reach;                             // seeds of the regions next to g
+      int vital = 0;
+      while (vital < 2) {
+        const int t = first_point(touching);
+        if (t < 0) break;
+        const uint32_t r = flood(point_bit(t, lane), regions, lane);
+        touching &= ~r;
+        if (!__any_sync(kAll, (r & empty & ~reach) != 0)) ++vital;
+      }
+      if (vital < 2) {
+        groups &= ~g;
+        const uint32_t gone = flood(regions & reach, regions, lane);
+        if (__any_sync(kAll, gone != 0)) regions &= ~gone;
+        changed = true;
+      }
+    }
+    if (!changed) break;
+  }
+  return groups | regions;
+}
+
 // ---- kernel 1: replay, atari groups, quick reject -> search tasks ------------------------------------------------------
 struct LadderTask {
   int pos, root, liberty;
@@ -181,10 +225,25 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
   const int nm = min(max(num_moves[pos], 0), max_moves);
   const int16_t* mv = moves + static_cast<size_t>(pos) * max_moves;
   const SeenSet none{nullptr, 0, nullptr, 0};
+  // Board::Pass (board.cc:582-593): from the third pass of the game on (and unless the pass ends the game) the pass-alive regions
+  // are recomputed AT THAT MOMENT and stay as they are until the next such pass - keep the board of the last one
+  int passes = 0, consecutive = 0;
+  bool have_snapshot = false;
+  Board snap{0, 0};
   for (int m = 0; m < nm; ++m) {
     const int code = mv[m];
     const int point = code & (kWhiteBit - 1);
-    if (code < 0 || point >= P3_PASS_ENCODING) continue;  // pass (or padding): Board::Pass leaves seen_states_ alone
+    if (code < 0) continue;                                // padding
+    if (point >= P3_PASS_ENCODING) {                       // Board::Pass leaves seen_states_ alone
+      ++passes;
+      ++consecutive;
+      if (consecutive != 2 && passes >= 3) {               // kNumPassesBeforeBensons, cc/constants/constants.h:75
+        snap = b;
+        have_snapshot = true;
+      }
+      continue;
+    }
+    consecutive = 0;
     const int color = (code & kWhiteBit) ? P3_WHITE : P3_BLACK;
     if (__any_sync(kAll, (point_bit(point, lane) & (b.bk | b.wh)) != 0)) {
       st = 1;  // not a legal game record
@@ -200,6 +259,8 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
     const int8_t* f = forbidden + static_cast<size_t>(pos) * P3_NUM_BOARD_LOCS + lane * P3_BOARD_LEN;
     for (int c = 0; c < P3_BOARD_LEN; ++c) fb |= f[c] ? 1u << c : 0u;
   }
+  if (have_snapshot)  // GroupTracker::CalculatePassAliveRegions (board.cc:223-233); PlayMoveDry refuses both colours there (:607)
+    fb |= benson_color(snap.bk, snap.wh, true, lane) | benson_color(snap.bk, snap.wh, false, lane);
   uint32_t* r = rows + static_cast<size_t>(pos) * 96;
   r[lane] = b.bk;
   r[32 + lane] = b.wh;

@@ -151,8 +151,8 @@ def test_oracle_game_rules_match_reference_fixture():
     outputs for 1297 game records (tests/golden/ladder_games.npz), among them the reference's own 17 ladder test positions with
     the values cc/game/__tests__/board_test.cc asserts."""
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ladder_games.npz"))
-    boards, lad, legal, status = oracle_lib.game_derive(z["moves"], z["num_moves"], z["colors"], z["forbidden"])
-    assert not status.any()
+    boards, lad, legal, status = oracle_lib.game_derive(z["moves"], z["num_moves"], z["colors"])   # pass-alive points restated too
+    assert not status.any() and int(z["forbidden"].sum()) > 300
     assert np.array_equal(boards, z["boards"])
     assert np.array_equal(lad, z["ladder"])
     assert np.array_equal(legal, z["legal"])

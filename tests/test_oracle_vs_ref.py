@@ -132,7 +132,7 @@ def test_game_rules_on_fresh_games():
         recs.append((moves, n, color, board, lad, legal, (st == 4).astype(np.int8)))
         R.ref_game_free(g)
     boards, lad, legal, status = oracle_lib.game_derive(np.stack([r[0] for r in recs]), np.array([r[1] for r in recs]),
-                                                        np.array([r[2] for r in recs], dtype=np.int8), np.stack([r[6] for r in recs]))
+                                                        np.array([r[2] for r in recs], dtype=np.int8))
     assert not status.any()
     assert np.array_equal(boards, np.stack([r[3] for r in recs]))
     assert np.array_equal(lad, np.stack([r[4] for r in recs]))
