@@ -184,6 +184,8 @@ struct p3_engine {
     int16_t* h_moves = nullptr;
     int32_t* h_nmoves = nullptr;
     int8_t* h_forbidden = nullptr;
+    int32_t* h_gstatus = nullptr;   // per-slot status of the last derivation (0 = ok), read back with the run
+    bool derived = false;
     DevBuf d_moves, d_nmoves, d_forbidden;
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
     std::atomic<int> in_flight{0};
@@ -212,6 +214,7 @@ struct p3_engine {
       if (b.h_moves) cudaFreeHost(b.h_moves);
       if (b.h_nmoves) cudaFreeHost(b.h_nmoves);
       if (b.h_forbidden) cudaFreeHost(b.h_forbidden);
+      if (b.h_gstatus) cudaFreeHost(b.h_gstatus);
       if (b.owns_host) {
         if (b.h_feats) cudaFreeHost(b.h_feats);
         if (b.h_results) cudaFreeHost(b.h_results);
@@ -291,6 +294,7 @@ struct p3_engine {
   int enqueue_game_records(Bank& bk, cudaStream_t copy_stream, cudaEvent_t copied) {
     bool any = false;
     for (int b = 0; b < batch && !any; ++b) any = bk.h_nmoves[b] >= 0;
+    bk.derived = any;
     if (!any) return P3_OK;
     int rc;
     if (!ladder_ws) {
@@ -315,8 +319,20 @@ struct p3_engine {
                         g_boards.as<int8_t>(), g_laddered.as<int8_t>(), nullptr, g_status.as<int32_t>(), stream, nullptr);
     if (rc) return rc;
     if ((rc = liberties_launch(g_boards.as<int8_t>(), batch, g_libs.as<int8_t>(), stream))) return rc;
+    P3_CUDA(cudaMemcpyAsync(bk.h_gstatus, g_status.p, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
     return assemble_features_launch(bk.d_moves.as<int16_t>(), bk.d_nmoves.as<int32_t>(), P3_MAX_GAME_MOVES, g_boards.as<int8_t>(),
                                     g_libs.as<int8_t>(), g_laddered.as<int8_t>(), batch, d_feats.as<p3_go_features>(), stream);
+  }
+
+  // after the run has completed: a slot whose move list was not a legal game record is an error (the reference CHECK-fails on
+  // impossible states); the other slots' results are valid
+  int check_game_records(Bank& bk) {
+    if (!bk.derived) return P3_OK;
+    for (int b = 0; b < batch; ++b)
+      if (bk.h_nmoves[b] >= 0 && bk.h_gstatus[b] != 0)
+        return fail(P3_ERR_INVALID_ARG, "slot " + std::to_string(b) + ": game record rejected by the replay (status " +
+                                            std::to_string(bk.h_gstatus[b]) + ": 1 = move onto an occupied point, 2 = reader overflow)");
+    return P3_OK;
   }
 
   int ensure_graph(bool to_host = false) {
@@ -477,6 +493,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_moves), sizeof(int16_t) * P3_MAX_GAME_MOVES * B));
     P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_nmoves), sizeof(int32_t) * B));
     P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_forbidden), static_cast<size_t>(361) * B));
+    P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_gstatus), sizeof(int32_t) * B));
+    std::memset(bk.h_gstatus, 0, sizeof(int32_t) * B);
     for (int b = 0; b < B; ++b) bk.h_nmoves[b] = -1;
     std::memset(bk.h_forbidden, 0, static_cast<size_t>(361) * B);
     if ((rc = bk.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
@@ -970,7 +988,7 @@ int p3_engine_run_inference(p3_engine* e) {
     cudaEventElapsedTime(&d2h, e->ev[2], e->ev[3]);
     std::fprintf(stderr, "[p3 run] h2d %.1f us  device %.1f us  d2h %.1f us\n", h2d * 1e3f, dev * 1e3f, d2h * 1e3f);
   }
-  return P3_OK;
+  return e->check_game_records(e->banks[0]);
 }
 
 int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result) {
@@ -1045,7 +1063,7 @@ int p3_engine_wait(p3_engine* e, int bank) {
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaEventSynchronize(bk.ev_d2h));
   bk.in_flight.store(0, std::memory_order_release);
-  return P3_OK;
+  return e->check_game_records(bk);
 }
 
 int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result) {

@@ -279,3 +279,57 @@ def test_interface_from_game_records(banks, games, weight_dir):
             for f in r.dtype.names:
                 assert np.array_equal(np.asarray(r[f]), np.asarray(results[lo + s][f])), (lo + s, f)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_engine_rejects_impossible_game_record(games, weight_dir):
+    """A move list that is not a legal game (a stone onto an occupied point) makes the run fail loudly, as the reference's CHECKs
+    would; valid slots of the same batch still get their results, and the engine keeps working afterwards."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    eng = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=E.PRECISION_BF16)
+    good = games["moves"][20][: games["num_moves"][20]]
+    for b in range(4):
+        eng.LoadGameBank(0, b, good, int(games["colors"][20]), 7.5)
+    eng.RunInference()
+    want = eng.GetBatch(0).copy()
+    eng.LoadGameBank(0, 2, np.array([5, 5 + E.MOVE_WHITE], dtype=np.int16), 1, 7.5)
+    with pytest.raises(E.P3Error) as ei:
+        eng.RunInference()
+    assert "slot 2" in str(ei.value)
+    got = eng.GetBatch(0)
+    assert all(np.array_equal(got[f], want[f]) for f in got.dtype.names)
+    eng.LoadGameBank(0, 2, good, int(games["colors"][20]), 7.5)
+    eng.RunInference()
+    got = eng.GetBatch(2)
+    assert all(np.array_equal(got[f], want[f]) for f in got.dtype.names)
+    with pytest.raises(E.P3Error):
+        eng.LoadGameBank(0, 0, np.zeros(2000, dtype=np.int16), 1, 7.5)     # longer than P3_MAX_GAME_MOVES
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_game_derive_is_symmetry_equivariant_at_full_size(games, known_answers):
+    """Size-independent property at 8 x 1297 = 10 376 records (more than the bench's 8192 positions): playing the same game on a
+    rotated / reflected board gives the rotated / reflected board, laddered stones and legal mask - the reference's rules have no
+    preferred direction, while the kernels' row / lane layout does."""
+    from p3achygo_b200 import engine as E
+    sym_fwd = known_answers["sym_fwd"]        # [8, 361] TransformIndex tables of the compiled reference
+    mv = games["moves"].astype(np.int32)
+    point = mv & 511
+    is_stone = (mv >= 0) & (point < 361)
+    all_moves = []
+    for s in range(8):
+        t = mv.copy()
+        t[is_stone] = sym_fwd[s][point[is_stone]] + (mv[is_stone] & 512)
+        all_moves.append(t.astype(np.int16))
+    n = len(mv)
+    boards, lad, legal, status = E.game_derive(np.concatenate(all_moves), np.tile(games["num_moves"], 8), colors=np.tile(games["colors"], 8))
+    assert not status.any()
+    for s in range(8):
+        sl = slice(s * n, (s + 1) * n)
+        for got, ref in ((boards[sl], boards[:n]), (lad[sl], lad[:n]), (legal[sl][:, :361], legal[:n][:, :361])):
+            want = np.zeros_like(ref)
+            want[:, sym_fwd[s]] = ref          # sym_grid[T(i)] = grid[i]  (cc/game/symmetry.h:42-51)
+            assert np.array_equal(got, want), s
+    assert np.array_equal(lad[:n], games["ladder"]) and np.array_equal(legal[:n], games["legal"])
