@@ -5,6 +5,7 @@
 // LoadBatch / GetBatch calls spread over `threads` host threads the way NNInterface's workers issue them
 // (cc/nn/nn_interface.cc:245-277, cc/nn/nn_interface.h:251-290).
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "b200_engine.h"
+#include "go_dataset.h"
 
 namespace {
 using Clock = std::chrono::steady_clock;
@@ -201,6 +203,58 @@ static int pipelined_cycle(const char* weights_path, int device, int batch, int 
   out[2] = t_get / steps;
   out[3] = t_wait / steps;
   out[4] = checksum;
+  return 0;
+}
+
+// nn::Benchmark(engine, go_ds, stats) with nn::DefaultStats (cc/nn/engine/benchmark_engine.cc:24-109): warm-up runs, then per
+// dataset batch LoadBatch x B -> RunInference (timed) -> GetBatch x B, accumulating the reference's accuracy statistics.
+//   out[0] num_examples  out[1] avg_us  out[2] policy_loss  out[3] outcome_loss  out[4] policy_percent  out[5] outcome_percent
+//   out[6] score_diff
+int p3_host_benchmark_dataset(const char* weights_path, int device, int batch, int version, int precision, const char* ds_path,
+                              int warmup, double* out) {
+  auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
+  nn::GoDataset ds(static_cast<size_t>(batch), ds_path);
+  for (int i = 0; i < warmup; ++i) engine->RunInference();  // "Warming Up...", :79-82
+  auto argmax = [](const float* v, int n) {
+    int best = 0;
+    for (int i = 1; i < n; ++i)
+      if (v[i] > v[best]) best = i;
+    return best;
+  };
+  auto avg = [](double a, double x, double cnt) { return ((cnt - 1) / cnt) * a + (1 / cnt) * x; };
+  double cnt = 0, avg_us = 0, policy_loss = 0, outcome_loss = 0, policy_percent = 0, outcome_percent = 0, score_diff = 0;
+  constexpr double kMaxLoss = 16;
+  int num_inferences = 0;
+  nn::NNInferResult result;
+  size_t remaining = ds.num_examples();
+  for (auto& rows : ds) {
+    if (num_inferences > 1000) break;  // :88-90
+    for (size_t b = 0; b < rows.size(); ++b) engine->LoadBatch(static_cast<int>(b), rows[b].features);
+    auto t0 = Clock::now();
+    engine->RunInference();
+    const double elapsed_us = static_cast<double>(static_cast<long long>(us_since(t0)));  // duration_cast<microseconds>, :96-99
+    for (size_t b = 0; b < rows.size() && remaining > 0; ++b, --remaining) {  // (the reference also scores the padding rows of the last batch)
+      engine->GetBatch(static_cast<int>(b), result);
+      const nn::GoDataset::Row& row = rows[b];
+      const int mv_pred = argmax(result.move_probs, P3_MAX_MOVES);
+      const int outcome_pred = argmax(result.value_probs, P3_NUM_VALUE_LOGITS);
+      const int score_pred = static_cast<int>(argmax(result.score_probs, P3_NUM_SCORE_LOGITS) + 0.5 - 400);  // kScoreInflectionPoint
+      const int mv = argmax(row.labels.policy.data(), P3_MAX_MOVES);
+      const int won = row.labels.did_win ? 1 : 0;
+      const float pi_ce = result.move_probs[mv] != 0.0f ? -std::log(result.move_probs[mv]) : static_cast<float>(kMaxLoss);
+      const float v_ce = result.value_probs[won] != 0.0f ? -std::log(result.value_probs[won]) : static_cast<float>(kMaxLoss);
+      cnt += 1;
+      avg_us = avg(avg_us, elapsed_us, cnt);
+      policy_loss = avg(policy_loss, pi_ce, cnt);
+      outcome_loss = avg(outcome_loss, v_ce, cnt);
+      policy_percent = avg(policy_percent, mv == mv_pred ? 1 : 0, cnt);
+      outcome_percent = avg(outcome_percent, won == outcome_pred ? 1 : 0, cnt);
+      score_diff = avg(score_diff, std::abs(row.labels.score_margin - score_pred), cnt);
+    }
+    ++num_inferences;
+  }
+  out[0] = cnt, out[1] = avg_us, out[2] = policy_loss, out[3] = outcome_loss, out[4] = policy_percent, out[5] = outcome_percent;
+  out[6] = score_diff;
   return 0;
 }
 

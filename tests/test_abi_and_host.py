@@ -44,7 +44,8 @@ def test_struct_layouts_mirror_reference():
 def test_host_library_loads():
     host = ctypes.CDLL(os.path.join(ROOT, "p3achygo_b200", "libp3host.so"))
     for sym in ("p3_host_benchmark", "p3_host_benchmark_pipelined", "p3_host_benchmark_games", "p3_host_iface_sync_test", "p3_host_iface_run",
-                "p3_host_iface_run_banks", "p3_host_iface_run_games"):
+                "p3_host_iface_run_banks", "p3_host_iface_run_games", "p3_host_dataset_read", "p3_host_benchmark_dataset",
+                "p3_host_tfrecord_frame"):
         assert hasattr(host, sym), sym
 
 
