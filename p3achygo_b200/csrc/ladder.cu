@@ -279,10 +279,14 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
   if (!tasks) return;
   // groups in atari (board.cc:874-882) that survive the quick reject (board.cc:857-860)
   const uint32_t empty = ~(b.bk | b.wh) & row_mask(lane);
-  // only groups next to an empty point with at most 2 empty neighbours can be laddered candidates; enumerate the
-  // groups touching any empty point's neighbourhood instead of all groups: every group has a liberty, so that is all of
-  // them - but visit each once
-  uint32_t todo = b.bk | b.wh;
+  // a group holding a stone with two empty neighbours of its own is not in atari: drop those groups wholesale (one multi-seed
+  // flood per colour) and look at the few that remain one by one
+  uint32_t eu = __shfl_up_sync(kAll, empty, 1), ed = __shfl_down_sync(kAll, empty, 1);
+  if (lane == 0) eu = 0;
+  if (lane == 31) ed = 0;
+  const uint32_t el = empty << 1, er = empty >> 1;
+  const uint32_t two = (el & er) | (el & eu) | (el & ed) | (er & eu) | (er & ed) | (eu & ed);
+  uint32_t todo = (b.bk & ~flood(two & b.bk, b.bk, lane)) | (b.wh & ~flood(two & b.wh, b.wh, lane));
   while (true) {
     const int s = first_point(todo);
     if (s < 0) break;
