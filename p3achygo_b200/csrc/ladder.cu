@@ -476,7 +476,14 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
     if (lane == 0) idx = atomicAdd(&q->head, 1);
     idx = __shfl_sync(kAll, idx, 0);
     bool have = false;
-    while (true) {
+    for (long long polls = 0;; ++polls) {
+      if (polls > (1ll << 25)) {  // ~10 s of polling: something is wrong; leave instead of hanging the device
+        if (lane == 0) {
+          atomicOr(&q->full, 1 << 30);
+          atomicOr(&status[0], 8);  // reported on the batch's first position: the whole batch's reader output is incomplete
+        }
+        break;
+      }
       int r = 0, out = 1;
       if (lane == 0) {
         r = idx < item_cap ? v_ready[idx] : 0;
