@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
 // 31 = n_cand | next << 8; [2] the rows of the hunted group at this node (it only grows along a path, so the flood
 // after a move starts from it and converges in a step or two).  A node's kind needs no storage: the defender moves at
 // even call depths, so frame d is an AND node iff d is odd.
-constexpr int kSmemFrames = 40;
+constexpr int kSmemFrames = 16;
 constexpr int kHistSmem = 608;
 constexpr int kReaderWarps = 4;
 constexpr int kFrameWords = 96;
@@ -840,7 +840,8 @@ int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, dev);
-  w->blocks = w->sms * 2;                                  // 8 resident warps per SM, each with its own frame stack in shared memory
+  w->blocks = w->sms * 2;                                  // 8 resident warps per SM (measured: 2, 3, 4 blocks per SM are equal - the split chain's latency bounds the reader)
+  if (const char* bl = std::getenv("P3_LADDER_BLOCKS_PER_SM")) w->blocks = w->sms * std::max(1, std::atoi(bl));
   const int max_tasks = n * (P3_NUM_BOARD_LOCS / 2);       // groups in atari per position
   w->item_cap = max_tasks + (1 << 17);
   w->node_cap = max_tasks + (1 << 19);
