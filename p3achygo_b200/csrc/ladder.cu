@@ -317,7 +317,7 @@ constexpr int kHistSmem = 608;
 constexpr int kReaderWarps = 4;
 constexpr int kFrameWords = 96;
 constexpr int kMaxCandPacked = 26;
-constexpr size_t kWarpSmemBytes = kHistSmem * 8 + kMaxDepth * 8 + kSmemFrames * kFrameWords * 4 + (kMaxDepth + 3) * 2;
+constexpr size_t kWarpSmemBytes = kHistSmem * 8 + (kMaxDepth + 1) * 8 + kSmemFrames * kFrameWords * 4;
 static_assert(kWarpSmemBytes % 8 == 0, "per-warp shared memory slices stay 8-byte aligned");
 static_assert(kMaxCandPacked <= kMaxCand, "candidate capacity");
 
@@ -368,15 +368,17 @@ __device__ __forceinline__ bool play_checked(Board& b, uint64_t& hash, int point
   return true;
 }
 
-// A long search is split among warps.  Work items are sub-searches: "the value of Solve() entered with this move after
-// this path from the search root".  A warp runs an item as a plain depth-first search; when the item has cost kSplitNodes
+// A long search is split among warps.  Work items are sub-searches: "the value of Solve() entered with this move from this
+// position" (the position - rows, hunted group, hashes of the path to it - travels in a state pool; replaying the path instead
+// cost more than the searching).  A warp runs an item as a plain depth-first search; when the item has cost kSplitNodes
 // nodes it stops, turns its live stack into nodes of an AND/OR tree (one per frame; the untried sibling moves of every
-// frame become new items, replayed from the root by whichever warp picks them up) and goes back to the queue.  A finished
+// frame become new items for whichever warp picks them up) and goes back to the queue.  A finished
 // item reports its value to its parent node: a deciding value (false under AND, true under OR) settles the parent at once,
 // otherwise the parent's pending count drops and the last child settles it with the neutral value; settled nodes report
 // upwards, a settled root writes the task's answer.  Items whose ancestors are already settled are dropped unrun.  Every
 // sub-search is a pure function of (position, path), so the answer is the sequential one; only the order differs.
-constexpr int kSplitNodesDefault = 16;   // measured: 10.6 ms unsplit, 2.2 ms at 96, 1.4 ms at 32, 0.98 ms at 16 (1024 random-playout positions)
+constexpr int kSplitNodesDefault = 6;   // measured (1024 random-playout positions): unsplit 10.6 ms; items replaying their path: 0.98 ms at 16;
+                                       // items carrying their position: 0.98 ms at 32, 0.53 at 16, 0.40 at 8, 0.37 at 6, 0.41 at 4, 0.61 at 2
 constexpr unsigned kDecided = 0x80000000u, kValTrue = 0x40000000u, kIsAnd = 0x20000000u, kPendMask = 0xFFFFu;
 
 struct TreeNode {
@@ -385,9 +387,12 @@ struct TreeNode {
 };
 
 struct Item {
-  int task, node, n_moves;
-  int moves_at;      // offset into the move pool: moves[0..n_moves-2] the path from the search root (known legal), moves[n_moves-1] the move to enter
+  int task, node;
+  int base_move;     // call depth of the move to enter | move << 16
+  int state_at;      // offset (in 8-byte words) of the position to enter it from in the state pool, -1 = the task's root position:
+                     //   [base] hashes of the path's positions, then 48 words = the frame's 96 row words (black, white, hunted group)
 };
+constexpr int kStateWords = 48;
 
 struct Queue {
   int n_tasks;       // written by replay_kernel (atomic counter)
@@ -398,18 +403,16 @@ struct Queue {
   int dropped;       // items skipped because an ancestor was settled
   int splits;        // successful splits
   int full;          // splits refused for lack of room (the item then just keeps searching)
-  int pool_used;     // int16 entries of the move pool handed out
+  int pool_used;     // 8-byte words of the state pool handed out
   int pad;
   long long nodes;   // Solve() activations over all items
 };
 
-__global__ void seed_items_kernel(const LadderTask* __restrict__ tasks, Queue* q, TreeNode* nodes, Item* items, int16_t* pool,
-                                  int* ready) {
+__global__ void seed_items_kernel(const LadderTask* __restrict__ tasks, Queue* q, TreeNode* nodes, Item* items, int* ready) {
   const int n = q->n_tasks;   // <= the capacities by construction (ladder_run sizes them from the batch)
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     nodes[t] = TreeNode{-1, 0u};
-    items[t] = Item{t, t, 1, t};
-    pool[t] = static_cast<int16_t>(tasks[t].liberty);
+    items[t] = Item{t, t, tasks[t].liberty << 16, -1};
     __threadfence();
     ready[t] = 1;
   }
@@ -417,7 +420,7 @@ __global__ void seed_items_kernel(const LadderTask* __restrict__ tasks, Queue* q
     q->tail = n;
     q->outstanding = n;
     q->n_nodes = n;
-    q->pool_used = n;
+    q->pool_used = 0;
   }
 }
 
@@ -451,7 +454,7 @@ __device__ __forceinline__ bool report_up(TreeNode* nodes, int parent, bool v, b
 }
 
 __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderTask* __restrict__ tasks, Queue* q, TreeNode* nodes,
-                                                                   int node_cap, Item* items, int16_t* pool, int pool_cap,
+                                                                   int node_cap, Item* items, uint64_t* pool, int pool_cap,
                                                                    int* ready, int item_cap,
                                                                    const uint32_t* __restrict__ rows, const uint64_t* __restrict__ hist,
                                                                    const int32_t* __restrict__ n_hist, int max_moves,
@@ -463,8 +466,7 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
   unsigned char* base_ptr = smem_raw + wib * kWarpSmemBytes;
   uint64_t* hist_s = reinterpret_cast<uint64_t*>(base_ptr);
   uint64_t* path_s = hist_s + kHistSmem;
-  uint32_t* frames_s = reinterpret_cast<uint32_t*>(path_s + kMaxDepth);
-  int16_t* pmove = reinterpret_cast<int16_t*>(frames_s + kSmemFrames * kFrameWords);   // move entered at each call depth
+  uint32_t* frames_s = reinterpret_cast<uint32_t*>(path_s + kMaxDepth + 1);
   DeepFrames& D = deep[warp];
   auto frame = [&](int d) -> uint32_t* { return d < kSmemFrames ? frames_s + d * kFrameWords : D.w[d - kSmemFrames]; };
   volatile int* v_ready = ready;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
     if (!have) break;
     __threadfence();
     const Item it = items[idx];
-    const int task_id = it.task, node_id = it.node, n_moves = it.n_moves;
+    const int task_id = it.task, node_id = it.node, base = it.base_move & 0xFFFF, first_move = it.base_move >> 16;
     if (task_id < 0) {  // a reserved slot that was given back
       if (lane == 0) atomicSub(&q->outstanding, 1);
       continue;
@@ -535,7 +537,8 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
     const int nh_s = min(nh, kHistSmem);
     __syncwarp();
     for (int i = lane; i < nh_s; i += 32) hist_s[i] = my_hist[i];
-    for (int i = lane; i < n_moves; i += 32) pmove[i] = pool[it.moves_at + i];
+    if (it.state_at >= 0)
+      for (int i = lane; i < base; i += 32) path_s[i] = pool[it.state_at + i];
     __syncwarp();
     const uint32_t rootbit = point_bit(task.root, lane);
     const int g_color = __any_sync(kAll, (rootbit & root_board.bk) != 0) ? P3_BLACK : P3_WHITE;
@@ -554,19 +557,17 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
         if (__any_sync(kAll, (nbrs(mbit, lane) & own & ~grp) != 0)) grp = flood(grp, own, lane);  // ... and brings others along
       }
     };
-    // ---- replay the path to this item's position (moves at call depths 0 .. base-1, all legal when they were searched)
-    const int base = n_moves - 1;
-    for (int j = 0; j < base; ++j) {
-      const int mv = pmove[j];
-      const int who = (j & 1) ? -g_color : g_color;   // Solve(..., liberty, 0) is the defender's move (board.cc:863-866)
-      if (!play_checked(b, hash, mv, who, fb, hist_s, nh_s, my_hist, nh, path_s, j, lane)) bad = true;
-      if (who == g_color) grow(mv);
-      if (lane == 0) path_s[j] = hash;
-      __syncwarp();
+    // ---- the position this item starts from: the task's root, or the frame state its parent item left in the pool
+    if (it.state_at >= 0) {
+      const uint32_t* st = reinterpret_cast<const uint32_t*>(pool + it.state_at + base);
+      b.bk = lane < P3_BOARD_LEN ? st[lane] : 0u;
+      b.wh = lane < P3_BOARD_LEN ? st[32 + lane] : 0u;
+      grp = st[64 + lane];
+      hash = path_s[base - 1];
     }
     int top = base - 1;      // index of the frame whose children are being tried; the call being entered has call_depth top + 1
-    int move = pmove[base];
-    int mover = (base & 1) ? -g_color : g_color;
+    int move = first_move;
+    int mover = (base & 1) ? -g_color : g_color;   // Solve(..., liberty, 0) is the defender's move (board.cc:863-866)
     bool value = false;
     bool overflow = false, split_done = false, may_split = true;
     int nodes_here = 0;
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
         for (int j = base; j <= top; ++j) {
           const uint32_t meta = frame(j)[32 + 31];
           const int n_cand = meta & 0xFF, next = static_cast<int>(meta >> 8);
-          n_pool += (j < top ? n_cand - next - 1 : n_cand - next) * (j + 2);
+          if ((j < top ? n_cand - next - 1 : n_cand - next) > 0) n_pool += j + 1 + kStateWords;   // one state per frame, shared by its siblings
         }
         int node0 = 0, item0 = 0, pool0 = 0, ok = 0;
         if (lane == 0) {
@@ -628,19 +629,24 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
               if (j > base) nodes[my_node].parent = j - 1 == base ? node_id : my_node - 1;
               atomicExch(&nodes[my_node].state, ((j & 1) ? kIsAnd : 0u) | static_cast<unsigned>(pending));
             }
+            if (first < n_cand) {  // the position of frame j (after the move at call depth j) + the hashes of the path to it
+              for (int i = lane; i <= j; i += 32) pool[at + i] = path_s[i];
+              uint32_t* st = reinterpret_cast<uint32_t*>(pool + at + j + 1);
+              st[lane] = f[lane];
+              st[32 + lane] = f[32 + lane];
+              st[64 + lane] = f[64 + lane];
+            }
             for (int c = first; c < n_cand; ++c) {
               const uint32_t packed = f[19 + (c >> 1)];
               const int mv = (packed >> ((c & 1) * 16)) & 0xFFFF;
-              for (int i = lane; i <= j; i += 32) pool[at + i] = pmove[i];
               if (lane == 0) {
-                pool[at + j + 1] = static_cast<int16_t>(mv);
-                items[slot] = Item{task_id, leaf, j + 2, at};
+                items[slot] = Item{task_id, leaf, (j + 1) | (mv << 16), at};
                 nodes[leaf] = TreeNode{my_node, 0u};
               }
-              at += j + 2;
               ++leaf;
               ++slot;
             }
+            if (first < n_cand) at += j + 1 + kStateWords;
           }
           __threadfence();
           __syncwarp();
@@ -717,10 +723,7 @@ __global__ void __launch_bounds__(kReaderWarps * 32) ladder_kernel(const LadderT
           f[lane] = lane < P3_BOARD_LEN ? b.bk : cand_reg;
           f[32 + lane] = lane == 31 ? static_cast<uint32_t>(nc) : b.wh;   // next = 0
           f[64 + lane] = grp;
-          if (lane == 0) {
-            path_s[depth] = hash;
-            pmove[depth] = static_cast<int16_t>(move);
-          }
+          if (lane == 0) path_s[depth] = hash;
           __syncwarp();
           top = depth;
           mover = to_move;
@@ -822,7 +825,7 @@ struct LadderWorkspace {
   Queue* queue = nullptr;
   TreeNode* nodes = nullptr;
   Item* items = nullptr;
-  int16_t* pool = nullptr;
+  uint64_t* pool = nullptr;
   int* ready = nullptr;
   DeepFrames* scratch = nullptr;
 };
@@ -845,7 +848,7 @@ int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out) {
   const int max_tasks = n * (P3_NUM_BOARD_LOCS / 2);       // groups in atari per position
   w->item_cap = max_tasks + (1 << 17);
   w->node_cap = max_tasks + (1 << 19);
-  w->pool_cap = max_tasks + (1 << 24);
+  w->pool_cap = 1 << 23;                                   // 64 MB of sub-search states
   if (const char* sn = std::getenv("P3_LADDER_SPLIT")) w->split_nodes = std::max(1, std::atoi(sn));
 #define P3_TRY(call)                                                                                     \
   do {                                                                                                   \
@@ -862,7 +865,7 @@ int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out) {
   P3_TRY(cudaMalloc(&w->tasks, static_cast<size_t>(max_tasks) * sizeof(LadderTask)));
   P3_TRY(cudaMalloc(&w->nodes, static_cast<size_t>(w->node_cap) * sizeof(TreeNode)));
   P3_TRY(cudaMalloc(&w->items, static_cast<size_t>(w->item_cap) * sizeof(Item)));
-  P3_TRY(cudaMalloc(&w->pool, static_cast<size_t>(w->pool_cap) * sizeof(int16_t)));
+  P3_TRY(cudaMalloc(&w->pool, static_cast<size_t>(w->pool_cap) * sizeof(uint64_t)));
   P3_TRY(cudaMalloc(&w->ready, static_cast<size_t>(w->item_cap) * sizeof(int)));
   P3_TRY(cudaMalloc(&w->scratch, static_cast<size_t>(w->blocks) * kReaderWarps * sizeof(DeepFrames)));
   P3_TRY(cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kReaderWarps * kWarpSmemBytes)));
@@ -886,7 +889,7 @@ int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_
   P3_CUDA(cudaGetLastError());
   if (ev) cudaEventRecord(ev[1], stream);
   if (want_ladder) {
-    seed_items_kernel<<<w->sms, 256, 0, stream>>>(w->tasks, w->queue, w->nodes, w->items, w->pool, w->ready);
+    seed_items_kernel<<<w->sms, 256, 0, stream>>>(w->tasks, w->queue, w->nodes, w->items, w->ready);
     P3_CUDA(cudaGetLastError());
     ladder_kernel<<<w->blocks, kReaderWarps * 32, kReaderWarps * kWarpSmemBytes, stream>>>(
         w->tasks, w->queue, w->nodes, w->node_cap, w->items, w->pool, w->pool_cap, w->ready, w->item_cap, w->rows, w->hist, w->n_hist,
