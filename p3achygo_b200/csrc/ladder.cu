@@ -134,13 +134,15 @@ __device__ __forceinline__ bool play(Board& b, uint64_t& hash, int point, int co
   uint32_t opp = black ? b.wh : b.bk;
   uint32_t empty = ~(own | opp) & row_mask(lane);
   uint32_t captured = 0;
-  const uint32_t seeds = nbrs(bit, lane) & opp;
+  bool any_capture = false;
+  const uint32_t near_empty = nbrs(empty, lane);                            // points with an empty neighbour
+  const uint32_t seeds = nbrs(bit, lane) & opp & ~near_empty;               // adjacent opposing stones without a liberty of their own
   if (__any_sync(kAll, seeds != 0)) {
-    const uint32_t touched = flood(seeds, opp, lane);                      // the adjacent opposing groups
-    const uint32_t alive = flood(nbrs(empty, lane) & touched, touched, lane);  // ... that still reach an empty point
+    const uint32_t touched = flood(seeds, opp, lane);                       // their groups
+    const uint32_t alive = flood(near_empty & touched, touched, lane);      // ... that still reach an empty point
     captured = touched & ~alive;
+    any_capture = __any_sync(kAll, captured != 0);
   }
-  const bool any_capture = __any_sync(kAll, captured != 0);
   if (any_capture) {
     opp &= ~captured;
   } else if (check) {  // IsSelfCapture, board.cc:901-915
@@ -230,8 +232,10 @@ __global__ void __launch_bounds__(128) replay_kernel(const int16_t* __restrict__
   int passes = 0, consecutive = 0;
   bool have_snapshot = false;
   Board snap{0, 0};
+  int chunk = 0;
   for (int m = 0; m < nm; ++m) {
-    const int code = mv[m];
+    if ((m & 31) == 0) chunk = m + lane < nm ? mv[m + lane] : -1;   // 32 moves per global load instead of one dependent load per move
+    const int code = __shfl_sync(kAll, chunk, m & 31);
     const int point = code & (kWhiteBit - 1);
     if (code < 0) continue;                                // padding
     if (point >= P3_PASS_ENCODING) {                       // Board::Pass leaves seen_states_ alone
