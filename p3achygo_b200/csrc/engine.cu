@@ -1120,8 +1120,10 @@ int p3_engine_upload(p3_engine* e) {
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_sym.p, e->h_sym, e->batch, cudaMemcpyHostToDevice, e->stream));
+  int rc = e->enqueue_game_records(e->banks[0], e->stream, nullptr);   // slots loaded as game records: derive their features now
+  if (rc) return rc;
   P3_CUDA(cudaStreamSynchronize(e->stream));
-  return P3_OK;
+  return e->check_game_records(e->banks[0]);
 }
 
 int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
