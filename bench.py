@@ -13,7 +13,11 @@ A "step" is one pass of the hot path over one batch of 1024 synthetic positions 
           e2e.value uses the engine's two slot banks (LoadBatchBank x B -> Submit | Wait -> GetBatchBank x B, one bank's host
           phases and copies overlapping the other's kernels); e2e.serial is the reference's un-overlapped cycle
           LoadBatch x B -> RunInference -> GetBatch x B.
-Prints ONE JSON line on rank 0.
+  e2e_from_game_records : the slot-bank cycle with the slots loaded as move lists (rules derived on the GPU inside the step).
+  sustained : 150 back-to-back device steps with the NVML clocks of that interval (the board power limit shows here).
+  game_records (rank 0) : p3_game_derive stand-alone on 1024 fixture records, checked against the reference fixture, with the
+          compiled reference timed on the same records when oracle/_ref is present.
+Prints ONE JSON line on rank 0 (stdout carries nothing else).
 """
 from __future__ import annotations
 
