@@ -333,3 +333,30 @@ def test_game_derive_is_symmetry_equivariant_at_full_size(games, known_answers):
             want[:, sym_fwd[s]] = ref          # sym_grid[T(i)] = grid[i]  (cc/game/symmetry.h:42-51)
             assert np.array_equal(got, want), s
     assert np.array_equal(lad[:n], games["ladder"]) and np.array_equal(legal[:n], games["legal"])
+
+
+@pytest.mark.gpu
+def test_root_sampling_from_game_records(games):
+    """The root's candidate moves end to end on the GPU: game record -> exact legal mask (p3_game_derive) -> Gumbel top-k
+    (p3_gumbel_topk, cc/mcts/gumbel.cc:283-321), against the oracle fed with the reference's own Game::IsValidMove mask
+    (superko-illegal and pass-alive points are not drawn for, which shifts every later PRNG draw if a mask bit is wrong)."""
+    from oracle import oracle_lib
+    from p3achygo_b200 import engine as E
+    idx = np.concatenate([np.arange(1217, 1297), np.arange(200, 248)])      # the ko positions + playouts
+    rng = np.random.default_rng(12)
+    logits = (rng.standard_normal((len(idx), 362)) * 2.0).astype(np.float32)
+    _, _, legal, status = E.game_derive(games["moves"][idx], games["num_moves"][idx], colors=games["colors"][idx], want_ladder=False)
+    assert not status.any() and np.array_equal(legal, games["legal"][idx])
+    L = oracle_lib.oracle()
+    seeds = [L.orc_prng_seed(1000 + 17 * i) for i in range(len(idx))]
+    state = np.array(seeds, dtype=np.uint64)
+    k = 16
+    moves, scores, kvalid = E.gumbel_topk(logits, legal, state, 1.0, k)
+    same = 0
+    for i in range(len(idx)):
+        om, osc, okv, ost = oracle_lib.gumbel_topk(int(seeds[i]), logits[i], games["legal"][idx[i]], 1.0, k)
+        kk = min(k, okv)
+        assert kvalid[i] == okv and int(state[i]) == ost                      # same number of draws
+        np.testing.assert_allclose(scores[i][:kk], osc[:kk], rtol=0, atol=4e-6 * max(1.0, float(np.abs(osc[:kk]).max())))
+        same += int(np.array_equal(moves[i][:kk], om[:kk]))
+    assert same >= len(idx) - 1
