@@ -330,7 +330,9 @@ def main():
     dom_name = "tc_conv3x3_pair_kernel (3x3 layers)" if prof["conv3x3"][1] > 0 else "1x1 layers"
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
     traffic, traffic_src, ncu_share, ncu_tensor = None, None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v13.json")
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v17.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_v13.json")
     if os.path.exists(tpath) and args.config == CONFIG and B == BATCH and prof["conv3x3"][1] > 0:
         with open(tpath) as f:
             tj = json.load(f)

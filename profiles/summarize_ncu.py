@@ -48,11 +48,33 @@ def launch_shares(path):
     return {k: {"launches": n, "sum_us": v, "share": v / tot} for k, (n, v) in agg.items()}, tot, len(data)
 
 
+TO_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+TO_MB = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: a .ncu-rep, or the `ncu -i rep --page raw --csv` text saved on the GPU box (a full capture of a whole step with
+    sources is larger than gpurun brings back).  Times are normalised to us, DRAM bytes to MB (the raw page picks its own units)."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[0]
-    return [{k: r[hdr.index(k)] for k in KEYS if k in hdr} for r in rows[2:]]
+    hdr, units = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = {}
+        for k in KEYS:
+            if k not in hdr:
+                continue
+            v, u = r[hdr.index(k)], units[hdr.index(k)]
+            if k == "gpu__time_duration.sum":
+                v = str(float(v.replace(",", "")) * TO_US.get(u, 1.0))
+            elif k.startswith("dram__bytes"):
+                v = str(float(v.replace(",", "")) * TO_MB.get(u, 1.0))
+            d[k] = v
+        res.append(d)
+    return res
 
 
 def main():
