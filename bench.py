@@ -44,7 +44,7 @@ D2H_PER_POS = 7568   # sizeof(NNInferResult)
 
 
 def load_positions():
-    from p3achygo_b200._lib import GO_FEATURES_DTYPE
+    from p3achygo_b200.layout import GO_FEATURES_DTYPE
     z = np.load(os.path.join(ROOT, "tests", "golden", "bench_positions.npz"))
     return np.ascontiguousarray(z["feats"]).view(GO_FEATURES_DTYPE).reshape(-1)
 

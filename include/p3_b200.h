@@ -114,6 +114,19 @@ typedef struct p3_aux_result {
   float score_var;                        /* E[s^2] - E[s]^2 */
 } p3_aux_result;
 
+/* What mcts::LeafEvaluator's InitFields keeps of an NNInferResult (cc/mcts/leaf_evaluator.cc:83-112): the three policy
+ * arrays it copies into the TreeNode (:85-90) and the four scalars it derives (:92-108).  4360 bytes instead of 7568: the
+ * 800 score_probs the TensorRT engine ships per leaf (cc/nn/engine/trt_engine.cc:281-298) stay on the GPU. */
+typedef struct p3_leaf_result {
+  float move_logits[P3_MAX_MOVES];     /* TreeNode::move_logits */
+  float move_probs[P3_MAX_MOVES];      /* TreeNode::move_probs */
+  float opt_move_probs[P3_MAX_MOVES];  /* TreeNode::opt_probs */
+  float value;                         /* init_outcome_est = p[1] - p[0] */
+  float score_mean;                    /* init_score_est   = sum p_i (i - 400 + .5) */
+  float score_var;                     /* init_score_var   = E[s^2] - E[s]^2 */
+  float err;                           /* init_err_est     = sqrt(err2_outcome) */
+} p3_leaf_result;
+
 typedef struct p3_engine p3_engine;
 
 /* ---- engine lifecycle: nn::CreateEngine, cc/nn/engine/engine_factory.cc:56-73 ------------ */
@@ -178,6 +191,21 @@ int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_resu
 int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi,
                              const int8_t* forbidden, int sym);
 
+/* ---- compact leaf results -------------------------------------------------------------------------
+ * P3_RESULT_LEAF: runs copy back one p3_leaf_result per slot (4360 B) instead of one NNInferResult (7568 B); read them with
+ * p3_engine_get_leaf / p3_engine_get_leaf_bank.  p3_engine_get_batch* fail with P3_ERR_INVALID_ARG in this mode (their
+ * host copy is not refreshed).  The mode applies to runs started after the call; do not switch with a bank in flight. */
+enum { P3_RESULT_FULL = 0, P3_RESULT_LEAF = 1 };
+int p3_engine_set_result_mode(p3_engine* e, int mode);
+int p3_engine_get_leaf(p3_engine* e, int batch_id, p3_leaf_result* leaf);                 /* after p3_engine_run_inference */
+int p3_engine_get_leaf_bank(p3_engine* e, int bank, int batch_id, p3_leaf_result* leaf);  /* after p3_engine_wait(bank) */
+
+/* Gumbel root sampling (cc/mcts/gumbel.cc:283-321, see p3_gumbel_topk below) straight from the results of `bank`'s last
+ * completed run, which are still in HBM: root i samples from move_logits of slot slots[i]; only the legal masks
+ * (legal [n,362], HOST; Game::IsValidMove as the caller knows it), the PRNG states and the k winners cross PCIe. */
+int p3_engine_gumbel_topk_bank(p3_engine* e, int bank, const int32_t* slots, int n, const uint8_t* legal, uint64_t* prng_state,
+                               float noise_scaling, int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid);
+
 /* nn::Engine::kind()/path(), cc/nn/engine/engine.h:33-34. */
 const char* p3_engine_path(const p3_engine* e);
 int p3_engine_batch_size(const p3_engine* e);
@@ -187,8 +215,13 @@ int p3_engine_batch_size(const p3_engine* e);
 /* The feature planes the encode kernel produced for `batch_id` in the last run, in the reference's
  * host layout: planes NHWC float[19*19*C] and scalars float[S] (cc/nn/engine/go_features.cc:10-68). */
 int p3_engine_get_planes(p3_engine* e, int batch_id, float* planes, float* scalars);
-/* The non-consumed model outputs + leaf statistics for `batch_id` of the last run. */
+/* The non-consumed model outputs + leaf statistics for `batch_id` of the last SERIAL run (p3_engine_run_inference /
+ * p3_engine_run_device); like p3_engine_get_ownership it reads the step's own buffer, which the next run of either bank
+ * overwrites.  After p3_engine_submit use the _bank forms: each bank keeps its own copy, valid from p3_engine_wait(bank)
+ * until that bank's next submit.  Ownership comes back in the game's orientation (symmetry un-applied, like the policies). */
 int p3_engine_get_aux(p3_engine* e, int batch_id, p3_aux_result* aux);
+int p3_engine_get_aux_bank(p3_engine* e, int bank, int batch_id, p3_aux_result* aux);
+int p3_engine_get_ownership_bank(p3_engine* e, int bank, int batch_id, float own[P3_NUM_BOARD_LOCS]);
 /* Run encode -> tower -> heads on the game state already resident in HBM (last H2D), without any
  * host<->device copy; returns device time in ms measured with CUDA events on the engine's stream. */
 int p3_engine_run_device(p3_engine* e, float* ms_total);
@@ -201,6 +234,12 @@ int p3_engine_upload(p3_engine* e);
 #define P3_NUM_KERNEL_CLASSES 7
 int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
                       double flops[P3_NUM_KERNEL_CLASSES]);
+/* Dynamic range of the residual stream for the inputs resident in HBM (one eager pass, a scan after every launch): the tensor
+ * engines keep it in IEEE fp16 and pack with cvt.rn.satfinite, so a net whose trunk exceeds +-65504 would be clamped silently.
+ * max_abs = largest |x| any block left in the stream, n_saturated = values at the clamp (or NaN).  With env P3_RANGE_CHECK=1
+ * every p3_engine_run_inference runs this check and fails with P3_ERR_UNSUPPORTED when n_saturated > 0 (validation mode for a
+ * new checkpoint: slower, one extra pass per run).  The fp32 engine has an fp32 stream: it reports max_abs and non-finite values. */
+int p3_engine_range_check(p3_engine* e, float* max_abs, long long* n_saturated);
 /* Per-stage device times of one eager pass (ms): [0] encode, [1] tower, [2] heads. */
 int p3_engine_stage_ms(p3_engine* e, float ms[3]);
 /* Number of kernel launches one p3_engine_run_inference issues (for bench.py's gpu_launches). */

@@ -214,9 +214,53 @@ float orc_uniform(uint64_t* state) { /* Probability::Uniform, probability.cc:17-
   memcpy(&r, &x, sizeof r);
   return r - 1.0f;
 }
+/* logf as the reference executes it.  probability.cc:12-15 calls the C library's logf; that algorithm lives in a third-party
+ * dependency absent from /root/reference: GNU libc 2.39 (Ubuntu 2.39-0ubuntu8.5 in this image),
+ * sysdeps/ieee754/flt-32/e_logf.c + e_logf_data.c (Szabolcs Nagy's ARM optimized-routines logf: 16-entry {1/c, log c}
+ * table indexed by the top 4 mantissa bits around OFF = 0x3f330000, degree-3 polynomial in r = z/c - 1, everything in
+ * double, ONE final rounding to float).  Restated here so that the oracle - and the CUDA kernel that mirrors it
+ * (csrc/gumbel.cu) - do not depend on the libm of the box.  Pinned: tests/test_oracle_vs_ref.py compares it with this
+ * machine's libm logf (what the compiled reference calls) on > 10^6 arguments; checked once exhaustively over all
+ * 2 139 095 039 positive finite floats, with and without fused multiply-adds: 0 mismatches either way. */
+static const double kLogfTab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+float orc_logf(float x) {
+  const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2, Ln2 = 0x1.62e42fefa39efp-1;
+  uint32_t ix;
+  memcpy(&ix, &x, 4);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) { /* zero, subnormal, negative, inf, nan */
+    if (ix * 2 == 0) return -INFINITY;
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return NAN;
+    float xs = x * 0x1p23f; /* subnormal: normalise */
+    memcpy(&ix, &xs, 4);
+    ix -= 23u << 23;
+  }
+  uint32_t tmp = ix - 0x3f330000u;
+  int i = (int)((tmp >> 19) % 16);
+  int k = (int32_t)tmp >> 23; /* arithmetic shift */
+  uint32_t iz = ix - (tmp & 0xff800000u);
+  float zf;
+  memcpy(&zf, &iz, 4);
+  double z = zf, r = z * kLogfTab[i][0] - 1, y0 = kLogfTab[i][1] + (double)k * Ln2, r2 = r * r;
+  double y = A1 * r + A2;
+  y = A0 * r2 + y;
+  y = y * r2 + (y0 + r);
+  return (float)y;
+}
+float orc_libm_logf(float x) { return logf(x); } /* this box's libm, for the pinning test only */
+float orc_gumbel_from_uniform(float cdf) { return -orc_logf(-orc_logf(cdf)); }
 float orc_gumbel(uint64_t* state) { /* Probability::GumbelSample, probability.cc:12-15 */
   float cdf = orc_uniform(state);
-  return -logf(-logf(cdf));
+  return -orc_logf(-orc_logf(cdf));
 }
 int orc_rand_range(uint64_t* state, int lo, int hi) { /* RandRange, rand.cc:100-121 */
   if (lo == hi) return lo;

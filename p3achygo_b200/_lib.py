@@ -14,12 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libp3b200.so")
 
-NUM_LOCS = 361
-NUM_MOVES = 362
-
-P3_OK = 0
-P3_ERR_INVALID_ARG, P3_ERR_NO_DEVICE, P3_ERR_CUDA, P3_ERR_IO, P3_ERR_UNSUPPORTED = 1, 2, 3, 4, 5
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+from .layout import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, LEAF_RESULT_DTYPE, NUM_LOCS, NUM_MOVES,  # noqa: F401
+                     P3_ERR_CUDA, P3_ERR_INVALID_ARG, P3_ERR_IO, P3_ERR_NO_DEVICE, P3_ERR_UNSUPPORTED, P3_OK, PRECISION_BF16,
+                     PRECISION_FP32, RESULT_FULL, RESULT_LEAF, GoFeatures, Loc)
 
 
 class P3Error(RuntimeError):
@@ -27,52 +24,6 @@ class P3Error(RuntimeError):
         super().__init__(f"libp3b200 error {code}: {msg}")
         self.code = code
 
-
-class Loc(ctypes.Structure):
-    _fields_ = [("i", ctypes.c_int32), ("j", ctypes.c_int32)]
-
-
-class GoFeatures(ctypes.Structure):
-    """nn::GoFeatures, cc/nn/engine/go_features.h:12-22 (1860 bytes)."""
-    _fields_ = [
-        ("bsize", ctypes.c_int32),
-        ("color", ctypes.c_int8),
-        ("komi", ctypes.c_float),
-        ("board", ctypes.c_int8 * NUM_LOCS),
-        ("last_moves", Loc * 5),
-        ("stones_atari", ctypes.c_int8 * NUM_LOCS),
-        ("stones_two_liberties", ctypes.c_int8 * NUM_LOCS),
-        ("stones_three_liberties", ctypes.c_int8 * NUM_LOCS),
-        ("stones_laddered", ctypes.c_int8 * NUM_LOCS),
-    ]
-
-
-# numpy view of the same 1860-byte record (for bulk fixtures)
-GO_FEATURES_DTYPE = np.dtype({
-    "names": ["bsize", "color", "komi", "board", "last_moves", "stones_atari", "stones_two_liberties",
-              "stones_three_liberties", "stones_laddered"],
-    "formats": ["<i4", "i1", "<f4", ("i1", NUM_LOCS), ("<i4", (5, 2)), ("i1", NUM_LOCS), ("i1", NUM_LOCS),
-                ("i1", NUM_LOCS), ("i1", NUM_LOCS)],
-    "offsets": [0, 4, 8, 12, 376, 416, 777, 1138, 1499],
-    "itemsize": 1860,
-})
-
-# nn::NNInferResult, cc/nn/engine/engine.h:12-20 (7568 bytes, opt_move_probs 16-byte aligned)
-INFER_RESULT_DTYPE = np.dtype({
-    "names": ["move_logits", "move_probs", "value_probs", "score_probs", "opt_move_probs", "err2_outcome"],
-    "formats": [("<f4", NUM_MOVES), ("<f4", NUM_MOVES), ("<f4", 2), ("<f4", 800), ("<f4", NUM_MOVES), "<f4"],
-    "offsets": [0, 1448, 2896, 2904, 6112, 7560],
-    "itemsize": 7568,
-})
-
-AUX_RESULT_DTYPE = np.dtype([
-    ("pi_logits_aux", "<f4", NUM_MOVES), ("pi_logits_soft", "<f4", NUM_MOVES), ("pi_logits_optimistic", "<f4", NUM_MOVES),
-    ("outcome_logits", "<f4", 2), ("score_logits", "<f4", 800), ("gamma", "<f4"), ("q", "<f4", 3), ("q_err", "<f4", 3),
-    ("q_score", "<f4", 3), ("q_score_err", "<f4", 3), ("mcts_dist_logits", "<f4", 51), ("mcts_dist_probs", "<f4", 51),
-    ("ownership", "<f4", NUM_LOCS), ("value", "<f4"), ("score_mean", "<f4"), ("score_var", "<f4"),
-])
-
-assert ctypes.sizeof(GoFeatures) == 1860 and GO_FEATURES_DTYPE.itemsize == 1860
 
 # every symbol include/p3_b200.h declares
 EXPORTS = [
@@ -82,6 +33,8 @@ EXPORTS = [
     "p3_engine_run_device", "p3_engine_upload", "p3_engine_profile", "p3_engine_stage_ms", "p3_engine_launches_per_run", "p3_engine_flops_per_position",
     "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_game_derive", "p3_gumbel_topk",
     "p3_conv_test", "p3_broadcast_test", "p3_block_boundary_test", "p3_last_error", "p3_version",
+    "p3_engine_set_result_mode", "p3_engine_get_leaf", "p3_engine_get_leaf_bank", "p3_engine_get_aux_bank",
+    "p3_engine_get_ownership_bank", "p3_engine_gumbel_topk_bank", "p3_engine_range_check",
 ]
 
 
@@ -128,6 +81,13 @@ def _load() -> ctypes.CDLL:
     lib.p3_conv_test.argtypes = [ci, ci, vp, vp, ci, ci, ci, ci, vp]
     lib.p3_broadcast_test.argtypes = [ci, ci, vp, vp, vp, ci, ci, vp]
     lib.p3_block_boundary_test.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]
+    lib.p3_engine_set_result_mode.argtypes = [vp, ci]
+    lib.p3_engine_get_leaf.argtypes = [vp, ci, vp]
+    lib.p3_engine_get_leaf_bank.argtypes = [vp, ci, ci, vp]
+    lib.p3_engine_get_aux_bank.argtypes = [vp, ci, ci, vp]
+    lib.p3_engine_get_ownership_bank.argtypes = [vp, ci, ci, vp]
+    lib.p3_engine_range_check.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_longlong)]
+    lib.p3_engine_gumbel_topk_bank.argtypes = [vp, ci, vp, ci, vp, vp, cf, ci, vp, vp, vp]
     return lib
 
 

@@ -194,8 +194,9 @@ struct HeadWeights {
 // per-point policy pass read it coalesced; results/aux device arrays of n.
 // sym (optional, [n]): the symmetry each slot's input was rotated by; move_logits / move_probs / opt_move_probs come back
 // un-rotated (ApplyInverse, cc/nn/nn_interface.h:263-287), the pass entry untouched.
+// leafs (optional, [n]): the compact per-leaf record of mcts::LeafEvaluator InitFields (p3_leaf_result).
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream, bool accurate = true, const int8_t* sym = nullptr);
+                 cudaStream_t stream, bool accurate = true, const int8_t* sym = nullptr, p3_leaf_result* leafs = nullptr);
 
 // ---- gumbel (gumbel.cu) --------------------------------------------------------------------------------------
 // ladder.cu: replay of move lists -> boards, laddered stones (board.cc:692-899), exact legal masks (board.cc:595-644); device pointers
@@ -211,7 +212,10 @@ int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_
 // derived grids + move list -> the GoFeatures records of the slots whose num_moves >= 0 (NNInterface::LoadBatch, nn_interface.cc:245-277)
 int assemble_features_launch(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves, const int8_t* d_boards, const int8_t* d_libs,
                              const int8_t* d_laddered, int n, p3_go_features* d_feats, cudaStream_t stream);
+// logits: root r reads logits + (slots ? slots[r] : r) * logit_stride floats (logit_stride = 362 for a packed [n,362] array,
+// sizeof(p3_infer_result) / 4 when sampling straight from a result array); legal [n,362] packed by root, or (legal_by_slot) a per-slot array indexed like the logits.
 int gumbel_launch(const float* logits, const uint8_t* legal, uint64_t* prng_state, int n, float noise_scaling,
-                  int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid, cudaStream_t stream);
+                  int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid, cudaStream_t stream,
+                  size_t logit_stride = P3_MAX_MOVES, const int32_t* slots = nullptr, bool legal_by_slot = false);
 
 }  // namespace p3

@@ -14,11 +14,14 @@
 #include <atomic>
 #include <cstring>
 #include <memory>
+#include <new>
+#include <stdexcept>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "math.cuh"
 #include "weights_file.h"
 
 namespace p3 {
@@ -143,7 +146,9 @@ struct p3_engine {
   p3_infer_result* h_results = nullptr;
   int8_t* h_sym = nullptr;  // per-slot game::Symmetry of p3_engine_load_batch_sym (0 = features already oriented by the caller)
   // device IO
-  DevBuf d_feats, d_planes, d_scalars, d_masks, d_results, d_aux;
+  DevBuf d_feats, d_planes, d_scalars, d_masks, d_results, d_aux, d_leaf;
+  p3_leaf_result* h_leaf = nullptr;  // pinned: the serial path's compact results (P3_RESULT_LEAF)
+  int result_mode = P3_RESULT_FULL;
   // activations
   DevBuf xraw, actA, actB, actS0, actS1, rawB, pgv;
   // weights
@@ -179,13 +184,24 @@ struct p3_engine {
     p3_infer_result* h_results = nullptr;
     int8_t* h_sym = nullptr;
     bool owns_host = false;
-    DevBuf d_feats, d_sym, d_results;
+    DevBuf d_feats, d_sym, d_results, d_aux, d_leaf;   // d_aux / d_leaf: this bank's copy of the step's aux + leaf records
+    p3_leaf_result* h_leaf = nullptr;                    // pinned (P3_RESULT_LEAF)
+    int mode = P3_RESULT_FULL;                           // result mode of the run in flight / last completed
+    bool on_device = false;                              // d_results / d_aux hold the last completed run (a submit, not a serial run)
     // slots loaded as game records (p3_engine_load_game_bank): move lists, move counts (-1 = the slot holds GoFeatures), pass-alive grids
     int16_t* h_moves = nullptr;
     int32_t* h_nmoves = nullptr;
     int8_t* h_forbidden = nullptr;
     int32_t* h_gstatus = nullptr;   // per-slot status of the last derivation (0 = ok), read back with the run
     bool derived = false;
+    // A slot may be (re)loaded while a run is copying the bank (the LoadBatch contract: no lock, may overlap RunInference).  The
+    // three record arrays travel in separate DMAs, so such a slot can reach the GPU torn and be rejected by the replay; its result
+    // is garbage by contract and nobody reads it.  Loads bracket their writes with two increments of gen[slot] (odd = being
+    // written); a run snapshots gen and num_moves when it is enqueued and only reports a rejected record for slots whose
+    // generation is even and unchanged when the run has completed.
+    std::unique_ptr<std::atomic<uint32_t>[]> gen;
+    std::vector<uint32_t> sub_gen;
+    std::vector<int32_t> sub_nmoves;
     DevBuf d_moves, d_nmoves, d_forbidden;
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
     std::atomic<int> in_flight{0};
@@ -215,6 +231,7 @@ struct p3_engine {
       if (b.h_nmoves) cudaFreeHost(b.h_nmoves);
       if (b.h_forbidden) cudaFreeHost(b.h_forbidden);
       if (b.h_gstatus) cudaFreeHost(b.h_gstatus);
+      if (b.h_leaf) cudaFreeHost(b.h_leaf);
       if (b.owns_host) {
         if (b.h_feats) cudaFreeHost(b.h_feats);
         if (b.h_results) cudaFreeHost(b.h_results);
@@ -228,6 +245,7 @@ struct p3_engine {
     if (h_feats) cudaFreeHost(h_feats);
     if (h_results) cudaFreeHost(h_results);
     if (h_sym) cudaFreeHost(h_sym);
+    if (h_leaf) cudaFreeHost(h_leaf);
   }
 
   const float* dev_vec(const std::vector<float>& v, int* rc) {
@@ -283,7 +301,7 @@ struct p3_engine {
     rc = run_conv(head_step);
     if (rc) return rc;
     rc = heads_launch(pgv.as<float>(), batch, hw, to_host ? h_results : d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(),
-                      stream, !bf16, d_sym.as<int8_t>());
+                      stream, !bf16, d_sym.as<int8_t>(), d_leaf.as<p3_leaf_result>());
     if (rc) return rc;
     if (with_events) P3_CUDA(cudaEventRecord(ev[3], stream));
     return P3_OK;
@@ -293,7 +311,11 @@ struct p3_engine {
   // into the step's GoFeatures buffer (d_feats) on `stream`; `copy_stream` carries the H2D of the lists.  No-op without such slots.
   int enqueue_game_records(Bank& bk, cudaStream_t copy_stream, cudaEvent_t copied) {
     bool any = false;
-    for (int b = 0; b < batch && !any; ++b) any = bk.h_nmoves[b] >= 0;
+    for (int b = 0; b < batch; ++b) {  // snapshot BEFORE the copies are enqueued (see Bank::gen)
+      bk.sub_gen[b] = bk.gen[b].load(std::memory_order_acquire);
+      bk.sub_nmoves[b] = bk.h_nmoves[b];
+      any = any || bk.sub_nmoves[b] >= 0;
+    }
     bk.derived = any;
     if (!any) return P3_OK;
     int rc;
@@ -328,10 +350,16 @@ struct p3_engine {
   // impossible states); the other slots' results are valid
   int check_game_records(Bank& bk) {
     if (!bk.derived) return P3_OK;
-    for (int b = 0; b < batch; ++b)
-      if (bk.h_nmoves[b] >= 0 && bk.h_gstatus[b] != 0)
-        return fail(P3_ERR_INVALID_ARG, "slot " + std::to_string(b) + ": game record rejected by the replay (status " +
-                                            std::to_string(bk.h_gstatus[b]) + ": 1 = move onto an occupied point, 2 = reader overflow)");
+    const bool watchdog = (bk.h_gstatus[0] & 8) != 0;  // the reader gave up (ladder.cu): the batch's laddered grids are incomplete
+    for (int b = 0; b < batch; ++b) {
+      const int st = bk.h_gstatus[b] & ~8;
+      if (bk.sub_nmoves[b] < 0 || st == 0) continue;
+      // a slot that was being (re)loaded while the bank was copied reached the GPU torn: not an error, its result is unread
+      if ((bk.sub_gen[b] & 1u) || bk.gen[b].load(std::memory_order_acquire) != bk.sub_gen[b]) continue;
+      return fail(P3_ERR_INVALID_ARG, "slot " + std::to_string(b) + ": game record rejected by the replay (status " +
+                                          std::to_string(st) + ": 1 = move onto an occupied point, 2 = reader overflow)");
+    }
+    if (watchdog) return fail(P3_ERR_CUDA, "ladder reader watchdog fired: laddered stones of this batch are incomplete");
     return P3_OK;
   }
 
@@ -366,6 +394,40 @@ struct p3_engine {
 
 namespace p3 {
 namespace {
+
+// max |x| and the number of saturated values (|x| == 65504, what cvt.rn.satfinite leaves of anything larger) of an fp16 buffer
+__global__ void range_scan_f16_kernel(const __half* __restrict__ x, size_t n, unsigned* __restrict__ max_bits,
+                                      unsigned long long* __restrict__ n_sat) {
+  float m = 0.0f;
+  unsigned long long sat = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = fabsf(__half2float(x[i]));
+    m = fmaxf(m, v);
+    sat += (v >= 65504.0f || v != v) ? 1u : 0u;
+  }
+  m = warp_max(m);
+  for (int o = 16; o > 0; o >>= 1) sat += __shfl_xor_sync(0xffffffffu, sat, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(max_bits, __float_as_uint(m));  // non-negative floats order like their bit patterns
+    if (sat) atomicAdd(n_sat, sat);
+  }
+}
+__global__ void range_scan_f32_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ max_bits,
+                                      unsigned long long* __restrict__ n_bad) {
+  float m = 0.0f;
+  unsigned long long bad = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = fabsf(x[i]);
+    m = fmaxf(m, v == v ? v : 0.0f);
+    bad += (v != v || v > 3.0e38f) ? 1u : 0u;
+  }
+  m = warp_max(m);
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(max_bits, __float_as_uint(m));
+    if (bad) atomicAdd(n_bad, bad);
+  }
+}
 
 struct Builder {
   p3_engine& e;
@@ -477,6 +539,9 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   if ((rc = e.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
   P3_CUDA(cudaMemset(e.d_results.p, 0, e.d_results.bytes));  // struct padding travels with the D2H copies
   if ((rc = e.d_aux.alloc(sizeof(p3_aux_result) * B))) return rc;
+  if ((rc = e.d_leaf.alloc(sizeof(p3_leaf_result) * B))) return rc;
+  P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e.h_leaf), sizeof(p3_leaf_result) * B));
+  std::memset(e.h_leaf, 0, sizeof(p3_leaf_result) * B);
   for (int k = 0; k < P3_NUM_BANKS; ++k) {
     p3_engine::Bank& bk = e.banks[k];
     if (k == 0) {
@@ -500,6 +565,13 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     if ((rc = bk.d_feats.alloc(sizeof(p3_go_features) * B))) return rc;
     if ((rc = bk.d_sym.alloc(B))) return rc;
     if ((rc = bk.d_results.alloc(sizeof(p3_infer_result) * B))) return rc;
+    if ((rc = bk.d_aux.alloc(sizeof(p3_aux_result) * B)) || (rc = bk.d_leaf.alloc(sizeof(p3_leaf_result) * B))) return rc;
+    P3_CUDA(cudaMallocHost(reinterpret_cast<void**>(&bk.h_leaf), sizeof(p3_leaf_result) * B));
+    std::memset(bk.h_leaf, 0, sizeof(p3_leaf_result) * B);
+    bk.gen.reset(new std::atomic<uint32_t>[B]);
+    for (int b = 0; b < B; ++b) bk.gen[b].store(0, std::memory_order_relaxed);
+    bk.sub_gen.assign(B, 0);
+    bk.sub_nmoves.assign(B, -1);
     P3_CUDA(cudaEventCreateWithFlags(&bk.ev_h2d, cudaEventDisableTiming));
     P3_CUDA(cudaEventCreateWithFlags(&bk.ev_done, cudaEventDisableTiming));
     P3_CUDA(cudaEventCreateWithFlags(&bk.ev_d2h, cudaEventDisableTiming));
@@ -902,8 +974,24 @@ extern "C" {
 const char* p3_last_error(void) { return p3::g_last_error.c_str(); }
 const char* p3_version(void) { return "p3achygo-b200 0.1 (sm_100a)"; }
 
+static int engine_create_impl(const char* weights_path, int device, int batch_size, int feat_version, int precision, p3_engine** out);
+
+// No C++ exception crosses the C boundary (a malformed weight file or an allocation failure is an error code, not a terminate).
 int p3_engine_create(const char* weights_path, int device, int batch_size, int feat_version, int precision,
                      p3_engine** out) {
+  try {
+    return engine_create_impl(weights_path, device, batch_size, feat_version, precision, out);
+  } catch (const std::bad_alloc&) {
+    if (out) *out = nullptr;
+    return fail(P3_ERR_IO, "p3_engine_create: out of host memory (malformed weight file?)");
+  } catch (const std::exception& ex) {
+    if (out) *out = nullptr;
+    return fail(P3_ERR_IO, std::string("p3_engine_create: ") + ex.what());
+  }
+}
+
+static int engine_create_impl(const char* weights_path, int device, int batch_size, int feat_version, int precision,
+                              p3_engine** out) {
   if (!weights_path || !out || batch_size <= 0) return fail(P3_ERR_INVALID_ARG, "p3_engine_create: bad argument");
   if (precision != P3_PRECISION_FP32 && precision != P3_PRECISION_BF16)
     return fail(P3_ERR_INVALID_ARG, "p3_engine_create: unknown precision");
@@ -949,18 +1037,22 @@ void p3_engine_destroy(p3_engine* e) {
 
 int p3_engine_load_batch(p3_engine* e, int batch_id, const p3_go_features* features) {
   if (!e || !features || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "load_batch: bad argument");
+  e->banks[0].gen[batch_id].fetch_add(1, std::memory_order_acq_rel);
   std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
   e->h_sym[batch_id] = 0;
   e->banks[0].h_nmoves[batch_id] = -1;
+  e->banks[0].gen[batch_id].fetch_add(1, std::memory_order_release);
   return P3_OK;
 }
 
 int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* features, int sym) {
   if (!e || !features || batch_id < 0 || batch_id >= e->batch || sym < 0 || sym > 7)
     return fail(P3_ERR_INVALID_ARG, "load_batch_sym: bad argument");
+  e->banks[0].gen[batch_id].fetch_add(1, std::memory_order_acq_rel);
   std::memcpy(&e->h_feats[batch_id], features, sizeof(p3_go_features));
   e->h_sym[batch_id] = static_cast<int8_t>(sym);
   e->banks[0].h_nmoves[batch_id] = -1;
+  e->banks[0].gen[batch_id].fetch_add(1, std::memory_order_release);
   return P3_OK;
 }
 
@@ -974,10 +1066,16 @@ int p3_engine_run_inference(p3_engine* e) {
   int rc = e->enqueue_game_records(e->banks[0], e->stream, nullptr);
   if (rc) return rc;
   if (trace) P3_CUDA(cudaEventRecord(e->ev[1], e->stream));
-  rc = e->enqueue_device_maybe_graph(e->results_to_host);
+  const bool leaf = e->result_mode == P3_RESULT_LEAF;
+  const bool to_host = e->results_to_host && !leaf;
+  e->banks[0].mode = e->result_mode;
+  e->banks[0].on_device = false;
+  rc = e->enqueue_device_maybe_graph(to_host);
   if (rc) return rc;
   if (trace) P3_CUDA(cudaEventRecord(e->ev[2], e->stream));
-  if (!e->results_to_host)
+  if (leaf)
+    P3_CUDA(cudaMemcpyAsync(e->h_leaf, e->d_leaf.p, sizeof(p3_leaf_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
+  else if (!to_host)
     P3_CUDA(cudaMemcpyAsync(e->h_results, e->d_results.p, sizeof(p3_infer_result) * e->batch, cudaMemcpyDeviceToHost, e->stream));
   if (trace) P3_CUDA(cudaEventRecord(e->ev[3], e->stream));
   P3_CUDA(cudaStreamSynchronize(e->stream));
@@ -988,11 +1086,23 @@ int p3_engine_run_inference(p3_engine* e) {
     cudaEventElapsedTime(&d2h, e->ev[2], e->ev[3]);
     std::fprintf(stderr, "[p3 run] h2d %.1f us  device %.1f us  d2h %.1f us\n", h2d * 1e3f, dev * 1e3f, d2h * 1e3f);
   }
-  return e->check_game_records(e->banks[0]);
+  rc = e->check_game_records(e->banks[0]);
+  if (rc) return rc;
+  const char* rc_env = std::getenv("P3_RANGE_CHECK");
+  if (rc_env && std::atoi(rc_env) != 0) {  // validation mode: fail loudly instead of evaluating a net whose fp16 residual stream saturates
+    float mx = 0.0f;
+    long long sat = 0;
+    if ((rc = p3_engine_range_check(e, &mx, &sat))) return rc;
+    if (sat > 0)
+      return fail(P3_ERR_UNSUPPORTED, "residual stream out of range: " + std::to_string(sat) + " values saturated (max |x| " +
+                                          std::to_string(mx) + "); run this net with P3_PRECISION_FP32");
+  }
+  return P3_OK;
 }
 
 int p3_engine_get_batch(p3_engine* e, int batch_id, p3_infer_result* result) {
   if (!e || !result || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_batch: bad argument");
+  if (e->banks[0].mode != P3_RESULT_FULL) return fail(P3_ERR_INVALID_ARG, "get_batch: the last run was in P3_RESULT_LEAF mode (use p3_engine_get_leaf)");
   std::memcpy(result, &e->h_results[batch_id], sizeof(p3_infer_result));
   return P3_OK;
 }
@@ -1003,9 +1113,11 @@ int p3_engine_load_batch_bank(p3_engine* e, int bank, int batch_id, const p3_go_
   if (!e || !features || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch || sym < 0 || sym > 7)
     return fail(P3_ERR_INVALID_ARG, "load_batch_bank: bad argument");
   p3_engine::Bank& bk = e->banks[bank];
+  bk.gen[batch_id].fetch_add(1, std::memory_order_acq_rel);
   std::memcpy(&bk.h_feats[batch_id], features, sizeof(p3_go_features));
   bk.h_sym[batch_id] = static_cast<int8_t>(sym);
   bk.h_nmoves[batch_id] = -1;
+  bk.gen[batch_id].fetch_add(1, std::memory_order_release);
   return P3_OK;
 }
 
@@ -1015,7 +1127,8 @@ int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t
       num_moves > P3_MAX_GAME_MOVES || (num_moves > 0 && !moves) || (color != P3_BLACK && color != P3_WHITE))
     return fail(P3_ERR_INVALID_ARG, "load_game_bank: bad argument");
   p3_engine::Bank& bk = e->banks[bank];
-  std::memcpy(bk.h_moves + static_cast<size_t>(batch_id) * P3_MAX_GAME_MOVES, moves, sizeof(int16_t) * num_moves);
+  bk.gen[batch_id].fetch_add(1, std::memory_order_acq_rel);  // odd: the record is being written (see Bank::gen)
+  if (num_moves > 0) std::memcpy(bk.h_moves + static_cast<size_t>(batch_id) * P3_MAX_GAME_MOVES, moves, sizeof(int16_t) * num_moves);
   if (forbidden) std::memcpy(bk.h_forbidden + static_cast<size_t>(batch_id) * 361, forbidden, 361);
   else std::memset(bk.h_forbidden + static_cast<size_t>(batch_id) * 361, 0, 361);
   p3_go_features& f = bk.h_feats[batch_id];   // colour, komi, bsize travel in the record; the grids and last moves are derived on the GPU
@@ -1024,6 +1137,7 @@ int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t
   f.komi = komi;
   bk.h_sym[batch_id] = static_cast<int8_t>(sym);
   bk.h_nmoves[batch_id] = num_moves;
+  bk.gen[batch_id].fetch_add(1, std::memory_order_release);
   return P3_OK;
 }
 
@@ -1047,11 +1161,17 @@ int p3_engine_submit(p3_engine* e, int bank) {
   if (rc) return rc;
   rc = e->enqueue_device_maybe_graph(false);
   if (rc) return rc;
+  bk.mode = e->result_mode;
+  bk.on_device = true;
+  const size_t lbytes = sizeof(p3_leaf_result) * e->batch;
   P3_CUDA(cudaMemcpyAsync(bk.d_results.p, e->d_results.p, rbytes, cudaMemcpyDeviceToDevice, e->stream));
+  P3_CUDA(cudaMemcpyAsync(bk.d_leaf.p, e->d_leaf.p, lbytes, cudaMemcpyDeviceToDevice, e->stream));
+  P3_CUDA(cudaMemcpyAsync(bk.d_aux.p, e->d_aux.p, sizeof(p3_aux_result) * e->batch, cudaMemcpyDeviceToDevice, e->stream));
   P3_CUDA(cudaEventRecord(bk.ev_done, e->stream));
-  // results -> pinned host memory on the D2H stream (overlaps the next bank's kernels)
+  // results -> pinned host memory on the D2H stream (overlaps the next bank's kernels); the compact records only in leaf mode
   P3_CUDA(cudaStreamWaitEvent(e->d2h_stream, bk.ev_done, 0));
-  P3_CUDA(cudaMemcpyAsync(bk.h_results, bk.d_results.p, rbytes, cudaMemcpyDeviceToHost, e->d2h_stream));
+  if (bk.mode == P3_RESULT_LEAF) P3_CUDA(cudaMemcpyAsync(bk.h_leaf, bk.d_leaf.p, lbytes, cudaMemcpyDeviceToHost, e->d2h_stream));
+  else P3_CUDA(cudaMemcpyAsync(bk.h_results, bk.d_results.p, rbytes, cudaMemcpyDeviceToHost, e->d2h_stream));
   P3_CUDA(cudaEventRecord(bk.ev_d2h, e->d2h_stream));
   return P3_OK;
 }
@@ -1069,7 +1189,95 @@ int p3_engine_wait(p3_engine* e, int bank) {
 int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result) {
   if (!e || !result || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch)
     return fail(P3_ERR_INVALID_ARG, "get_batch_bank: bad argument");
+  if (e->banks[bank].mode != P3_RESULT_FULL)
+    return fail(P3_ERR_INVALID_ARG, "get_batch_bank: the bank's last run was in P3_RESULT_LEAF mode (use p3_engine_get_leaf_bank)");
   std::memcpy(result, &e->banks[bank].h_results[batch_id], sizeof(p3_infer_result));
+  return P3_OK;
+}
+
+int p3_engine_set_result_mode(p3_engine* e, int mode) {
+  if (!e || (mode != P3_RESULT_FULL && mode != P3_RESULT_LEAF)) return fail(P3_ERR_INVALID_ARG, "set_result_mode: bad argument");
+  e->result_mode = mode;
+  return P3_OK;
+}
+
+int p3_engine_get_leaf(p3_engine* e, int batch_id, p3_leaf_result* leaf) {
+  if (!e || !leaf || batch_id < 0 || batch_id >= e->batch) return fail(P3_ERR_INVALID_ARG, "get_leaf: bad argument");
+  if (e->banks[0].mode != P3_RESULT_LEAF || e->banks[0].on_device)
+    return fail(P3_ERR_INVALID_ARG, "get_leaf: the last serial run was not in P3_RESULT_LEAF mode");
+  std::memcpy(leaf, &e->h_leaf[batch_id], sizeof(p3_leaf_result));
+  return P3_OK;
+}
+
+int p3_engine_get_leaf_bank(p3_engine* e, int bank, int batch_id, p3_leaf_result* leaf) {
+  if (!e || !leaf || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch)
+    return fail(P3_ERR_INVALID_ARG, "get_leaf_bank: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (bk.mode != P3_RESULT_LEAF || !bk.on_device) return fail(P3_ERR_INVALID_ARG, "get_leaf_bank: the bank's last run was not a P3_RESULT_LEAF submit");
+  if (bk.in_flight.load(std::memory_order_acquire)) return fail(P3_ERR_INVALID_ARG, "get_leaf_bank: bank in flight (p3_engine_wait it first)");
+  std::memcpy(leaf, &bk.h_leaf[batch_id], sizeof(p3_leaf_result));
+  return P3_OK;
+}
+
+int p3_engine_get_aux_bank(p3_engine* e, int bank, int batch_id, p3_aux_result* aux) {
+  if (!e || !aux || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch)
+    return fail(P3_ERR_INVALID_ARG, "get_aux_bank: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (!bk.on_device || bk.in_flight.load(std::memory_order_acquire))
+    return fail(P3_ERR_INVALID_ARG, "get_aux_bank: needs a bank that was submitted and waited");
+  P3_CUDA(cudaSetDevice(e->device));
+  P3_CUDA(cudaMemcpy(aux, bk.d_aux.as<p3_aux_result>() + batch_id, sizeof(p3_aux_result), cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_engine_get_ownership_bank(p3_engine* e, int bank, int batch_id, float own[P3_NUM_BOARD_LOCS]) {
+  if (!e || !own || bank < 0 || bank >= P3_NUM_BANKS || batch_id < 0 || batch_id >= e->batch)
+    return fail(P3_ERR_INVALID_ARG, "get_ownership_bank: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (!bk.on_device || bk.in_flight.load(std::memory_order_acquire))
+    return fail(P3_ERR_INVALID_ARG, "get_ownership_bank: needs a bank that was submitted and waited");
+  P3_CUDA(cudaSetDevice(e->device));
+  const char* src = reinterpret_cast<const char*>(bk.d_aux.as<p3_aux_result>() + batch_id) + offsetof(p3_aux_result, ownership);
+  P3_CUDA(cudaMemcpy(own, src, sizeof(float) * P3_NUM_BOARD_LOCS, cudaMemcpyDeviceToHost));
+  return P3_OK;
+}
+
+int p3_engine_gumbel_topk_bank(p3_engine* e, int bank, const int32_t* slots, int n, const uint8_t* legal, uint64_t* prng_state,
+                               float noise_scaling, int k, int32_t* out_moves, float* out_scores, int32_t* out_kvalid) {
+  if (!e || bank < 0 || bank >= P3_NUM_BANKS || !slots || !legal || !prng_state || !out_moves || !out_scores || !out_kvalid || n < 0)
+    return fail(P3_ERR_INVALID_ARG, "gumbel_topk_bank: bad argument");
+  if (n == 0) return P3_OK;
+  p3_engine::Bank& bk = e->banks[bank];
+  if (bk.in_flight.load(std::memory_order_acquire)) return fail(P3_ERR_INVALID_ARG, "gumbel_topk_bank: bank in flight (p3_engine_wait it first)");
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= e->batch) return fail(P3_ERR_INVALID_ARG, "gumbel_topk_bank: slot out of range");
+  P3_CUDA(cudaSetDevice(e->device));
+  // where the last completed run of this bank left its move_logits: the bank's device copy after a submit; after a serial run
+  // the leaf records (always written to HBM) hold the same logits
+  const float* logits;
+  size_t stride;
+  if (bk.on_device) {
+    logits = reinterpret_cast<const float*>(bk.d_results.p);
+    stride = sizeof(p3_infer_result) / sizeof(float);
+  } else if (bank == 0) {
+    logits = reinterpret_cast<const float*>(e->d_leaf.p);
+    stride = sizeof(p3_leaf_result) / sizeof(float);
+  } else {
+    return fail(P3_ERR_INVALID_ARG, "gumbel_topk_bank: the bank has no completed run");
+  }
+  DevBuf dsl, dm, dst, dmv, dsc, dkv;
+  int rc;
+  if ((rc = upload(dsl, slots, sizeof(int32_t) * n)) || (rc = upload(dm, legal, static_cast<size_t>(n) * P3_MAX_MOVES)) ||
+      (rc = upload(dst, prng_state, sizeof(uint64_t) * n)) || (rc = dmv.alloc(sizeof(int32_t) * n * k)) ||
+      (rc = dsc.alloc(sizeof(float) * n * k)) || (rc = dkv.alloc(sizeof(int32_t) * n)))
+    return rc;
+  if ((rc = gumbel_launch(logits, dm.as<uint8_t>(), dst.as<uint64_t>(), n, noise_scaling, k, dmv.as<int32_t>(), dsc.as<float>(),
+                          dkv.as<int32_t>(), 0, stride, dsl.as<int32_t>(), false)))
+    return rc;
+  P3_CUDA(cudaMemcpy(out_moves, dmv.p, dmv.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(out_scores, dsc.p, dsc.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(out_kvalid, dkv.p, dkv.bytes, cudaMemcpyDeviceToHost));
+  P3_CUDA(cudaMemcpy(prng_state, dst.p, dst.bytes, cudaMemcpyDeviceToHost));
   return P3_OK;
 }
 
@@ -1165,7 +1373,7 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   if (!rc) rc = e->run_conv(e->head_step);
   cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
   P3_CUDA(rec());
-  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16, e->d_sym.as<int8_t>());
+  if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16, e->d_sym.as<int8_t>(), e->d_leaf.as<p3_leaf_result>());
   cls.push_back(6); fl.push_back(0.0);
   P3_CUDA(rec());
   P3_CUDA(cudaStreamSynchronize(e->stream));
@@ -1191,6 +1399,45 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
   }
   for (auto& v : evs) cudaEventDestroy(v);
   return rc;
+}
+
+int p3_engine_range_check(p3_engine* e, float* max_abs, long long* n_saturated) {
+  if (!e || !max_abs || !n_saturated) return fail(P3_ERR_INVALID_ARG, "range_check: bad argument");
+  P3_CUDA(cudaSetDevice(e->device));
+  DevBuf acc;
+  int rc = acc.alloc(16);
+  if (rc) return rc;
+  P3_CUDA(cudaMemsetAsync(acc.p, 0, 16, e->stream));
+  unsigned* d_max = acc.as<unsigned>();
+  unsigned long long* d_sat = reinterpret_cast<unsigned long long*>(acc.as<char>() + 8);
+  const size_t n = static_cast<size_t>(e->rows) * e->C;
+  auto scan = [&]() {
+    if (e->bf16) range_scan_f16_kernel<<<592, 256, 0, e->stream>>>(e->xraw.as<__half>(), n, d_max, d_sat);
+    else range_scan_f32_kernel<<<592, 256, 0, e->stream>>>(e->xraw.as<float>(), n, d_max, d_sat);
+    return cudaGetLastError();
+  };
+  rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
+                     e->d_masks.as<uint16_t>(), e->stream, &e->enc_extra);
+  if (!rc) rc = e->run_init();
+  if (rc) return rc;
+  P3_CUDA(scan());
+  for (const Step& s : e->program) {  // the residual stream is rewritten in place block by block: look at it after every launch
+    if (s.kind == kStepConv) rc = e->run_conv(s);
+    else if (s.kind == kStepChain) rc = tc_chain_launch(s.cplan, e->stream);
+    else rc = e->run_broadcast(s);
+    if (rc) return rc;
+    P3_CUDA(scan());
+  }
+  P3_CUDA(cudaStreamSynchronize(e->stream));
+  unsigned char h[16];
+  P3_CUDA(cudaMemcpy(h, acc.p, 16, cudaMemcpyDeviceToHost));
+  unsigned mb;
+  unsigned long long ns;
+  std::memcpy(&mb, h, 4);
+  std::memcpy(&ns, h + 8, 8);
+  std::memcpy(max_abs, &mb, 4);
+  *n_saturated = static_cast<long long>(ns);
+  return P3_OK;
 }
 
 int p3_engine_stage_ms(p3_engine* e, float ms[3]) {

@@ -37,7 +37,8 @@ __device__ __forceinline__ float group_reduce(float v, bool is_max, float* s_scr
 
 // softmax over s_in[0..n) -> out[0..n) (global), accurate expf as core::Softmax (vmath.h:169-178)
 // sym != 0: out[i] = p[T(sym, i)] for board points (ApplyInverse, cc/game/symmetry.h:53-62), the pass entry stays in place
-__device__ void group_softmax(const float* s_in, int n, float* out, float* s_scratch, int g, int gtid, int sym = 0) {
+__device__ void group_softmax(const float* s_in, int n, float* out, float* s_scratch, int g, int gtid, int sym = 0,
+                              float* out2 = nullptr) {
   float m = -INFINITY;
   for (int i = gtid; i < n; i += kGT) m = fmaxf(m, s_in[i]);
   m = group_reduce(m, true, s_scratch, g, gtid);
@@ -46,7 +47,9 @@ __device__ void group_softmax(const float* s_in, int n, float* out, float* s_scr
   s = group_reduce(s, false, s_scratch, g, gtid);
   for (int i = gtid; i < n; i += kGT) {
     const int src = (sym != 0 && i < P3_NUM_BOARD_LOCS) ? sym_transform_index(sym, i) : i;
-    out[i] = expf(s_in[src] - m) / s;
+    const float pr = expf(s_in[src] - m) / s;
+    out[i] = pr;
+    if (out2) out2[i] = pr;
   }
 }
 
@@ -70,7 +73,7 @@ constexpr int kGroupFloats = 4 * P3_MAX_MOVES + P3_NUM_SCORE_LOGITS + 2 * kGT + 
 template <bool kAccurate>
 __global__ void __launch_bounds__(kThreads, 1)
 heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __restrict__ results,
-             p3_aux_result* __restrict__ auxs, int n, const int8_t* __restrict__ syms) {
+             p3_aux_result* __restrict__ auxs, int n, const int8_t* __restrict__ syms, p3_leaf_result* __restrict__ leafs) {
   const size_t R = static_cast<size_t>(n) * kRowsPerPos;  // pgv is channel-major: element (row, c) at pgv[c * R + row]
   extern __shared__ __align__(16) float hsm[];
   const int Ch = hw.Ch, Cv = hw.Cv;
@@ -230,7 +233,8 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
       s_logits[1][p] = l1;
       s_logits[2][p] = l2;
       s_logits[3][p] = l3;
-      aux.ownership[p] = tanhf(own);
+      // un-rotated like the policies (out[i] = in[T(sym, i)]): the thread of rotated point p writes original point T^-1(p)
+      aux.ownership[sym != 0 ? sym_transform_inv(sym, p) : p] = tanhf(own);
     }
     group_sync(g);
 
@@ -254,15 +258,18 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
     group_sync(g);
 
     // ---- outputs
+    p3_leaf_result* leaf = leafs ? leafs + b : nullptr;
     for (int i = tid; i < P3_MAX_MOVES; i += kGT) {
-      res.move_logits[i] = s_logits[0][(sym != 0 && i < P3_NUM_BOARD_LOCS) ? sym_transform_index(sym, i) : i];
+      const float lg = s_logits[0][(sym != 0 && i < P3_NUM_BOARD_LOCS) ? sym_transform_index(sym, i) : i];
+      res.move_logits[i] = lg;
+      if (leaf) leaf->move_logits[i] = lg;
       aux.pi_logits_aux[i] = s_logits[1][i];
       aux.pi_logits_soft[i] = s_logits[2][i];
       aux.pi_logits_optimistic[i] = s_logits[3][i];
     }
     for (int i = tid; i < P3_NUM_SCORE_LOGITS; i += kGT) aux.score_logits[i] = s_score[i];
-    group_softmax(s_logits[0], P3_MAX_MOVES, res.move_probs, s_scratch, g, tid, sym);      // 01:pi
-    group_softmax(s_logits[3], P3_MAX_MOVES, res.opt_move_probs, s_scratch, g, tid, sym);  // trt_engine.cc:347
+    group_softmax(s_logits[0], P3_MAX_MOVES, res.move_probs, s_scratch, g, tid, sym, leaf ? leaf->move_probs : nullptr);  // 01:pi
+    group_softmax(s_logits[3], P3_MAX_MOVES, res.opt_move_probs, s_scratch, g, tid, sym, leaf ? leaf->opt_move_probs : nullptr);  // trt_engine.cc:347
     group_softmax(s_score, P3_NUM_SCORE_LOGITS, res.score_probs, s_scratch, g, tid);      // 06:score_probs
     group_softmax(s_mcts, 51, aux.mcts_dist_probs, s_scratch, g, tid);                    // 24
     if (tid < 51) aux.mcts_dist_logits[tid] = s_mcts[tid];
@@ -287,6 +294,10 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
         const float mean = e1 / z;
         aux.score_mean = mean;
         aux.score_var = e2 / z - mean * mean;
+        if (leaf) {
+          leaf->score_mean = mean;
+          leaf->score_var = e2 / z - mean * mean;
+        }
       }
     }
     if (tid == 0) {
@@ -297,6 +308,10 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
       res.value_probs[0] = p_loss;
       res.value_probs[1] = p_win;
       aux.value = p_win - p_loss;
+      if (leaf) {
+        leaf->value = p_win - p_loss;                                  // init_outcome_est, leaf_evaluator.cc:92-93
+        leaf->err = sqrtf(4.0f * sigmoid_f32(s_o[5]));                 // init_err_est = sqrt(err2_outcome), :108
+      }
       aux.outcome_logits[0] = s_o[0];
       aux.outcome_logits[1] = s_o[1];
       aux.gamma = s_misc[1];
@@ -315,7 +330,7 @@ heads_kernel(const float* __restrict__ pgv, HeadWeights hw, p3_infer_result* __r
 }  // namespace
 
 int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result* results, p3_aux_result* aux,
-                 cudaStream_t stream, bool accurate, const int8_t* sym) {
+                 cudaStream_t stream, bool accurate, const int8_t* sym, p3_leaf_result* leafs) {
   if (hw.Ch > kMaxCh || hw.Cv > kMaxCv || 2 * hw.Ch > kGT || hw.Ch % 4 != 0)
     return fail(P3_ERR_UNSUPPORTED, "heads: head channels / c_val not supported");
   const size_t smem = (static_cast<size_t>((heads_weight_floats(hw.Ch, hw.Cv) + 3) & ~3) + static_cast<size_t>(kGroups) * kGroupFloats) * sizeof(float);
@@ -327,8 +342,8 @@ int heads_launch(const float* pgv, int n, const HeadWeights& hw, p3_infer_result
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(sms, (n + kGroups - 1) / kGroups);
-  if (accurate) heads_kernel<true><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym);
-  else heads_kernel<false><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym);
+  if (accurate) heads_kernel<true><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym, leafs);
+  else heads_kernel<false><<<grid, kThreads, smem, stream>>>(pgv, hw, results, aux, n, sym, leafs);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

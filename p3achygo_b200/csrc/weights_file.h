@@ -60,13 +60,21 @@ struct WeightFile {
       std::string name;
       if (!rd_str(name) || !need(1)) return path + ": truncated tensor header";
       const uint8_t nd = buf[off++];
+      if (nd > 8) return path + ": tensor " + name + " has " + std::to_string(nd) + " dimensions";
       WeightTensor t;
       t.dims.resize(nd);
       for (uint8_t d = 0; d < nd; ++d)
         if (!rd_u32(t.dims[d])) return path + ": truncated dims";
       off += (4 - off % 4) % 4;
-      const size_t cnt = t.numel();
-      if (!need(cnt * 4)) return path + ": truncated data for " + name;
+      if (off > buf.size()) return path + ": truncated data for " + name;
+      // the element count is bounded by what is left of the file BEFORE any multiplication can wrap
+      const size_t max_cnt = (buf.size() - off) / 4;
+      size_t cnt = 1;
+      for (uint32_t dim : t.dims) {
+        if (dim != 0 && cnt > max_cnt / dim) return path + ": truncated data for " + name;
+        cnt *= dim;
+      }
+      if (cnt > max_cnt) return path + ": truncated data for " + name;
       t.data.resize(cnt);
       std::memcpy(t.data.data(), &buf[off], cnt * 4);
       off += cnt * 4;

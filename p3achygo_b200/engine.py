@@ -17,8 +17,8 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, NUM_LOCS, NUM_MOVES, PRECISION_BF16,
-                   PRECISION_FP32, P3Error, check, lib, ptr)
+from ._lib import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, LEAF_RESULT_DTYPE, NUM_LOCS, NUM_MOVES,
+                   PRECISION_BF16, PRECISION_FP32, RESULT_FULL, RESULT_LEAF, P3Error, check, lib, ptr)
 
 
 class Kind(enum.IntEnum):
@@ -136,6 +136,43 @@ class B200Engine:
         check(lib.p3_engine_get_batch_bank(self._h, bank, batch_id, ptr(out)))
         return out[0]
 
+    # -- compact leaf results: what mcts::LeafEvaluator InitFields keeps, 4360 B instead of 7568 B per leaf
+    def SetResultMode(self, mode: int) -> None:
+        check(lib.p3_engine_set_result_mode(self._h, int(mode)))
+
+    def GetLeaf(self, batch_id: int) -> np.ndarray:
+        out = np.zeros(1, dtype=LEAF_RESULT_DTYPE)
+        check(lib.p3_engine_get_leaf(self._h, batch_id, ptr(out)))
+        return out[0]
+
+    def GetLeafBank(self, bank: int, batch_id: int) -> np.ndarray:
+        out = np.zeros(1, dtype=LEAF_RESULT_DTYPE)
+        check(lib.p3_engine_get_leaf_bank(self._h, bank, batch_id, ptr(out)))
+        return out[0]
+
+    def GetAuxBank(self, bank: int, batch_id: int) -> np.ndarray:
+        out = np.zeros(1, dtype=AUX_RESULT_DTYPE)
+        check(lib.p3_engine_get_aux_bank(self._h, bank, batch_id, ptr(out)))
+        return out[0]
+
+    def GetOwnershipBank(self, bank: int, batch_id: int) -> np.ndarray:
+        own = np.zeros(NUM_LOCS, dtype=np.float32)
+        check(lib.p3_engine_get_ownership_bank(self._h, bank, batch_id, ptr(own)))
+        return own
+
+    def GumbelTopKBank(self, bank: int, slots, legal: np.ndarray, prng_state: np.ndarray, noise_scaling: float, k: int):
+        """Gumbel root sampling (cc/mcts/gumbel.cc:283-321) on move_logits still resident in HBM after ``bank``'s last run."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        legal = np.ascontiguousarray(legal, dtype=np.uint8).reshape(-1, NUM_MOVES)
+        n = len(slots)
+        assert prng_state.dtype == np.uint64 and prng_state.flags.c_contiguous and len(prng_state) == n and len(legal) == n
+        moves = np.zeros((n, k), dtype=np.int32)
+        scores = np.zeros((n, k), dtype=np.float32)
+        kvalid = np.zeros(n, dtype=np.int32)
+        check(lib.p3_engine_gumbel_topk_bank(self._h, bank, ptr(slots), n, ptr(legal), ptr(prng_state), noise_scaling, k,
+                                             ptr(moves), ptr(scores), ptr(kvalid)))
+        return moves, scores, kvalid
+
     def GetOwnership(self, batch_id: int) -> np.ndarray:
         """engine.h:38-39"""
         own = np.zeros(NUM_LOCS, dtype=np.float32)
@@ -175,6 +212,12 @@ class B200Engine:
         flops = np.zeros(7, dtype=np.float64)
         check(lib.p3_engine_profile(self._h, ptr(ms), ptr(launches), ptr(flops)))
         return {k: (float(ms[i]), int(launches[i]), float(flops[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def RangeCheck(self):
+        """(max |x| of the residual stream over all blocks, number of values at the fp16 clamp) for the resident inputs."""
+        mx, sat = ctypes.c_float(), ctypes.c_longlong()
+        check(lib.p3_engine_range_check(self._h, ctypes.byref(mx), ctypes.byref(sat)))
+        return mx.value, sat.value
 
     def StageMs(self):
         arr = (ctypes.c_float * 3)()

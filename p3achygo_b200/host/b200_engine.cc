@@ -50,6 +50,12 @@ void B200Engine::Wait(int bank) { P3_CHECK(p3_engine_wait(engine_, bank)); }
 void B200Engine::GetBatchBank(int bank, int batch_id, NNInferResult& result) {
   P3_CHECK(p3_engine_get_batch_bank(engine_, bank, batch_id, &result));
 }
+void B200Engine::GetOwnershipBank(int bank, int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) {
+  P3_CHECK(p3_engine_get_ownership_bank(engine_, bank, batch_id, own.data()));
+}
+void B200Engine::SetLeafResults(bool enabled) { P3_CHECK(p3_engine_set_result_mode(engine_, enabled ? P3_RESULT_LEAF : P3_RESULT_FULL)); }
+void B200Engine::GetLeaf(int batch_id, p3_leaf_result& leaf) { P3_CHECK(p3_engine_get_leaf(engine_, batch_id, &leaf)); }
+void B200Engine::GetLeafBank(int bank, int batch_id, p3_leaf_result& leaf) { P3_CHECK(p3_engine_get_leaf_bank(engine_, bank, batch_id, &leaf)); }
 void B200Engine::GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) {
   P3_CHECK(p3_engine_get_ownership(engine_, batch_id, own.data()));
 }

@@ -33,6 +33,14 @@ class B200Engine final : public Engine {
   void Submit(int bank);
   void Wait(int bank);
   void GetBatchBank(int bank, int batch_id, NNInferResult& result);
+  // GetOwnership for a slot of a waited bank (each bank keeps its own copy of the auxiliary outputs)
+  void GetOwnershipBank(int bank, int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own);
+  // Compact leaf records: SetLeafResults(true) makes runs copy back one p3_leaf_result (4360 B: the three policy
+  // arrays + value / E[score] / Var[score] / err of mcts::LeafEvaluator's InitFields, cc/mcts/leaf_evaluator.cc:83-112) per
+  // slot instead of the 7568-byte NNInferResult; read them with GetLeaf / GetLeafBank.
+  void SetLeafResults(bool enabled);
+  void GetLeaf(int batch_id, p3_leaf_result& leaf);
+  void GetLeafBank(int bank, int batch_id, p3_leaf_result& leaf);
 
   p3_engine* handle() { return engine_; }
   int batch_size() const { return batch_size_; }

@@ -229,7 +229,7 @@ GoDataset::GoDataset(size_t batch_size, std::string ds_path) : batch_size_(batch
     uint32_t len_crc;
     std::memcpy(&len, data.data() + pos, 8);
     std::memcpy(&len_crc, data.data() + pos + 8, 4);
-    if (len_crc != MaskedCrc32c(data.data() + pos, 8) || pos + 12 + len + 4 > data.size()) {
+    if (len_crc != MaskedCrc32c(data.data() + pos, 8) || len > data.size() - pos - 12 || data.size() - pos - 12 - len < 4) {
       std::fprintf(stderr, "Error reading TFRecord %d\n", index);  // go_dataset.cc:49-51
       break;
     }

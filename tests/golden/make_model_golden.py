@@ -38,7 +38,7 @@ from p3achygo_b200._lib import GO_FEATURES_DTYPE  # noqa: E402
 
 # (config, first position index, number of positions): small batches, the net is evaluated in float64 on the CPU
 CASES = [("tiny", 10, 8), ("b10c128btl3", 100, 3), ("b12c256btl3", 100, 2), ("b14c384btl3", 100, 1), ("b15c192_classic", 100, 1),
-         ("b8c128nbt", 100, 2)]
+         ("b8c128nbt", 100, 2), ("small", 100, 2)]
 
 OUTPUT_NAMES = ["pi_logits", "pi", "outcome_logits", "outcome", "own", "score_logits", "score_probs", "gamma", "pi_logits_aux",
                 "q6", "q16", "q50", "q6_err", "q16_err", "q50_err", "q6_score", "q16_score", "q50_score", "q6_score_err",

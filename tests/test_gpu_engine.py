@@ -63,17 +63,27 @@ def _compare(res, aux, o, tol_logits, tol_probs, tol_value, tol_smean):
         ("ownership", stack("ownership", aux), o["own"], tol_value),
         ("value", stack("value", aux), o["value"], 2 * tol_value),
         ("score_mean", stack("score_mean", aux), o["score_mean"], tol_smean),
+        # outputs no round-1 test compared (python/model.py:955-963, :903; cc/mcts/leaf_evaluator.cc:95-107)
+        ("q_err", stack("q_err", aux), o["q_err"], tol_logits),
+        ("q_score_err", stack("q_score_err", aux), o["q_score_err"], tol_logits),
+        ("mcts_dist_logits", stack("mcts_dist_logits", aux), o["mcts_dist_logits"], tol_logits * 4),
     ]
+    # Var[score] = E[s^2] - E[s]^2 over 800 bins of +-400 points: compared relative to E[s^2] (the cancellation's scale)
+    sv = stack("score_var", aux).reshape(n)
+    es2 = np.asarray(o["score_var"], dtype=np.float64).reshape(n) + np.asarray(o["score_mean"], dtype=np.float64).reshape(n) ** 2
+    sv_err = float((np.abs(sv - np.asarray(o["score_var"], dtype=np.float64).reshape(n)) / np.maximum(es2, 1.0)).max())
     worst = {}
     for name, got, exp, tol in checks:
         err = float(np.abs(got.reshape(n, -1) - np.asarray(exp).reshape(n, -1)).max())
         worst[name] = (err, tol)
+    worst["score_var(rel E[s^2])"] = (sv_err, 50 * tol_probs)
     bad = {k: v for k, v in worst.items() if not (v[0] <= v[1])}
     assert not bad, f"out of tolerance: {bad}\nall: {worst}"
     return worst
 
 
-@pytest.mark.parametrize("config,n", [("tiny", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b15c192_classic", 3), ("b8c128nbt", 4)])
+@pytest.mark.parametrize("config,n", [("tiny", 32), ("small", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2),
+                                      ("b15c192_classic", 3), ("b8c128nbt", 4)])
 def test_fp32_engine_matches_oracle(config, n, weight_dir, golden_positions):
     from p3achygo_b200 import engine as E
     path, cfg, tensors = weight_dir(config)
@@ -92,8 +102,8 @@ def test_fp32_engine_matches_oracle(config, n, weight_dir, golden_positions):
     eng.close()
 
 
-@pytest.mark.parametrize("config,n", [("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2), ("b15c192_classic", 3), ("b8c128nbt", 4),
-                                      ("b12c256nbt", 2)])
+@pytest.mark.parametrize("config,n", [("small", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2), ("b15c192_classic", 3),
+                                      ("b8c128nbt", 4), ("b12c256nbt", 2)])
 def test_bf16_engine_within_documented_bound(config, n, weight_dir, golden_positions):
     from p3achygo_b200 import engine as E
     path, cfg, tensors = weight_dir(config)
@@ -196,11 +206,12 @@ _GOLDEN_MAP = [("move_logits", "res", "pi_logits"), ("move_probs", "res", "pi"),
                ("score_probs", "res", "score_probs"), ("pi_logits_aux", "aux", "pi_logits_aux"),
                ("pi_logits_soft", "aux", "pi_logits_soft"), ("pi_logits_optimistic", "aux", "pi_logits_optimistic"),
                ("outcome_logits", "aux", "outcome_logits"), ("score_logits", "aux", "score_logits"), ("gamma", "aux", "gamma"),
-               ("mcts_dist_probs", "aux", "mcts_dist_probs"), ("ownership", "aux", "own")]
+               ("mcts_dist_probs", "aux", "mcts_dist_probs"), ("ownership", "aux", "own"),
+               ("mcts_dist_logits", "aux", "mcts_dist_logits")]
 
 
 @pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("config", ["tiny", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic", "b8c128nbt"])
+@pytest.mark.parametrize("config", ["tiny", "small", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic", "b8c128nbt"])
 def test_engine_matches_reference_model_golden(config, precision_name, weight_dir, golden_positions):
     """The CUDA engine on the positions / weights of the fixture produced by the reference's unmodified python/model.py
     (float64, on oracle/tf_shim).  fp32 engine: max-abs 1e-3 (north star); bf16 engine: the documented bound."""
@@ -217,7 +228,7 @@ def test_engine_matches_reference_model_golden(config, precision_name, weight_di
     tl, tp, tv = (FP32_TOL, FP32_TOL, FP32_TOL) if precision_name == "fp32" else (BF16_TOL["logits"], BF16_TOL["probs"], BF16_TOL["value"])
     tol_of = {"move_logits": tl, "pi_logits_aux": tl, "pi_logits_soft": tl, "pi_logits_optimistic": tl, "outcome_logits": tl,
               "score_logits": 4 * tl, "gamma": tl, "move_probs": tp, "score_probs": tp, "mcts_dist_probs": tp, "value_probs": tv,
-              "ownership": tv}
+              "ownership": tv, "mcts_dist_logits": 4 * tl}
     worst = {}
     for field, src, gname in _GOLDEN_MAP:
         got = np.stack([np.asarray((res if src == "res" else aux)[b][field], dtype=np.float64) for b in range(n)]).reshape(n, -1)
@@ -225,9 +236,14 @@ def test_engine_matches_reference_model_golden(config, precision_name, weight_di
         worst[field] = (float(np.abs(got - ref).max()), tol_of[field])
     bad = {k: v for k, v in worst.items() if not v[0] <= v[1]}
     assert not bad, f"out of tolerance vs the reference model code: {bad}\nall: {worst}"
-    q = np.stack([np.asarray(aux[b]["q"], dtype=np.float64) for b in range(n)])
-    for k, nm in enumerate(("q6", "q16", "q50")):
-        assert np.abs(q[:, k] - z[f"{config}/{nm}"].reshape(n)).max() <= tv
+    for field, suffix, tol in (("q", "", tv), ("q_err", "_err", tl), ("q_score", "_score", tl), ("q_score_err", "_score_err", tl)):
+        q = np.stack([np.asarray(aux[b][field], dtype=np.float64) for b in range(n)])
+        for k, nm in enumerate(("q6", "q16", "q50")):
+            err = float(np.abs(q[:, k] - z[f"{config}/{nm}{suffix}"].reshape(n)).max())
+            worst[f"{nm}{suffix}"] = (err, tol)
+            assert err <= tol, (field, nm, err)
+    e2 = np.array([float(res[b]["err2_outcome"]) for b in range(n)])
+    assert np.abs(e2 - z[f"{config}/q6_err"].reshape(n)).max() <= tl   # 12:q6_err -> err2_outcome (cc/nn/engine/trt_names.h:19)
     print(config, precision_name, "worst vs reference model code:", {k: f"{v[0]:.2e}" for k, v in worst.items()})
     eng.close()
 
@@ -354,3 +370,258 @@ def test_garbage_slots_do_not_fault(weight_dir, golden_positions):
     for b in range(B):
         assert _same(eng.GetBatch(b), want[b])
     eng.close()
+
+
+# ---- batch independence at the OTHER BASELINE configurations: each takes a different tile / plan path (N = 96 pair tile for
+# C = 128, C = 384 off the fused boundary kernel, classic blocks on the residual 3x3 kernel) -----------------------------------
+@pytest.mark.parametrize("config,B", [("b10c128btl3", 256), ("b14c384btl3", 2048), ("b15c192_classic", 1024), ("small", 32)])
+def test_full_size_batch_independence_other_configs(config, B, weight_dir, golden_positions):
+    """BASELINE.json's other configurations at their full batch sizes: a position's result does not depend on the batch it is
+    evaluated in, nor on its slot (bit-exact against the same positions in a batch of 4), and stays within the documented
+    bf16 bound of the fp32 engine."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir(config)
+    feats = golden_positions["feats"]
+    reps = (B + len(feats) - 1) // len(feats)
+    allf = np.concatenate([feats] * reps)[:B] if reps > 1 else feats[:B]
+    big = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    big.LoadBatchAll(allf)
+    big.RunInference()
+    sample = sorted({0, 1, 2, 3, B // 2 - 1, B // 2, B - 3, B - 2, B - 1, B // 3, (2 * B) // 3, B // 5})
+    big_res = {b: big.GetBatch(b).copy() for b in sample}
+    big.close()
+    small = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=E.PRECISION_BF16)
+    ref32 = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=E.PRECISION_FP32)
+    for lo in range(0, len(sample), 4):
+        grp = sample[lo:lo + 4]
+        for s, b in enumerate(grp):
+            small.LoadBatch(s, allf[b])
+            ref32.LoadBatch(s, allf[b])
+        small.RunInference()
+        ref32.RunInference()
+        for s, b in enumerate(grp):
+            assert _same(small.GetBatch(s), big_res[b]), (config, b)
+            r32 = ref32.GetBatch(s)
+            assert np.abs(np.asarray(r32["move_logits"]) - np.asarray(big_res[b]["move_logits"])).max() < BF16_TOL["logits"]
+            assert np.abs(np.asarray(r32["value_probs"]) - np.asarray(big_res[b]["value_probs"])).max() < BF16_TOL["value"]
+    small.close()
+    ref32.close()
+
+
+# ---- compact leaf records, per-bank auxiliary outputs, ownership symmetry, root sampling on resident logits ---------------------
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+def test_leaf_results_equal_initfields_of_full_results(precision_name, weight_dir, golden_positions):
+    """P3_RESULT_LEAF: the 4360-byte record per slot holds exactly the three policy arrays of the NNInferResult of
+    the same run plus InitFields' four scalars (cc/mcts/leaf_evaluator.cc:83-112, restated as oracle orc_init_fields) - serial
+    and over the slot banks; GetBatch refuses to serve stale full results in that mode."""
+    import ctypes
+    from p3achygo_b200 import engine as E
+    L = oracle_lib.oracle()
+    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 8
+    feats = golden_positions["feats"][200:200 + 2 * B]
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=prec)
+    full = []
+    for lo in (0, B):
+        for b in range(B):
+            eng.LoadBatchSym(b, feats[lo + b], (lo + b) % 8)
+        eng.RunInference()
+        full += [eng.GetBatch(b).copy() for b in range(B)]
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def check(leaf, r):
+        for f in ("move_logits", "move_probs", "opt_move_probs"):
+            assert np.array_equal(np.asarray(leaf[f]), np.asarray(r[f])), f
+        want = np.zeros(3, dtype=np.float32)
+        L.orc_init_fields(vp(np.ascontiguousarray(r["value_probs"], dtype=np.float32)),
+                          vp(np.ascontiguousarray(r["score_probs"], dtype=np.float32)), vp(want))
+        assert abs(float(leaf["value"]) - float(want[0])) <= 1e-6
+        es2 = float(want[2]) + float(want[1]) ** 2
+        assert abs(float(leaf["score_mean"]) - float(want[1])) <= 1e-4 * max(1.0, abs(float(want[1])))
+        assert abs(float(leaf["score_var"]) - float(want[2])) <= 2e-5 * max(1.0, es2)      # fp32 cancellation scale
+        assert abs(float(leaf["err"]) - float(np.sqrt(np.float32(r["err2_outcome"])))) <= 1e-6
+
+    eng.SetResultMode(E.RESULT_LEAF)
+    for b in range(B):
+        eng.LoadBatchSym(b, feats[b], b % 8)
+    eng.RunInference()
+    for b in range(B):
+        check(eng.GetLeaf(b), full[b])
+    with pytest.raises(E.P3Error):
+        eng.GetBatch(0)
+    for bank in (0, 1):
+        for b in range(B):
+            eng.LoadBatchBank(bank, b, feats[bank * B + b], (bank * B + b) % 8)
+        eng.Submit(bank)
+    for bank in (1, 0):
+        eng.Wait(bank)
+        for b in range(B):
+            check(eng.GetLeafBank(bank, b), full[bank * B + b])
+        with pytest.raises(E.P3Error):
+            eng.GetBatchBank(bank, 0)
+    eng.SetResultMode(E.RESULT_FULL)
+    for b in range(B):
+        eng.LoadBatchSym(b, feats[b], b % 8)
+    eng.RunInference()
+    assert _same(eng.GetBatch(3), full[3])
+    with pytest.raises(E.P3Error):
+        eng.GetLeaf(0)
+    eng.close()
+
+
+def test_bank_aux_and_ownership_symmetry(weight_dir, golden_positions):
+    """each slot bank keeps its own auxiliary outputs (ownership, leaf statistics), valid after Wait while the other
+    bank's step has already overwritten the shared step buffer; ownership is un-rotated like the policies (ApplyInverse)."""
+    import ctypes
+    from p3achygo_b200 import engine as E
+    L = oracle_lib.oracle()
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 8
+    feats = golden_positions["feats"][300:300 + 2 * B]
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_FP32)
+    want = []
+    for lo in (0, B):                               # identity orientation, serial: the reference point
+        for b in range(B):
+            eng.LoadBatch(b, feats[lo + b])
+        eng.RunInference()
+        want += [eng.GetAux(b).copy() for b in range(B)]
+    with pytest.raises(E.P3Error):
+        eng.GetAuxBank(0, 0)                        # no submitted run yet
+    for bank in (0, 1):
+        for b in range(B):
+            eng.LoadBatchBank(bank, b, feats[bank * B + b], 0)
+        eng.Submit(bank)
+    eng.Wait(0)
+    eng.Wait(1)                                     # bank 1's step ran last: the shared buffer holds bank 1
+    for bank in (0, 1):
+        for b in range(B):
+            a = eng.GetAuxBank(bank, b)
+            for f in a.dtype.names:
+                assert np.array_equal(np.asarray(a[f]), np.asarray(want[bank * B + b][f])), (bank, b, f)
+            assert np.array_equal(eng.GetOwnershipBank(bank, b), np.asarray(want[bank * B + b]["ownership"]))
+    # ownership under a symmetry: the net sees the rotated board; the result must come back in the game's orientation.
+    # Rotating the input is not bit-neutral for the net, so compare with the host-side route: rotate features on the host,
+    # run with sym = 0, ApplyInverse on the ownership (oracle), against LoadBatchSym + GetOwnership.
+    from p3achygo_b200._lib import GO_FEATURES_DTYPE
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for sym in range(8):
+        f = np.array(feats[sym:sym + 1], dtype=GO_FEATURES_DTYPE)
+        fs = f.copy()
+        for grid in ("board", "stones_atari", "stones_two_liberties", "stones_three_liberties", "stones_laddered"):
+            src = np.ascontiguousarray(f[grid][0], dtype=np.int8)
+            dst = np.zeros(361, dtype=np.int8)
+            L.orc_apply_symmetry_i8(sym, vp(src), vp(dst))
+            fs[grid][0] = dst
+        for k in range(5):
+            i, j = (int(v) for v in f["last_moves"][0][k])
+            if 0 <= i < 19 and 0 <= j < 19:
+                t = L.orc_transform_index(sym, i * 19 + j)
+                fs["last_moves"][0][k] = (t // 19, t % 19)
+        eng.LoadBatch(0, fs[0])
+        eng.LoadBatchSym(1, f[0], sym)
+        eng.RunInference()
+        rot = np.ascontiguousarray(eng.GetOwnership(0), dtype=np.float32)
+        inv = np.zeros(361, dtype=np.float32)
+        L.orc_apply_inverse_f32(sym, vp(rot), vp(inv))
+        assert np.array_equal(eng.GetOwnership(1), inv), sym
+    eng.close()
+
+
+def test_root_sampling_on_resident_logits(weight_dir, golden_positions):
+    """p3_engine_gumbel_topk_bank: Gumbel top-k (cc/mcts/gumbel.cc:283-321) drawn from move_logits that never left HBM equals
+    the oracle fed with the logits GetBatch returns - after a submit (bank copies) and after a serial run."""
+    from p3achygo_b200 import engine as E
+    L = oracle_lib.oracle()
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B, k = 16, 16
+    feats = golden_positions["feats"][400:400 + B]
+    legal = golden_positions["legal"][400:400 + B] if "legal" in golden_positions else None
+    rng = np.random.default_rng(3)
+    if legal is None:
+        legal = (rng.random((B, 362)) < 0.8).astype(np.uint8)
+        legal[:, 361] = 1
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    slots = np.array([5, 0, 15, 7, 7, 3], dtype=np.int32)
+    seeds = [L.orc_prng_seed(900 + i) for i in range(len(slots))]
+    for mode in ("submit", "serial"):
+        if mode == "submit":
+            for b in range(B):
+                eng.LoadBatchBank(1, b, feats[b], 0)
+            eng.Submit(1)
+            eng.Wait(1)
+            res = [eng.GetBatchBank(1, b).copy() for b in range(B)]
+            bank = 1
+        else:
+            for b in range(B):
+                eng.LoadBatch(b, feats[B - 1 - b])
+            eng.RunInference()
+            res = [eng.GetBatch(b).copy() for b in range(B)]
+            bank = 0
+        state = np.array(seeds, dtype=np.uint64)
+        moves, scores, kvalid = eng.GumbelTopKBank(bank, slots, legal[slots], state, 1.0, k)
+        for i, sl in enumerate(slots):
+            om, osc, okv, ost = oracle_lib.gumbel_topk(int(seeds[i]), np.asarray(res[sl]["move_logits"], dtype=np.float32),
+                                                       legal[sl], 1.0, k)
+            kk = min(k, okv)
+            assert kvalid[i] == okv and int(state[i]) == ost
+            assert np.array_equal(moves[i][:kk], om[:kk]) and np.array_equal(scores[i][:kk], osc[:kk]), (mode, i)
+    eng.close()
+
+
+# ---- dynamic range of the fp16 residual stream (ADVICE r1 / VERDICT r1 weak 1) ------------------------------------------------
+def _scaled_family(cfg, base, f_expand):
+    """synthetic_weights with every block's last conv scaled by f_expand: the residual stream grows block by block
+    (b10c128btl3: max |x| 2.3 / 275 / 3.4e3 / 1.9e5 for f = 1 / 8 / 12 / 20, measured with the fp64 oracle)."""
+    from p3achygo_b200 import weights as W
+    t = {k: v.copy() for k, v in base.items()}
+    for name in t:
+        if "/trunk/" in name and name.endswith("conv/kernel"):
+            blk, j = int(name.split("/")[2].split(":")[0]), int(name.split("/")[3].split(":")[0])
+            if j == (2 if "broadcast_res" in name else len(W.block_convs(cfg, blk)) - 1):
+                t[name] *= np.float32(f_expand)
+    return t
+
+
+def test_large_magnitude_trunk_bounded_or_loud(tmp_path, golden_positions):
+    """The tensor engine keeps the residual stream in IEEE fp16 with a saturating pack.  Large but representable trunks
+    (max |x| up to 3.4e3, 1500 x the He-scaled family every other test uses) keep the documented RELATIVE accuracy; a trunk beyond
+    +-65504 is reported by p3_engine_range_check and, in validation mode (P3_RANGE_CHECK=1), makes RunInference fail loudly
+    instead of returning clamped evaluations; the fp32 engine evaluates the same net within its bound."""
+    import os
+    from p3achygo_b200 import engine as E
+    from p3achygo_b200 import weights as W
+    cfg = W.config_from_str("b10c128btl3")
+    base = W.synthetic_weights(cfg, 0)
+    feats = golden_positions["feats"][100:104]
+    for f, expect_sat in ((8.0, False), (12.0, False), (20.0, True)):
+        tensors = _scaled_family(cfg, base, f)
+        path = os.path.join(tmp_path, f"scaled_{int(f)}.p3w")
+        W.save_weights(path, cfg, tensors)
+        o = _oracle_outputs(cfg, tensors, feats, torch.float64)
+        scale = float(np.abs(o["pi_logits"]).max())
+        trunk_max = float(np.abs(o["trunk"]).max())
+        for prec in (E.PRECISION_FP32, E.PRECISION_BF16):
+            eng = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=prec)
+            for b in range(4):
+                eng.LoadBatch(b, feats[b])
+            eng.RunInference()
+            mx, sat = eng.RangeCheck()
+            got = np.stack([np.asarray(eng.GetBatch(b)["move_logits"], dtype=np.float64) for b in range(4)])
+            rel = float(np.abs(got - o["pi_logits"]).max()) / scale
+            print(f"f={f} prec={prec}: oracle trunk max {trunk_max:.3g}, engine stream max {mx:.3g}, saturated {sat}, rel logit err {rel:.2e}")
+            assert mx >= 0.5 * min(trunk_max, 65504.0)            # the scan sees every block, the oracle's number is the last one
+            if prec == E.PRECISION_FP32:
+                assert sat == 0 and rel <= 1e-4                    # fp32 stream: no clamp, 1e-3-class accuracy at any scale
+            elif not expect_sat:
+                assert sat == 0 and rel <= 2e-2                    # documented bf16 bound, relative to the logit scale
+            else:
+                assert sat > 0                                     # the clamp was hit ...
+                os.environ["P3_RANGE_CHECK"] = "1"
+                try:
+                    with pytest.raises(E.P3Error) as ei:           # ... and validation mode refuses to evaluate
+                        eng.RunInference()
+                    assert ei.value.code == E._lib.P3_ERR_UNSUPPORTED and "saturated" in str(ei.value)
+                finally:
+                    del os.environ["P3_RANGE_CHECK"]
+            eng.close()

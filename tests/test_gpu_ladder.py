@@ -352,11 +352,66 @@ def test_root_sampling_from_game_records(games):
     state = np.array(seeds, dtype=np.uint64)
     k = 16
     moves, scores, kvalid = E.gumbel_topk(logits, legal, state, 1.0, k)
-    same = 0
     for i in range(len(idx)):
         om, osc, okv, ost = oracle_lib.gumbel_topk(int(seeds[i]), logits[i], games["legal"][idx[i]], 1.0, k)
         kk = min(k, okv)
         assert kvalid[i] == okv and int(state[i]) == ost                      # same number of draws
-        np.testing.assert_allclose(scores[i][:kk], osc[:kk], rtol=0, atol=4e-6 * max(1.0, float(np.abs(osc[:kk]).max())))
-        same += int(np.array_equal(moves[i][:kk], om[:kk]))
-    assert same >= len(idx) - 1
+        assert np.array_equal(scores[i][:kk], osc[:kk]) and np.array_equal(moves[i][:kk], om[:kk])   # bit-exact
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_slot_reloaded_during_the_copy_is_not_an_error(games, weight_dir):
+    """LoadBatch may overlap RunInference (cc/nn/nn_interface.cc:276).  A game-record slot that is being
+    re-loaded while its bank is copied can reach the GPU torn (move list of one game, length of another) and be rejected by the
+    replay; that slot's result is unread by contract, so the run must NOT fail - while a genuinely impossible record in a
+    stable slot still does (test_engine_rejects_impossible_game_record).  One thread hammers slot 0 with two different games
+    while the main thread runs 400 steps over both submit/wait and the serial call; the other slots' results never change."""
+    import threading
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 8
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    order = np.argsort(games["num_moves"])
+    long_i, short_i = int(order[-1]), int(order[len(order) // 8])
+    recs = [(games["moves"][i][: games["num_moves"][i]].copy(), int(games["colors"][i])) for i in (long_i, short_i)]
+    assert len(recs[0][0]) > 200 and 5 < len(recs[1][0]) < 120
+    stable = [int(i) for i in order[-B:-1]]
+    for bank in (0, 1):
+        eng.LoadGameBank(bank, 0, recs[0][0], recs[0][1], 7.5)
+        for b in range(1, B):
+            i = stable[b - 1]
+            eng.LoadGameBank(bank, b, games["moves"][i][: games["num_moves"][i]], int(games["colors"][i]), 7.5)
+    eng.RunInference()
+    want = [eng.GetBatch(b).copy() for b in range(B)]
+    stop = threading.Event()
+
+    def hammer():
+        k = 0
+        while not stop.is_set():
+            for bank in (0, 1):
+                eng.LoadGameBank(bank, 0, recs[k & 1][0], recs[k & 1][1], 7.5)
+            k += 1
+
+    t = threading.Thread(target=hammer)
+    t.start()
+    try:
+        for it in range(400):
+            if it % 4 == 3:
+                eng.RunInference()
+                got = [eng.GetBatch(b) for b in range(1, B)]
+            else:
+                bank = it & 1
+                eng.Submit(bank)
+                eng.Wait(bank)
+                got = [eng.GetBatchBank(bank, b) for b in range(1, B)]
+            for b in range(1, B):
+                assert all(np.array_equal(got[b - 1][f], want[b][f]) for f in want[b].dtype.names), (it, b)
+    finally:
+        stop.set()
+        t.join()
+    # a stable impossible record is still an error
+    eng.LoadGameBank(0, 0, np.array([5, 5 + E.MOVE_WHITE], dtype=np.int16), 1, 7.5)
+    with pytest.raises(E.P3Error):
+        eng.RunInference()
+    eng.close()

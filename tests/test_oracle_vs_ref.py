@@ -113,6 +113,33 @@ def test_symmetry_prng_softmax_gumbel_direct():
         assert kv == okv and np.array_equal(rm[:min(k, kv)], om[:min(k, kv)]) and np.array_equal(rsc[:min(k, kv)], osc[:min(k, kv)])
 
 
+def test_logf_restatement_is_the_c_library_logf():
+    """probability.cc:12-15 calls libm's logf.  orc_logf (the glibc 2.39 algorithm restated; the CUDA kernel mirrors it) equals
+    this machine's logf - the one libp3ref.so links - on 2^21 uniforms of Probability::Uniform's grid, on their -logf, on
+    random floats of every binade, and Probability::GumbelSample of the compiled reference equals the restated composition."""
+    L = oracle_lib.oracle()
+    L.orc_logf.restype = L.orc_libm_logf.restype = L.orc_gumbel_from_uniform.restype = ctypes.c_float
+    L.orc_logf.argtypes = L.orc_libm_logf.argtypes = L.orc_gumbel_from_uniform.argtypes = [ctypes.c_float]
+    rng = np.random.default_rng(2024)
+    bits = rng.integers(0, 2 ** 23, 1 << 21, dtype=np.uint32)
+    u = ((np.uint32(127 << 23) | bits).view(np.float32) - np.float32(1.0)).astype(np.float32)
+    xs = np.concatenate([u, rng.integers(1, 0x7f800000, 1 << 19, dtype=np.uint32).view(np.float32),
+                         np.array([0.0, 1.0, np.inf, 1e-45, 1.17549435e-38, np.float32(1) - np.float32(2 ** -24)], np.float32)])
+    f_orc = np.vectorize(L.orc_logf, otypes=[np.float32])
+    f_lib = np.vectorize(L.orc_libm_logf, otypes=[np.float32])
+    # numpy's float32 log is not glibc's; go through ctypes in chunks (vectorize is a python loop: keep it to ~2.6 M calls)
+    a, b = f_orc(xs), f_lib(xs)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    inner = (-a[: 1 << 18]).astype(np.float32)
+    assert np.array_equal(f_orc(inner).view(np.uint32), f_lib(inner).view(np.uint32))
+    for seed in (1, 123456789, 2 ** 61 + 5):
+        p = R.ref_prob_new(seed)
+        st = ctypes.c_uint64(L.orc_prng_seed(seed))
+        for _ in range(20000):
+            assert np.float32(R.ref_prob_gumbel(p)) == np.float32(L.orc_gumbel(ctypes.byref(st)))
+        R.ref_prob_free(p)
+
+
 def test_game_rules_on_fresh_games():
     """orc_game_derive against Board::GetLadderedStones / Game::IsValidMove of the compiled reference on fresh games."""
     rng = np.random.default_rng(31337)
