@@ -3,7 +3,9 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <array>
 #include <functional>
+#include <tuple>
 #include <type_traits>
 #include <utility>
 namespace absl {
@@ -27,10 +29,20 @@ struct HasAbslHashValue<T, std::void_t<decltype(AbslHashValue(std::declval<HashS
 inline void Mix(HashState& s, size_t v) {
   s.h ^= v + 0x9e3779b97f4a7c15ull + (s.h << 6) + (s.h >> 2);
 }
+template <typename T> struct IsTuple : std::false_type {};
+template <typename... Ts> struct IsTuple<std::tuple<Ts...>> : std::true_type {};
+template <typename A, typename B> struct IsTuple<std::pair<A, B>> : std::true_type {};
+template <typename T> struct IsStdArray : std::false_type {};
+template <typename T, size_t N> struct IsStdArray<std::array<T, N>> : std::true_type {};
 template <typename T>
 HashState HashOne(HashState s, const T& v) {
   if constexpr (HasAbslHashValue<T>::value) {
     return AbslHashValue(std::move(s), v);
+  } else if constexpr (IsTuple<T>::value) {
+    return std::apply([&](const auto&... e) { return HashState::combine(std::move(s), e...); }, v);
+  } else if constexpr (IsStdArray<T>::value) {
+    for (const auto& e : v) s = HashState::combine(std::move(s), e);
+    return s;
   } else if constexpr (std::is_same_v<T, unsigned __int128>) {
     Mix(s, static_cast<size_t>(v >> 64));
     Mix(s, static_cast<size_t>(v));

@@ -32,14 +32,14 @@ std::unique_ptr<B200Engine> B200Engine::Create(std::string path, int batch_size,
 }
 
 B200Engine::~B200Engine() { p3_engine_destroy(engine_); }
-void B200Engine::LoadBatch(int batch_id, const GoFeatures& features) { P3_CHECK(p3_engine_load_batch(engine_, batch_id, &features)); }
+void B200Engine::LoadBatch(int batch_id, const GoFeatures& features) { P3_CHECK(p3_engine_load_batch(engine_, batch_id, AsC(features))); }
 void B200Engine::LoadBatchSym(int batch_id, const GoFeatures& features, int sym) {
-  P3_CHECK(p3_engine_load_batch_sym(engine_, batch_id, &features, sym));
+  P3_CHECK(p3_engine_load_batch_sym(engine_, batch_id, AsC(features), sym));
 }
 void B200Engine::RunInference() { P3_CHECK(p3_engine_run_inference(engine_)); }
-void B200Engine::GetBatch(int batch_id, NNInferResult& result) { P3_CHECK(p3_engine_get_batch(engine_, batch_id, &result)); }
+void B200Engine::GetBatch(int batch_id, NNInferResult& result) { P3_CHECK(p3_engine_get_batch(engine_, batch_id, AsC(result))); }
 void B200Engine::LoadBatchBank(int bank, int batch_id, const GoFeatures& features, int sym) {
-  P3_CHECK(p3_engine_load_batch_bank(engine_, bank, batch_id, &features, sym));
+  P3_CHECK(p3_engine_load_batch_bank(engine_, bank, batch_id, AsC(features), sym));
 }
 void B200Engine::LoadGameBank(int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi,
                               const int8_t* forbidden, int sym) {
@@ -48,7 +48,7 @@ void B200Engine::LoadGameBank(int bank, int batch_id, const int16_t* moves, int 
 void B200Engine::Submit(int bank) { P3_CHECK(p3_engine_submit(engine_, bank)); }
 void B200Engine::Wait(int bank) { P3_CHECK(p3_engine_wait(engine_, bank)); }
 void B200Engine::GetBatchBank(int bank, int batch_id, NNInferResult& result) {
-  P3_CHECK(p3_engine_get_batch_bank(engine_, bank, batch_id, &result));
+  P3_CHECK(p3_engine_get_batch_bank(engine_, bank, batch_id, AsC(result)));
 }
 void B200Engine::GetOwnershipBank(int bank, int batch_id, std::array<float, P3_NUM_BOARD_LOCS>& own) {
   P3_CHECK(p3_engine_get_ownership_bank(engine_, bank, batch_id, own.data()));
@@ -60,6 +60,7 @@ void B200Engine::GetOwnership(int batch_id, std::array<float, P3_NUM_BOARD_LOCS>
   P3_CHECK(p3_engine_get_ownership(engine_, batch_id, own.data()));
 }
 
+#ifndef P3_REFERENCE_TREE  // the reference tree has its own KindToString (engine.h:45-57) and engine factory (engine_factory.cc)
 std::string KindToString(Engine::Kind kind) {
   switch (kind) {
     case Engine::Kind::kTrt: return "TensorRT";
@@ -107,5 +108,6 @@ std::unique_ptr<Engine> CreateEngine(Engine::Kind kind, std::string path, int ba
       std::abort();
   }
 }
+#endif  // !P3_REFERENCE_TREE
 
 }  // namespace nn

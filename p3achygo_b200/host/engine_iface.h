@@ -12,12 +12,27 @@
 
 #include "p3_b200.h"
 
+#ifdef P3_REFERENCE_TREE
+// Inside the reference tree (oracle/Makefile builds this configuration against the unmodified reference
+// sources): the real nn::Engine / GoFeatures / NNInferResult, with Engine::Kind::kB200 added by edit 1 of INTEGRATION.md.
+#include "cc/nn/engine/engine.h"
+
+namespace nn {
+static_assert(sizeof(GoFeatures) == sizeof(p3_go_features), "nn::GoFeatures and p3_go_features must be the same bytes");
+static_assert(sizeof(NNInferResult) == sizeof(p3_infer_result) && alignof(NNInferResult) == 16, "nn::NNInferResult layout");
+inline const p3_go_features* AsC(const GoFeatures& f) { return reinterpret_cast<const p3_go_features*>(&f); }
+inline p3_infer_result* AsC(NNInferResult& r) { return reinterpret_cast<p3_infer_result*>(&r); }
+}  // namespace nn
+#else
+
 namespace nn {
 
 using GoFeatures = ::p3_go_features;
 using NNInferResult = ::p3_infer_result;
 static_assert(sizeof(GoFeatures) == 1860, "GoFeatures mirror");
 static_assert(sizeof(NNInferResult) == 7568 && alignof(NNInferResult) == 16, "NNInferResult mirror");
+inline const p3_go_features* AsC(const GoFeatures& f) { return &f; }
+inline p3_infer_result* AsC(NNInferResult& r) { return &r; }
 
 class Engine {
  public:
@@ -43,3 +58,4 @@ int GetVersionFromModelPath(std::string path);                                //
 std::unique_ptr<Engine> CreateEngine(Engine::Kind kind, std::string path, int batch_size, int version);  // :56-73
 
 }  // namespace nn
+#endif  // P3_REFERENCE_TREE
