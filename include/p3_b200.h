@@ -229,11 +229,13 @@ int p3_engine_run_device(p3_engine* e, float* ms_total);
  * p3_engine_run_device resident in HBM outside its timed region. */
 int p3_engine_upload(p3_engine* e);
 /* One eager (non-graph) pass with a CUDA event around every launch; accumulates device ms and launch counts
- * per kernel class: [0] encode [1] init conv [2] conv 1x1 [3] conv 3x3 [4] broadcast mix [5] head conv [6] heads.
- * flops[c] = algorithmic FLOPs (2*MAC) those launches performed for the whole batch. */
-#define P3_NUM_KERNEL_CLASSES 7
+ * per kernel class: [0] encode [1] init conv [2] stand-alone conv 1x1 [3] conv 3x3 [4] broadcast mix [5] head conv [6] heads
+ * [7] fused block boundaries (expand 1x1 + residual + next reduce 1x1, chain_tc.cu).
+ * flops[c] = algorithmic FLOPs (2*MAC) those launches performed for the whole batch;
+ * bytes[c] (may be NULL) = algorithmic HBM bytes: every input / output tensor of the launch read / written once. */
+#define P3_NUM_KERNEL_CLASSES 8
 int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
-                      double flops[P3_NUM_KERNEL_CLASSES]);
+                      double flops[P3_NUM_KERNEL_CLASSES], double bytes[P3_NUM_KERNEL_CLASSES]);
 /* Dynamic range of the residual stream for the inputs resident in HBM (one eager pass, a scan after every launch): the tensor
  * engines keep it in IEEE fp16 and pack with cvt.rn.satfinite, so a net whose trunk exceeds +-65504 would be clamped silently.
  * max_abs = largest |x| any block left in the stream, n_saturated = values at the clamp (or NaN).  With env P3_RANGE_CHECK=1

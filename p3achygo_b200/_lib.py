@@ -68,7 +68,7 @@ def _load() -> ctypes.CDLL:
     lib.p3_engine_get_aux.argtypes = [vp, ci, vp]
     lib.p3_engine_run_device.argtypes = [vp, ctypes.POINTER(cf)]
     lib.p3_engine_upload.argtypes = [vp]
-    lib.p3_engine_profile.argtypes = [vp, vp, vp, vp]
+    lib.p3_engine_profile.argtypes = [vp, vp, vp, vp, vp]
     lib.p3_engine_stage_ms.argtypes = [vp, ctypes.POINTER(cf * 3)]
     lib.p3_engine_launches_per_run.argtypes = [vp]
     lib.p3_engine_flops_per_position.argtypes = [vp]

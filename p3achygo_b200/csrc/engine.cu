@@ -1335,24 +1335,27 @@ int p3_engine_upload(p3_engine* e) {
 }
 
 int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launches[P3_NUM_KERNEL_CLASSES],
-                      double flops[P3_NUM_KERNEL_CLASSES]) {
+                      double flops[P3_NUM_KERNEL_CLASSES], double bytes[P3_NUM_KERNEL_CLASSES]) {
   if (!e || !ms || !launches || !flops) return fail(P3_ERR_INVALID_ARG, "profile: bad argument");
   P3_CUDA(cudaSetDevice(e->device));
   const int n_launch = e->launches;
   std::vector<cudaEvent_t> evs(n_launch + 1);
   for (auto& v : evs) P3_CUDA(cudaEventCreate(&v));
   std::vector<int> cls;
-  std::vector<double> fl;
+  std::vector<double> fl, by;
   int idx = 0, rc = P3_OK;
-  const double B = e->batch, Pn = 361.0;
+  const double B = e->batch, Pn = 361.0, R = e->rows;
+  const double esz = e->bf16 ? 2.0 : 4.0, rsz = e->bf16 ? 2.0 : 4.0;  // operand / residual-stream element sizes
   auto rec = [&]() { return cudaEventRecord(evs[idx++], e->stream); };
   P3_CUDA(rec());
   rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
                      e->d_masks.as<uint16_t>(), e->stream, &e->enc_extra);
   cls.push_back(0); fl.push_back(0.0);
+  by.push_back(B * (sizeof(p3_go_features) + 361.0 * e->nplanes * 4 + e->nscalars * 4 + 722 + (e->init_tc ? kMaskPadElems * 2.0 + e->C * 4.0 : 0.0)));
   P3_CUDA(rec());
   if (!rc) rc = e->run_init();
   cls.push_back(1); fl.push_back(2.0 * (25.0 * e->nplanes * e->C * Pn + double(e->nscalars) * e->C) * B);
+  by.push_back(B * (e->init_tc ? kMaskPadElems * 2.0 + e->C * 4.0 : 722.0) + R * e->C * (rsz + esz));
   P3_CUDA(rec());
   for (const Step& s : e->program) {
     if (rc) break;
@@ -1360,41 +1363,51 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
       rc = e->run_conv(s);
       cls.push_back(s.layer->taps == 1 ? 2 : 3);
       fl.push_back(2.0 * s.layer->taps * double(s.layer->cin) * s.layer->cout * Pn * B);
+      by.push_back(R * (s.layer->cin * esz + (s.ep.act_out ? s.layer->cout * esz : 0.0) + (s.ep.residual ? s.layer->cout * rsz : 0.0) +
+                        (s.ep.raw_out ? s.layer->cout * rsz : 0.0)));
     } else if (s.kind == kStepChain) {
       rc = tc_chain_launch(s.cplan, e->stream);
-      cls.push_back(2);
+      cls.push_back(7);
       fl.push_back(2.0 * (double(s.layer->cin) * s.layer->cout + double(s.layer2->cin) * s.layer2->cout) * Pn * B);
+      by.push_back(R * (s.layer->cin * esz + 2.0 * s.layer->cout * rsz + s.layer2->cout * esz));  // t, x in, x' out, next reduce out
     } else {
       rc = e->run_broadcast(s);
       cls.push_back(4); fl.push_back(2.0 * e->C * Pn * Pn * B);
+      by.push_back(R * e->C * 2.0 * esz);
     }
     P3_CUDA(rec());
   }
   if (!rc) rc = e->run_conv(e->head_step);
   cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
+  by.push_back(R * (e->C * (e->bf16 ? esz : 4.0) + 3.0 * e->Ch * 4.0));
   P3_CUDA(rec());
   if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16, e->d_sym.as<int8_t>(), e->d_leaf.as<p3_leaf_result>());
   cls.push_back(6); fl.push_back(0.0);
+  by.push_back(R * 3.0 * e->Ch * 4.0 + B * (sizeof(p3_infer_result) + sizeof(p3_aux_result) + sizeof(p3_leaf_result)));
   P3_CUDA(rec());
   P3_CUDA(cudaStreamSynchronize(e->stream));
-  for (int c = 0; c < P3_NUM_KERNEL_CLASSES; ++c) { ms[c] = 0.0f; launches[c] = 0; flops[c] = 0.0; }
+  for (int c = 0; c < P3_NUM_KERNEL_CLASSES; ++c) {
+    ms[c] = 0.0f; launches[c] = 0; flops[c] = 0.0;
+    if (bytes) bytes[c] = 0.0;
+  }
   for (size_t i = 0; i < cls.size() && !rc; ++i) {
     float t = 0.0f;
     cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
     ms[cls[i]] += t;
     launches[cls[i]] += 1;
     flops[cls[i]] += fl[i];
+    if (bytes) bytes[cls[i]] += by[i];
     if (std::getenv("P3_PROFILE_VERBOSE")) {  // per-launch listing (perf work)
       const Step* st = (i >= 2 && i - 2 < e->program.size()) ? &e->program[i - 2] : nullptr;
       if (st && st->kind == kStepChain)
-        std::fprintf(stderr, "[p3 profile] #%zu class %d chain %d -> %d (+res) -> %d: %.1f us\n", i, cls[i], st->layer->cin,
-                     st->layer->cout, st->layer2->cout, t * 1e3f);
+        std::fprintf(stderr, "[p3 profile] #%zu class %d chain %d -> %d (+res) -> %d: %.1f us, %.0f MB\n", i, cls[i], st->layer->cin,
+                     st->layer->cout, st->layer2->cout, t * 1e3f, by[i] / 1e6);
       else if (st && st->kind == kStepConv)
-        std::fprintf(stderr, "[p3 profile] #%zu class %d conv taps=%d cin=%d cout=%d res=%d raw=%d act=%d: %.1f us\n", i, cls[i],
+        std::fprintf(stderr, "[p3 profile] #%zu class %d conv taps=%d cin=%d cout=%d res=%d raw=%d act=%d: %.1f us, %.0f MB\n", i, cls[i],
                      st->layer->taps, st->layer->cin, st->layer->cout, st->ep.residual != nullptr, st->ep.raw_out != nullptr,
-                     st->ep.act_out != nullptr, t * 1e3f);
+                     st->ep.act_out != nullptr, t * 1e3f, by[i] / 1e6);
       else
-        std::fprintf(stderr, "[p3 profile] #%zu class %d: %.1f us\n", i, cls[i], t * 1e3f);
+        std::fprintf(stderr, "[p3 profile] #%zu class %d: %.1f us, %.0f MB\n", i, cls[i], t * 1e3f, by[i] / 1e6);
     }
   }
   for (auto& v : evs) cudaEventDestroy(v);

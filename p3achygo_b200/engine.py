@@ -203,15 +203,17 @@ class B200Engine:
     def Upload(self) -> None:
         check(lib.p3_engine_upload(self._h))
 
-    KERNEL_CLASSES = ["encode", "init_conv", "conv1x1", "conv3x3", "broadcast", "head_conv", "heads"]
+    KERNEL_CLASSES = ["encode", "init_conv", "conv1x1", "conv3x3", "broadcast", "head_conv", "heads", "boundary"]
 
     def Profile(self):
-        """One eager pass with an event around every launch -> {class: (ms, launches, flops)}."""
-        ms = np.zeros(7, dtype=np.float32)
-        launches = np.zeros(7, dtype=np.int32)
-        flops = np.zeros(7, dtype=np.float64)
-        check(lib.p3_engine_profile(self._h, ptr(ms), ptr(launches), ptr(flops)))
-        return {k: (float(ms[i]), int(launches[i]), float(flops[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        """One eager pass with an event around every launch -> {class: (ms, launches, flops, algorithmic HBM bytes)}."""
+        n = len(self.KERNEL_CLASSES)
+        ms = np.zeros(n, dtype=np.float32)
+        launches = np.zeros(n, dtype=np.int32)
+        flops = np.zeros(n, dtype=np.float64)
+        nbytes = np.zeros(n, dtype=np.float64)
+        check(lib.p3_engine_profile(self._h, ptr(ms), ptr(launches), ptr(flops), ptr(nbytes)))
+        return {k: (float(ms[i]), int(launches[i]), float(flops[i]), float(nbytes[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def RangeCheck(self):
         """(max |x| of the residual stream over all blocks, number of values at the fp16 clamp) for the resident inputs."""

@@ -135,7 +135,15 @@ int p3_host_benchmark(const char* weights_path, int device, int batch, int versi
 // num_moves, colours; komi 7.5), so the board, the liberty grids and the laddered stones are derived on the GPU inside the step.
 static int pipelined_cycle(const char* weights_path, int device, int batch, int version, int precision,
                            const p3_go_features* positions, const int16_t* games, const int32_t* num_moves, const int8_t* colors,
-                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out);
+                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out, bool leaf = false);
+
+// The pipelined cycle with compact leaf records (P3_RESULT_LEAF): GetLeafBank x B reads 4360 B per slot - what
+// mcts::LeafEvaluator's InitFields keeps of an NNInferResult - and only those cross PCIe.
+int p3_host_benchmark_pipelined_leaf(const char* weights_path, int device, int batch, int version, int precision,
+                                     const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
+  return pipelined_cycle(weights_path, device, batch, version, precision, positions, nullptr, nullptr, nullptr, 0, n_positions, warmup,
+                         steps, threads, out, true);
+}
 
 int p3_host_benchmark_pipelined(const char* weights_path, int device, int batch, int version, int precision,
                                 const p3_go_features* positions, int n_positions, int warmup, int steps, int threads, double* out) {
@@ -152,9 +160,11 @@ int p3_host_benchmark_games(const char* weights_path, int device, int batch, int
 
 static int pipelined_cycle(const char* weights_path, int device, int batch, int version, int precision,
                            const p3_go_features* positions, const int16_t* games, const int32_t* num_moves, const int8_t* colors,
-                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out) {
+                           int max_moves, int n_positions, int warmup, int steps, int threads, double* out, bool leaf) {
   auto engine = nn::B200Engine::Create(weights_path, batch, version, device, precision);
-  std::vector<nn::NNInferResult> results(batch);
+  engine->SetLeafResults(leaf);
+  std::vector<nn::NNInferResult> results(leaf ? 0 : batch);
+  std::vector<p3_leaf_result> leaves(leaf ? batch : 0);
   WorkerPool pool(threads);
   double t_load = 0, t_get = 0, t_wait = 0, checksum = 0;
   int cursor = 0;
@@ -192,10 +202,11 @@ static int pipelined_cycle(const char* weights_path, int device, int batch, int 
     engine->Wait(cur);
     t_wait += us_since(w0);
     auto g0 = Clock::now();
-    pool.run(batch, [&](int b) { engine->GetBatchBank(cur, b, results[b]); });
+    if (leaf) pool.run(batch, [&](int b) { engine->GetLeafBank(cur, b, leaves[b]); });
+    else pool.run(batch, [&](int b) { engine->GetBatchBank(cur, b, results[b]); });
     t_get += us_since(g0);
     if (it >= warmup)
-      for (int b = 0; b < batch; ++b) checksum += results[b].value_probs[1];
+      for (int b = 0; b < batch; ++b) checksum += leaf ? leaves[b].value : results[b].value_probs[1];
   }
   const double total_us = us_since(t_start);
   out[0] = total_us / steps;
