@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default=CONFIG)
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -334,7 +334,7 @@ def main():
     wpath = os.path.join(tmpdir, f"{args.config}.p3w")
     tensors = W.synthetic_weights(cfg, 0)
     W.save_weights(wpath, cfg, tensors)
-    precision = E.PRECISION_BF16 if args.precision == "bf16" else E.PRECISION_FP32
+    precision = {"bf16": E.PRECISION_BF16, "fp16": E.PRECISION_FP16, "fp32": E.PRECISION_FP32}[args.precision]
     eng = E.CreateEngine(E.KindFromEnginePath(wpath), wpath, B, 1, precision=precision, device=local)
 
     def stage_batch(i: int):

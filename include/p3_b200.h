@@ -53,7 +53,10 @@ enum {
 /* Arithmetic the tower runs in.  Both accumulate in fp32. */
 enum {
   P3_PRECISION_FP32 = 0,  /* fp32 operands, CUDA-core FFMA: parity mode (max-abs 1e-3 vs fp32 oracle) */
-  P3_PRECISION_BF16 = 1   /* bf16 operands, tcgen05.mma with fp32 TMEM accumulators: throughput mode   */
+  P3_PRECISION_BF16 = 1,  /* bf16 operands, tcgen05.mma with fp32 TMEM accumulators: throughput mode   */
+  P3_PRECISION_FP16 = 2   /* IEEE fp16 operands (tcgen05.mma kind::f16, same rate as bf16), fp32 accumulators: the reference's
+                             production precision (whole-graph fp16, python/rl_loop/model_utils.py:181) with 3 more mantissa bits
+                             than bf16; activations and weights beyond +-65504 saturate (p3_engine_range_check) */
 };
 
 /* ---- POD mirrors of the reference structs ------------------------------------------------ */

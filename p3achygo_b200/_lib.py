@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("P3_LIB") or os.path.join(_HERE, "libp3b200.so")
 
 from .layout import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, LEAF_RESULT_DTYPE, NUM_LOCS, NUM_MOVES,  # noqa: F401
                      P3_ERR_CUDA, P3_ERR_INVALID_ARG, P3_ERR_IO, P3_ERR_NO_DEVICE, P3_ERR_UNSUPPORTED, P3_OK, PRECISION_BF16,
-                     PRECISION_FP32, RESULT_FULL, RESULT_LEAF, GoFeatures, Loc)
+                     PRECISION_FP16, PRECISION_FP32, RESULT_FULL, RESULT_LEAF, GoFeatures, Loc)
 
 
 class P3Error(RuntimeError):

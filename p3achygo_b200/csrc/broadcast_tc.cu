@@ -44,7 +44,7 @@ constexpr int kBFixedSmem = (4 * kBBoxes + 1) * kBBoxBytes + 1024 /*align*/ + 51
 
 struct TcBcastPlan {
   CUtensorMap map_wt, map_x, map_act, map_halo;
-  int B, C, n_tile, stages, tmem_cols, grid;
+  int B, C, n_tile, stages, tmem_cols, grid, f16 = 0;
   size_t smem_bytes;
   const float *bias_pad, *scale, *shift;
   void* wt_dev = nullptr;
@@ -82,7 +82,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
                     const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_halo, int B, int C,
                     int n_tile, int stages, int tmem_cols,
                     const float* __restrict__ bias_pad, const float* __restrict__ scale,
-                    const float* __restrict__ shift) {
+                    const float* __restrict__ shift, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_box = smem;                                  // [4 quarters][kBBoxes] output boxes, then one zero box
@@ -172,7 +172,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
     }
   } else if (warp == 1) {
     // A K-major, B MN-major (bit 16)
-    const uint32_t idesc = ptx::make_idesc_bf16(kBM, n_tile) | (1u << 16);
+    const uint32_t idesc = ptx::make_idesc_op(kBM, n_tile, f16) | (1u << 16);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
@@ -269,8 +269,8 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
         for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + bq;
         bn_mish8(x, a, sc, sh, col);
         bn_mish8(x + 8, a + 8, sc, sh, col + 8);
-        uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
-        uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+        uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+        uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
         if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // halo rows / columns of the layout stay zero
         const uint32_t ob = s % kBBoxes;
         ptx::mbar_wait(&my_ready[ob], ((s / kBBoxes) & 1u) ^ 1u);
@@ -319,23 +319,28 @@ bool tc_broadcast_supported(int C) { return C % 64 == 0 && pick_bcast_n(C) > 0; 
 
 // w [361][361] fp32 (Keras Dense kernel: [in p][out q]), bias [361]: HOST pointers. x / act_out: device bf16 [B*400, C].
 int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const void* x, void* act_out, int B, int C,
-                             const float* scale, const float* shift, TcBcastPlan** out) {
+                             const float* scale, const float* shift, TcBcastPlan** out, bool op_f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(P3_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!tc_broadcast_supported(C)) return fail(P3_ERR_UNSUPPORTED, "tc_broadcast: C % 64 != 0");
   TcBcastPlan* p = new TcBcastPlan();
+  p->f16 = op_f16 ? 1 : 0;
   p->B = B;
   p->C = C;
   p->scale = scale;
   p->shift = shift;
   p->n_tile = pick_bcast_n(C);
   // W^T in the padded board-row space: wt[q_pad][p_pad] = w[p][q]; halo rows / cols and padding are zero
-  std::vector<__nv_bfloat16> wt(static_cast<size_t>(kBMTotal) * kBKTotal, __float2bfloat16(0.0f));
+  std::vector<uint16_t> wt(static_cast<size_t>(kBMTotal) * kBKTotal, 0);  // 16-bit operand words (bf16 or fp16; zero is zero in both)
+  auto to_op = [&](float v) -> uint16_t {
+    if (op_f16) { const __half h = __float2half_rn(v); return *reinterpret_cast<const uint16_t*>(&h); }
+    const __nv_bfloat16 h = __float2bfloat16(v); return *reinterpret_cast<const uint16_t*>(&h);
+  };
   std::vector<float> bias_pad(kBMTotal, 0.0f);
   for (int q = 0; q < 361; ++q) {
     const int qp = board_row(q);
     bias_pad[qp] = bias_host[q];
-    for (int pt = 0; pt < 361; ++pt) wt[static_cast<size_t>(qp) * kBKTotal + board_row(pt)] = __float2bfloat16(w_host[pt * 361 + q]);
+    for (int pt = 0; pt < 361; ++pt) wt[static_cast<size_t>(qp) * kBKTotal + board_row(pt)] = to_op(w_host[pt * 361 + q]);
   }
   if (cudaMalloc(&p->wt_dev, wt.size() * 2) != cudaSuccess || cudaMalloc(&p->bias_dev, bias_pad.size() * 4) != cudaSuccess) {
     delete p;
@@ -413,7 +418,7 @@ void tc_broadcast_plan_destroy(TcBcastPlan* p) {
 
 int tc_broadcast_launch(const TcBcastPlan* p, cudaStream_t stream) {
   tc_broadcast_kernel<<<p->grid, kBThreads, p->smem_bytes, stream>>>(p->map_wt, p->map_x, p->map_act, p->map_halo, p->B, p->C, p->n_tile,
-                                                                     p->stages, p->tmem_cols, p->bias_pad, p->scale, p->shift);
+                                                                     p->stages, p->tmem_cols, p->bias_pad, p->scale, p->shift, p->f16);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

@@ -45,6 +45,7 @@ struct TcChainPlan {
   size_t smem_bytes = 0;
   const float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
   int act2_mode = kActMishBN;
+  int f16 = 0;                          // operands are IEEE fp16 instead of bf16 (P3_PRECISION_FP16)
   unsigned long long* trace = nullptr;  // P3_TC_TRACE
 };
 
@@ -69,7 +70,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                      const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_out2, int rows, int k1,
                      int n1, int n2, int acc2_stages, int a1_stages, int n_boxes, int tmem_cols, const float* __restrict__ scale1,
                      const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
-                     int act2_mode, unsigned long long* trace) {
+                     int act2_mode, unsigned long long* trace, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n1_slabs = n1 / 64, n2_slabs = n2 / 64;
@@ -182,7 +183,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   } else if (warp == 1) {
     if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
-      const uint32_t idesc1 = ptx::make_idesc_bf16(256, n1), idesc2 = ptx::make_idesc_bf16(256, n2);
+      const uint32_t idesc1 = ptx::make_idesc_op(256, n1, f16), idesc2 = ptx::make_idesc_op(256, n2, f16);
       const uint32_t w1_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_w1)), w2_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_w2));
       const uint32_t a1_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a1)), a2_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a2));
       ptx::mbar_wait_cluster(w_bar, 0);
@@ -390,8 +391,8 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           const uint4 r1 = make_uint4(tc_pack_f16(x[8], x[9]), tc_pack_f16(x[10], x[11]), tc_pack_f16(x[12], x[13]), tc_pack_f16(x[14], x[15]));
           float a[16];
           bn_mish16(x, a, sc1, sh1, col);
-          const uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
-          const uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+          const uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+          const uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
           // A2 slot free: the MMAs that read its previous slab have completed.  x' replaces the residual in place.
           const uint32_t slot = g & 1u;
           if (tr) t[3] = clock64() + (p0.x & 0);
@@ -451,8 +452,8 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
             bn_mish16(x, a, sc2, sh2, col);
           }
-          uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
-          uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+          uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+          uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
           if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
           ptx::mbar_wait(&my_ready[ob], ob_phase);
           const uint32_t obuf = box_base + ob * kChBoxBytes;
@@ -501,7 +502,7 @@ bool tc_chain_supported(int k1, int n1, int n2) {
 
 int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
                          int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
-                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out) {
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16) {
   if (!tc_chain_supported(k1, n1, n2)) return fail(P3_ERR_UNSUPPORTED, "tc_chain: shape not supported");
   if (!in || !w1 || !w2 || !residual_f16 || !raw_f16 || !scale1 || !shift1 || !out2)
     return fail(P3_ERR_INVALID_ARG, "tc_chain: null argument");
@@ -515,6 +516,7 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
   p->scale2 = scale2;
   p->shift2 = shift2;
   p->act2_mode = act2_mode;
+  p->f16 = op_f16 ? 1 : 0;
   p->acc2_stages = (512 - n1) / n2 >= 2 ? 2 : 1;
   p->tmem_cols = 512;
   {  // split what is left of shared memory between the A1 ring (up to one tile) and the box pool (up to 5 per quarter)
@@ -598,7 +600,7 @@ int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
   P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
                         p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->a1_stages, p->n_boxes, p->tmem_cols, p->scale1, p->shift1, p->scale2,
-                        p->shift2, p->act2_mode, p->trace));
+                        p->shift2, p->act2_mode, p->trace, p->f16));
   return P3_OK;
 }
 

@@ -64,6 +64,7 @@ struct ConvEpilogue {
   const float* scale = nullptr;     // [cout] next layer's folded BN (kActMishBN)
   const float* shift = nullptr;
   int act_mode = kActNone;
+  bool op_f16 = false;              // tensor path: operands (input, weights, act_out) are IEEE fp16 instead of bf16
 };
 
 // ---- fp32 CUDA-core path (conv_fp32.cu) ------------------------------------------------------
@@ -85,7 +86,7 @@ struct TcChainPlan;
 bool tc_chain_supported(int k1, int n1, int n2);
 int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
                          int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
-                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out);
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16 = false);
 void tc_chain_plan_destroy(TcChainPlan* p);
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
 
@@ -154,7 +155,8 @@ int init_conv_smem_launch(const uint16_t* masks, const float* scalars, int n, in
 bool init_tc_supported(int nplanes, int nscalars, int C);
 struct InitTcPlan;
 int init_tc_plan_create(const uint16_t* masks_padded, const float* gs, int n, int C, const __nv_bfloat16* w_packed,
-                        __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTcPlan** out);
+                        __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTcPlan** out,
+                        bool op_f16 = false);
 void init_tc_plan_destroy(InitTcPlan* p);
 int init_tc_launch(const InitTcPlan* p, cudaStream_t stream);
 
@@ -167,7 +169,7 @@ int broadcast_launch(const void* x, const float* w, const float* bias, int n, in
 struct TcBcastPlan;
 bool tc_broadcast_supported(int C);
 int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const void* x, void* act_out, int B, int C,
-                             const float* scale, const float* shift, TcBcastPlan** out);
+                             const float* scale, const float* shift, TcBcastPlan** out, bool op_f16 = false);
 void tc_broadcast_plan_destroy(TcBcastPlan* p);
 int tc_broadcast_launch(const TcBcastPlan* p, cudaStream_t stream);
 

@@ -82,10 +82,13 @@ struct TcConvPlan {
 
 namespace {
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+__device__ __forceinline__ uint32_t pack_bf16_only(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16(float a, float b);
+// activated operand pair in the engine's operand format (bf16, or IEEE fp16 for P3_PRECISION_FP16)
+__device__ __forceinline__ uint32_t pack_act(float a, float b, int f16) { return f16 ? pack_f16(a, b) : pack_bf16_only(a, b); }
 
 // two floats -> packed IEEE fp16 pair, saturating to +-65504 (the residual stream never overflows to inf)
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
@@ -109,7 +112,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                const __grid_constant__ CUtensorMap map_act, int rows, int cin, int cout, int taps, TcTaps tap, int n_tile,
                int stages, int tmem_cols, int has_res, int has_raw, int has_act, const float* __restrict__ scale,
-               const float* __restrict__ shift, int act_mode, int raw_f16, int raw_t, int debug, unsigned long long* trace) {
+               const float* __restrict__ shift, int act_mode, int raw_f16, int raw_t, int debug, unsigned long long* trace, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [staging: residual x4 | raw x2 | act x2, each only if used] | [ring: stages x (A 16 KB | B n_tile*128 B)] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -194,7 +197,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer: warp-converged loop, tcgen05.mma / commit issued by one elected lane =====
     {
-      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, n_tile);
+      const uint32_t idesc = ptx::make_idesc_op(kTileM, n_tile, f16);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -351,8 +354,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = live ? a[j] : 0.0f;
           }
-          pk0 = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
-          pk1 = make_uint4(pack_bf16(a[8], a[9]), pack_bf16(a[10], a[11]), pack_bf16(a[12], a[13]), pack_bf16(a[14], a[15]));
+          pk0 = make_uint4(pack_act(a[0], a[1], f16), pack_act(a[2], a[3], f16), pack_act(a[4], a[5], f16), pack_act(a[6], a[7], f16));
+          pk1 = make_uint4(pack_act(a[8], a[9], f16), pack_act(a[10], a[11], f16), pack_act(a[12], a[13], f16), pack_act(a[14], a[15], f16));
         }
 
         // group staging free? (the group's previous bulk stores have read it) and everyone is done with my_res[buf]
@@ -455,7 +458,7 @@ constexpr int kResThreads = 64 + kResEpiWarps * 32;  // 576
 __global__ void __launch_bounds__(kResThreads, 1)
 tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
                       int cin, int cout, TcTaps tap, __nv_bfloat16* __restrict__ act_out,
-                      const float* __restrict__ scale, const float* __restrict__ shift, int act_mode, int debug) {
+                      const float* __restrict__ scale, const float* __restrict__ shift, int act_mode, int debug, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k_slabs = cin / kSlabK;
@@ -533,7 +536,7 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp == 1) {
     {
-      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kResN);
+      const uint32_t idesc = ptx::make_idesc_op(kTileM, kResN, f16);
       const uint32_t w_lo_base = ptx::desc_lo_sw128(ptx::smem_u32(smem_w));
       const uint32_t w_tap_stride = static_cast<uint32_t>(k_slabs) * (kResWSlabBytes / 16);
       uint32_t tap_lo[9];
@@ -623,7 +626,7 @@ tc_conv3x3_res_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             a0 = mish_f32<false>(fmaf(a0, sc[2 * i], sh[2 * i]));
             a1 = mish_f32<false>(fmaf(a1, sc[2 * i + 1], sh[2 * i + 1]));
           }
-          packed[i] = pack_bf16(live ? a0 : 0.0f, live ? a1 : 0.0f);
+          packed[i] = pack_act(live ? a0 : 0.0f, live ? a1 : 0.0f, f16);
         }
         uint4* ap = reinterpret_cast<uint4*>(act_out + static_cast<size_t>(m) * cout + nb);
         if (!(debug & 8) || packed[0] == 0x12345678u) {  // ablation bit 3: no stores
@@ -672,7 +675,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                        int cin, int cout, int n_half, int stages, int staged, int tmem_cols, TcTaps tap,
                        __nv_bfloat16* __restrict__ act_out, const float* __restrict__ scale,
                        const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace,
-                       const __half* res, __half* raw) {
+                       const __half* res, __half* raw, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // P3_TC_TRACE: globaltimer stamps of CTA 0 (ns since its first instruction), summed over launches
@@ -775,7 +778,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   } else if (warp == 1) {
     if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
-      const uint32_t idesc = ptx::make_idesc_bf16(2 * kTileM, N);
+      const uint32_t idesc = ptx::make_idesc_op(2 * kTileM, N, f16);
       const uint32_t w_lo_base = ptx::desc_lo_sw128(ptx::smem_u32(smem_w));
       const uint32_t w_slab16 = static_cast<uint32_t>(w_slab_bytes / 16);
       const uint32_t w_tap_stride = static_cast<uint32_t>(k_slabs) * w_slab16;
@@ -903,7 +906,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const float x = __uint_as_float(v[g * 8 + i]);
             a[i] = (act_mode == kActIdentity || (debug & 16)) ? x : mish_f32<false>(fmaf(x, sc[i], sh[i]));
           }
-          const uint4 q = make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+          const uint4 q = make_uint4(pack_act(a[0], a[1], f16), pack_act(a[2], a[3], f16), pack_act(a[4], a[5], f16), pack_act(a[6], a[7], f16));
           pk[g] = live ? q : make_uint4(0, 0, 0, 0);  // padding rows / columns of the layout stay zero
         }
         if (staged) {
@@ -995,7 +998,7 @@ int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_
 
 typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int,
                              int, int, int, TcTaps, __nv_bfloat16*,
-                             const float*, const float*, int, int, unsigned long long*, const __half*, __half*);
+                             const float*, const float*, int, int, unsigned long long*, const __half*, __half*, int);
 PairKernelFn pair_kernel_for(int N, bool res = false) {
   switch (N) {
     case 128: return res ? tc_conv3x3_pair_kernel<32, true> : tc_conv3x3_pair_kernel<32, false>;
@@ -1196,16 +1199,18 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
     P3_CUDA(tc_launch_pdl(pair_kernel_for(p->n_tile, with_res), p->grid, kPairThreads, p->smem_bytes, stream, p->map_a, p->map_w,
                           p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0, p->tmem_cols,
                           p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff,
-                          p->trace, reinterpret_cast<const __half*>(ep.residual), reinterpret_cast<__half*>(ep.raw_out)));
+                          p->trace, reinterpret_cast<const __half*>(ep.residual), reinterpret_cast<__half*>(ep.raw_out),
+                          ep.op_f16 ? 1 : 0));
   } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,
-        ep.shift, ep.act_mode, p->debug & 0xff);
+        ep.shift, ep.act_mode, p->debug & 0xff, ep.op_f16 ? 1 : 0);
   } else {
     tc_conv_kernel<<<p->grid, kNumThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->map_res, p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->taps, p->tap, p->n_tile,
         p->stages, p->tmem_cols, ep.residual != nullptr && !(p->debug & 32), ep.raw_out != nullptr, ep.act_out != nullptr,
-        ep.scale, ep.shift, ep.act_mode, ep.raw_f16 ? 1 : 0, (ep.raw_transposed && !ep.raw_f16) ? 1 : 0, p->debug >> 8, p->trace);
+        ep.scale, ep.shift, ep.act_mode, ep.raw_f16 ? 1 : 0, (ep.raw_transposed && !ep.raw_f16) ? 1 : 0, p->debug >> 8, p->trace,
+        ep.op_f16 ? 1 : 0);
   }
   P3_CUDA(cudaGetLastError());
   return P3_OK;

@@ -25,7 +25,7 @@
 #include "weights_file.h"
 
 namespace p3 {
-int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out);  // init_tc.cu
+int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out, bool op_f16);  // init_tc.cu
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -73,6 +73,13 @@ int upload_bf16(DevBuf& buf, const std::vector<float>& v) {
   std::vector<__nv_bfloat16> h(v.size());
   for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
   return upload(buf, h.data(), h.size() * sizeof(__nv_bfloat16));
+}
+// 16-bit tensor-core operands: bf16, or IEEE fp16 (P3_PRECISION_FP16; values beyond +-65504 saturate like the activations do)
+int upload_op16(DevBuf& buf, const std::vector<float>& v, bool f16) {
+  if (!f16) return upload_bf16(buf, v);
+  std::vector<__half> h(v.size());
+  for (size_t i = 0; i < v.size(); ++i) h[i] = __float2half_rn(std::min(std::max(v[i], -65504.0f), 65504.0f));
+  return upload(buf, h.data(), h.size() * sizeof(__half));
 }
 
 // conv kernel OIHW [cout][cin][k][k] -> tap-major copies; tap = i*k + j <-> (dy, dx) = (i - k/2, j - k/2)
@@ -134,7 +141,8 @@ using namespace p3;
 struct p3_engine {
   std::string path;
   int device = 0, batch = 0, version = 1, precision = P3_PRECISION_FP32;
-  bool bf16 = false;
+  bool bf16 = false;  // tensor-core path (16-bit operands: bf16, or fp16 when `f16`)
+  bool f16 = false;   // P3_PRECISION_FP16: the operands are IEEE fp16
   int C = 0, Cb = 0, Ch = 0, Cv = 0, blocks = 0, nplanes = 15, nscalars = 8;
   double flops_per_pos = 0.0;
   int rows = 0;
@@ -468,7 +476,7 @@ struct Builder {
     L->tap_off = tap_offsets(L->ksize);
     std::vector<float> tkn, tnk;
     conv_repack(w, tkn, tnk);
-    int r = e.bf16 ? upload_bf16(L->w_bf16, tnk) : upload_f32(L->w_f32, tkn);
+    int r = e.bf16 ? upload_op16(L->w_bf16, tnk, e.f16) : upload_f32(L->w_f32, tkn);
     if (r) { *rc = r; return L; }
     if (!bn_tag.empty()) {
       std::vector<float> sc, sh;
@@ -612,13 +620,13 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
         for (int t = 0; t < 25; ++t) wt[(static_cast<size_t>(t) * P + c) * C + o] = w->data[(static_cast<size_t>(o) * P + c) * 25 + t];
     if ((rc = upload_f32(e.init_wt, wt)) || (rc = upload_f32(e.gs_w, gw->data)) || (rc = upload_f32(e.gs_b, gb->data))) return rc;
     const char* env_ic = std::getenv("P3_INIT_SMEM");
-    e.init_smem = e.bf16 && init_conv_smem_supported(P, C) && !(env_ic && std::atoi(env_ic) == 0);
-    if (e.init_smem && (rc = upload_bf16(e.init_wt_bf16, wt))) return rc;
+    e.init_smem = e.bf16 && !e.f16 && init_conv_smem_supported(P, C) && !(env_ic && std::atoi(env_ic) == 0);
+    if (e.init_smem && (rc = upload_bf16(e.init_wt_bf16, wt))) return rc;  // (CUDA-core fallback of the first layer: bf16 table)
     const char* env_it = std::getenv("P3_INIT_TC");
     e.init_tc = e.bf16 && init_tc_supported(P, e.nscalars, C) && !(env_it && std::atoi(env_it) == 0);
     if (e.init_tc) {
       std::vector<__nv_bfloat16> packed;
-      init_tc_pack_weights(wt.data(), P, C, packed);
+      init_tc_pack_weights(wt.data(), P, C, packed, e.f16);
       if ((rc = upload(e.init_wt_tc, packed.data(), packed.size() * sizeof(__nv_bfloat16)))) return rc;
       if ((rc = e.d_masks_pad.alloc(sizeof(uint16_t) * B * kMaskPadElems)) || (rc = e.d_gs.alloc(sizeof(float) * B * C))) return rc;
       P3_CUDA(cudaMemset(e.d_masks_pad.p, 0, e.d_masks_pad.bytes));  // the grid borders stay zero for the engine's lifetime
@@ -628,6 +636,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       e.enc_extra.C = C;
       e.enc_extra.gs_out = e.d_gs.as<float>();
     }
+    if (e.f16 && !e.init_tc)
+      return fail(P3_ERR_UNSUPPORTED, "P3_PRECISION_FP16 needs the tensor-core first layer (15/13 input planes, channels % 64 == 0, P3_INIT_TC not 0)");
   }
   {
     std::vector<float> ones(std::max(C, 3 * Ch), 1.0f), zeros(std::max(C, 3 * Ch), 0.0f);
@@ -694,7 +704,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   e.first_shift = blocks[0].convs[0]->in_shift.as<float>();
   if (e.init_tc && (rc = init_tc_plan_create(e.d_masks_pad.as<uint16_t>(), e.d_gs.as<float>(), B, C,
                                              e.init_wt_tc.as<__nv_bfloat16>(), e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(),
-                                             e.first_scale, e.first_shift, &e.init_plan)))
+                                             e.first_scale, e.first_shift, &e.init_plan, e.f16)))
     return rc;
   const char* env_pw = std::getenv("P3_TC_PW");
   const bool pw_enabled = !(env_pw && std::atoi(env_pw) == 0);
@@ -709,6 +719,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.ep.raw_f16 = e.bf16 && (residual != nullptr || raw != nullptr);
     s.ep.act_out = act;
     s.ep.act_mode = mode;
+    s.ep.op_f16 = e.f16;
     if (mode == kActMishBN) {
       s.ep.scale = next->in_scale.as<float>();
       s.ep.shift = next->in_shift.as<float>();
@@ -760,9 +771,11 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
       s.b_scale = bk.convs[1]->in_scale.as<float>();
       s.b_shift = bk.convs[1]->in_shift.as<float>();
       const char* env_tb = std::getenv("P3_TC_BROADCAST");
+      if (e.f16 && (!tc_broadcast_supported(C) || (env_tb && std::atoi(env_tb) == 0)))
+        return fail(P3_ERR_UNSUPPORTED, "P3_PRECISION_FP16 needs the tensor-core broadcast mix");
       if (e.bf16 && tc_broadcast_supported(C) && !(env_tb && std::atoi(env_tb) == 0)) {
         if ((rc = tc_broadcast_plan_create(bk.bw_host->data.data(), bk.bb_host->data.data(), t0, t1, B, C, s.b_scale,
-                                           s.b_shift, &s.bplan)))
+                                           s.b_shift, &s.bplan, e.f16)))
           return rc;
       }
       e.program.push_back(s);
@@ -780,7 +793,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
         if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(t1), c2->w_bf16.as<__nv_bfloat16>(),
                                        nr->w_bf16.as<__nv_bfloat16>(), e.rows, c2->cin, c2->cout, nr->cout, e.xraw.p, e.xraw.p,
                                        nr->in_scale.as<float>(), nr->in_shift.as<float>(), e.actS0.p, n2->in_scale.as<float>(),
-                                       n2->in_shift.as<float>(), kActMishBN, &cs.cplan)))
+                                       n2->in_shift.as<float>(), kActMishBN, &cs.cplan, e.f16)))
           return rc;
         e.program.push_back(cs);
         chain_out = e.actS0.p;
@@ -818,7 +831,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
         if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(s0), ex->w_bf16.as<__nv_bfloat16>(),
                                        nr->w_bf16.as<__nv_bfloat16>(), e.rows, ex->cin, ex->cout, nr->cout, e.xraw.p, e.xraw.p,
                                        nr->in_scale.as<float>(), nr->in_shift.as<float>(), s1, n2->in_scale.as<float>(),
-                                       n2->in_shift.as<float>(), kActMishBN, &s.cplan)))
+                                       n2->in_shift.as<float>(), kActMishBN, &s.cplan, e.f16)))
           return rc;
         e.program.push_back(s);
         chain_out = s1;
@@ -834,7 +847,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
         if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(s0), ex->w_bf16.as<__nv_bfloat16>(),
                                        c0->w_bf16.as<__nv_bfloat16>(), e.rows, ex->cin, ex->cout, c0->cout, e.xraw.p, e.xraw.p,
                                        c0->in_scale.as<float>(), c0->in_shift.as<float>(), other, nullptr, nullptr, kActMish,
-                                       &cs.cplan)))
+                                       &cs.cplan, e.f16)))
           return rc;
         e.program.push_back(cs);
         bcast_conv0_done = true;  // its output is in `other`, which becomes `cur` below
@@ -868,6 +881,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.layer = e.head_conv;
     s.in = head_in;
     s.ep.raw_out = e.pgv.as<float>();
+    s.ep.op_f16 = e.f16;
     s.ep.raw_transposed = true;  // channel-major [3Ch, rows]: what the heads kernel reads coalesced
     if (e.bf16) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(head_in), e.head_conv->w_bf16.as<__nv_bfloat16>(),
@@ -993,7 +1007,7 @@ int p3_engine_create(const char* weights_path, int device, int batch_size, int f
 static int engine_create_impl(const char* weights_path, int device, int batch_size, int feat_version, int precision,
                               p3_engine** out) {
   if (!weights_path || !out || batch_size <= 0) return fail(P3_ERR_INVALID_ARG, "p3_engine_create: bad argument");
-  if (precision != P3_PRECISION_FP32 && precision != P3_PRECISION_BF16)
+  if (precision != P3_PRECISION_FP32 && precision != P3_PRECISION_BF16 && precision != P3_PRECISION_FP16)
     return fail(P3_ERR_INVALID_ARG, "p3_engine_create: unknown precision");
   if (feat_version != 0 && feat_version != 1) return fail(P3_ERR_INVALID_ARG, "p3_engine_create: feature version must be 0 or 1");
   *out = nullptr;
@@ -1008,7 +1022,8 @@ static int engine_create_impl(const char* weights_path, int device, int batch_si
   e->batch = batch_size;
   e->version = feat_version;
   e->precision = precision;
-  e->bf16 = precision == P3_PRECISION_BF16;
+  e->bf16 = precision != P3_PRECISION_FP32;
+  e->f16 = precision == P3_PRECISION_FP16;
   if (const char* g = std::getenv("P3_CUDA_GRAPH")) e->use_graph = std::atoi(g) != 0;
   if (const char* g = std::getenv("P3_RESULTS_TO_HOST")) e->results_to_host = std::atoi(g) != 0;
   P3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

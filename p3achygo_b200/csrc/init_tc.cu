@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kItThreads, 1)
 init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_act,
                const uint16_t* __restrict__ masks_padded, const float* __restrict__ gs, int n, int C, int n_w,
                const __nv_bfloat16* __restrict__ w_packed, const float* __restrict__ scale, const float* __restrict__ shift,
-               int debug) {
+               int debug, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int w_bytes = (n_w / 8) * kItSbo;
@@ -89,8 +89,9 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     for (int i = tid; i < w_bytes / 16; i += kItThreads) dst[i] = src[i];
     for (int i = tid; i < 256; i += kItThreads) {
       uint32_t w[4];
+      const uint32_t one = f16 ? 0x3C00u : 0x3F80u;  // 1.0 in the operand format
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = (((i >> (2 * j)) & 1) ? 0x3F80u : 0u) | (((i >> (2 * j + 1)) & 1) ? 0x3F800000u : 0u);
+      for (int j = 0; j < 4; ++j) w[j] = (((i >> (2 * j)) & 1) ? one : 0u) | (((i >> (2 * j + 1)) & 1) ? (one << 16) : 0u);
       s_lut[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     constexpr float kLog2e = 1.4426950408889634f;
@@ -142,7 +143,7 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = ptx::make_idesc_bf16(128, n_w);
+    const uint32_t idesc = ptx::make_idesc_op(128, n_w, f16);
     const uint32_t a_lo = desc_lo_nosw(ptx::smem_u32(smem_a)), w_lo = desc_lo_nosw(ptx::smem_u32(smem_w));
     for (int it = 0; it < n_it; ++it) {
       const int as = it & 1;
@@ -266,8 +267,8 @@ init_tc_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constan
       }
       uint4 r0 = make_uint4(tc_pack_f16(x[0], x[1]), tc_pack_f16(x[2], x[3]), tc_pack_f16(x[4], x[5]), tc_pack_f16(x[6], x[7]));
       uint4 r1 = make_uint4(tc_pack_f16(x[8], x[9]), tc_pack_f16(x[10], x[11]), tc_pack_f16(x[12], x[13]), tc_pack_f16(x[14], x[15]));
-      uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
-      uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+      uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+      uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
       if (!live) r0 = r1 = p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout are zeros
       if (h == 0) {
         // the quarter's previous stores have read the boxes: waited for by the quarter leader AFTER the first pass's math,
@@ -317,16 +318,21 @@ bool init_tc_supported(int nplanes, int nscalars, int C) {
 }
 
 // [25][nplanes][C] fp32 tap-major table -> per N slice, K-major core-matrix order [n / 8][k / 8][n % 8][k % 8], k = tap * 16 + plane
-int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out) {
+int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out, bool op_f16) {
   const int n_w = init_tc_slice_width(C);
   out.assign(static_cast<size_t>(C) * kItK, __float2bfloat16(0.0f));
+  auto to_op = [&](float v) {  // the 16-bit operand word, carried in the bf16-typed vector
+    if (!op_f16) return __float2bfloat16(v);
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+  };
   for (int c = 0; c < C; ++c) {
     const int slice = c / n_w, nl = c % n_w;
     for (int t = 0; t < kItTaps; ++t)
       for (int p = 0; p < nplanes; ++p) {
         const int k = t * 16 + p;
         const size_t idx = static_cast<size_t>(slice) * n_w * kItK + (static_cast<size_t>(nl / 8) * kItKc + k / 8) * 64 + (nl % 8) * 8 + (k % 8);
-        out[idx] = __float2bfloat16(wt[(static_cast<size_t>(t) * nplanes + p) * C + c]);
+        out[idx] = to_op(wt[(static_cast<size_t>(t) * nplanes + p) * C + c]);
       }
   }
   return P3_OK;
@@ -334,7 +340,7 @@ int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_b
 
 struct InitTcPlan {
   CUtensorMap map_raw, map_act;  // 32-row x 64-column output boxes of the [rows, C] fp16 / bf16 matrices
-  int n = 0, C = 0, grid = 0, debug = 0;
+  int n = 0, C = 0, grid = 0, debug = 0, f16 = 0;
   size_t smem = 0;
   const uint16_t* masks_padded = nullptr;
   const float *gs = nullptr, *scale = nullptr, *shift = nullptr;
@@ -344,8 +350,10 @@ struct InitTcPlan {
 };
 
 int init_tc_plan_create(const uint16_t* masks_padded, const float* gs, int n, int C, const __nv_bfloat16* w_packed,
-                        __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTcPlan** out) {
+                        __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTcPlan** out,
+                        bool op_f16) {
   InitTcPlan* p = new InitTcPlan();
+  p->f16 = op_f16 ? 1 : 0;
   p->masks_padded = masks_padded; p->gs = gs; p->n = n; p->C = C; p->w_packed = w_packed;
   p->raw_out = raw_out; p->act_out = act_out; p->scale = scale; p->shift = shift;
   const int n_w = init_tc_slice_width(C);
@@ -378,7 +386,7 @@ void init_tc_plan_destroy(InitTcPlan* p) { delete p; }
 
 int init_tc_launch(const InitTcPlan* p, cudaStream_t stream) {
   init_tc_kernel<<<p->grid, kItThreads, p->smem, stream>>>(p->map_raw, p->map_act, p->masks_padded, p->gs, p->n, p->C,
-                                                           init_tc_slice_width(p->C), p->w_packed, p->scale, p->shift, p->debug);
+                                                           init_tc_slice_width(p->C), p->w_packed, p->scale, p->shift, p->debug, p->f16);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

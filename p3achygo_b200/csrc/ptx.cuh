@@ -305,6 +305,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+// the same with the operand format chosen at run time: A / B format 0 = F16 (IEEE half), 1 = BF16 (kind::f16 takes either at the
+// same rate; P3_PRECISION_FP16 runs the tower with fp16 operands, the reference's production precision)
+__host__ __device__ constexpr uint32_t make_idesc_op(int m, int n, int f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 // ---- tcgen05: TMEM -> registers ------------------------------------------------------------------------------
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i).

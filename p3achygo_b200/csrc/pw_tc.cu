@@ -35,7 +35,7 @@ constexpr int kPwMisc = 1024 /*align*/ + kPwBarRegion + 2 * kPwMaxN * 4;
 struct TcPwPlan {
   CUtensorMap map_a1, map_w1, map_res, map_raw, map_act;
   int rows = 0, k1 = 0, n1 = 0, n_tile = 0, a1_stages = 0, n_boxes = 0, grid = 0;
-  int has_res = 0, has_raw = 0, has_act = 0, act_mode = kActNone;
+  int has_res = 0, has_raw = 0, has_act = 0, act_mode = kActNone, f16 = 0;
   size_t smem_bytes = 0;
   const float *scale = nullptr, *shift = nullptr;
 };
@@ -53,7 +53,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                   const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                   const __grid_constant__ CUtensorMap map_act, int rows, int k1, int n1, int n_tile, int a1_stages, int n_boxes,
                   int has_res, int has_raw, int has_act, int act_mode, const float* __restrict__ scale,
-                  const float* __restrict__ shift) {
+                  const float* __restrict__ shift, int f16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n_slabs = n_tile / 64;
@@ -150,7 +150,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   } else if (warp == 1) {
     if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
-      const uint32_t idesc = ptx::make_idesc_bf16(256, n_tile);
+      const uint32_t idesc = ptx::make_idesc_op(256, n_tile, f16);
       const uint32_t w_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_w)), a1_lo = ptx::desc_lo_sw128(ptx::smem_u32(smem_a1));
       ptx::mbar_wait_cluster(w_bar, 0);
       ptx::tc_fence_after_sync();
@@ -295,8 +295,8 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             bn_mish8(x, a, sc, sh, col);
             bn_mish8(x + 8, a + 8, sc, sh, col + 8);
           }
-          uint4 p0 = make_uint4(tc_pack_bf16(a[0], a[1]), tc_pack_bf16(a[2], a[3]), tc_pack_bf16(a[4], a[5]), tc_pack_bf16(a[6], a[7]));
-          uint4 p1 = make_uint4(tc_pack_bf16(a[8], a[9]), tc_pack_bf16(a[10], a[11]), tc_pack_bf16(a[12], a[13]), tc_pack_bf16(a[14], a[15]));
+          uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+          uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
           if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
           if (has_raw) {  // second box of the slab
             obuf = box_base + ob * kPwBoxBytes;
@@ -338,6 +338,7 @@ int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows,
   if ((ep.residual || ep.raw_out) && !ep.raw_f16) return fail(P3_ERR_UNSUPPORTED, "tc_pw: the residual stream must be fp16");
   if (!ep.raw_out && !ep.act_out) return fail(P3_ERR_INVALID_ARG, "tc_pw: nothing to write");
   TcPwPlan* p = new TcPwPlan();
+  p->f16 = ep.op_f16 ? 1 : 0;
   p->rows = rows;
   p->k1 = k1;
   p->n1 = n1;
@@ -416,7 +417,7 @@ void tc_pw_plan_destroy(TcPwPlan* p) { delete p; }
 int tc_pw_launch(const TcPwPlan* p, cudaStream_t stream) {
   P3_CUDA(tc_launch_pdl(tc_pw_pair_kernel, p->grid, kPwThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_res, p->map_raw,
                         p->map_act, p->rows, p->k1, p->n1, p->n_tile, p->a1_stages, p->n_boxes, p->has_res, p->has_raw, p->has_act,
-                        p->act_mode, p->scale, p->shift));
+                        p->act_mode, p->scale, p->shift, p->f16));
   return P3_OK;
 }
 

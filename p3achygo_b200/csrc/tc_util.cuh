@@ -74,6 +74,9 @@ __device__ __forceinline__ uint32_t tc_pack_f16(float a, float b) {
   return r;
 }
 
+// activated operand pair in the engine's operand format (bf16, or IEEE fp16 when f16 != 0; both saturate instead of overflowing)
+__device__ __forceinline__ uint32_t tc_pack_act(float a, float b, int f16) { return f16 ? tc_pack_f16(a, b) : tc_pack_bf16(a, b); }
+
 // 8 activations a[i] = mish(t[i]), t = (x * scale + shift), with the constants pre-multiplied by log2(e): z = t log2(e) comes
 // straight out of the BN FFMA, e^t = ex2(z), and mish(t) = t (1 - 2/d) = z * (ln2 - 2 ln2 / d), d = e^t (e^t + 2) + 2.  Pairs
 // share one reciprocal (1/d0 = d1 / (d0 d1)).  Written phase by phase over the 8 values so that the 8 dependency chains are

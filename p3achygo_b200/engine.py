@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (AUX_RESULT_DTYPE, GO_FEATURES_DTYPE, INFER_RESULT_DTYPE, LEAF_RESULT_DTYPE, NUM_LOCS, NUM_MOVES,
-                   PRECISION_BF16, PRECISION_FP32, RESULT_FULL, RESULT_LEAF, P3Error, check, lib, ptr)
+                   PRECISION_BF16, PRECISION_FP16, PRECISION_FP32, RESULT_FULL, RESULT_LEAF, P3Error, check, lib, ptr)
 
 
 class Kind(enum.IntEnum):
@@ -71,7 +71,7 @@ class B200Engine:
 
     def __init__(self, path: str, batch_size: int, version: int = 1, precision: Optional[int] = None, device: int = 0):
         if precision is None:
-            precision = PRECISION_BF16 if os.environ.get("P3_PRECISION", "bf16") == "bf16" else PRECISION_FP32
+            precision = {"bf16": PRECISION_BF16, "fp16": PRECISION_FP16, "fp32": PRECISION_FP32}[os.environ.get("P3_PRECISION", "bf16")]
         self._h = ctypes.c_void_p()
         self._path = path
         self.batch_size = batch_size

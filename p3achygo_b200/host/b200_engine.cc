@@ -24,7 +24,8 @@ namespace fs = std::filesystem;
 std::unique_ptr<B200Engine> B200Engine::Create(std::string path, int batch_size, int version, int device, int precision) {
   if (precision < 0) {
     const char* env = std::getenv("P3_PRECISION");
-    precision = (env && std::strcmp(env, "fp32") == 0) ? P3_PRECISION_FP32 : P3_PRECISION_BF16;
+    precision = (env && std::strcmp(env, "fp32") == 0) ? P3_PRECISION_FP32
+                : (env && std::strcmp(env, "fp16") == 0) ? P3_PRECISION_FP16 : P3_PRECISION_BF16;
   }
   p3_engine* e = nullptr;
   P3_CHECK(p3_engine_create(path.c_str(), device, batch_size, version, precision, &e));

@@ -8,7 +8,7 @@ namespace nn {
 
 class B200Engine final : public Engine {
  public:
-  // precision: P3_PRECISION_BF16 (default; env P3_PRECISION=fp32 selects the parity path)
+  // precision: P3_PRECISION_BF16 (default; env P3_PRECISION=fp32 selects the parity path, fp16 the fp16-operand tensor path)
   static std::unique_ptr<B200Engine> Create(std::string path, int batch_size, int version, int device = 0,
                                             int precision = -1);
   ~B200Engine() override;

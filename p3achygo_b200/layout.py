@@ -14,7 +14,7 @@ NUM_MOVES = 362
 
 P3_OK = 0
 P3_ERR_INVALID_ARG, P3_ERR_NO_DEVICE, P3_ERR_CUDA, P3_ERR_IO, P3_ERR_UNSUPPORTED = 1, 2, 3, 4, 5
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16, PRECISION_FP16 = 0, 1, 2
 
 
 class Loc(ctypes.Structure):

@@ -16,7 +16,7 @@ cfg = W.config_from_str(config)
 d = tempfile.mkdtemp()
 path = os.path.join(d, "w.p3w")
 W.save_weights(path, cfg, W.synthetic_weights(cfg, 0))
-prec = {"bf16": E.PRECISION_BF16, "fp32": E.PRECISION_FP32}.get(os.environ.get("P3_PRECISION", "bf16"), E.PRECISION_BF16)
+prec = {"bf16": E.PRECISION_BF16, "fp16": E.PRECISION_FP16, "fp32": E.PRECISION_FP32}[os.environ.get("P3_PRECISION", "bf16")]
 eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=prec)
 eng.LoadBatchAll(feats)
 eng.Upload()

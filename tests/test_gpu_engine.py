@@ -115,6 +115,26 @@ def test_bf16_engine_within_documented_bound(config, n, weight_dir, golden_posit
     eng.close()
 
 
+# IEEE fp16 operands (11-bit mantissa, tcgen05 kind::f16 at the bf16 rate): the reference's production precision is whole-graph fp16
+# (python/rl_loop/model_utils.py:181).  Documented bound: 1/5 of the bf16 one (three more mantissa bits in the operands; the fp16
+# residual stream is common to both).  Measured on B200 (round 2): logits <= 8.6e-3 (3e-3 .. 6e-3 typical), probabilities <= 6e-5,
+# value_probs <= 1.3e-3, E[score] <= 0.52 points.
+FP16_TOL = {"logits": 1.2e-2, "probs": 3e-3, "value": 4e-3, "score_mean": 0.75}
+
+
+@pytest.mark.parametrize("config,n", [("small", 32), ("b10c128btl3", 6), ("b12c256btl3", 4), ("b14c384btl3", 2), ("b15c192_classic", 3),
+                                      ("b8c128nbt", 4), ("b12c256nbt", 2)])
+def test_fp16_engine_within_documented_bound(config, n, weight_dir, golden_positions):
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir(config)
+    feats = golden_positions["feats"][100:100 + n]
+    o = _oracle_outputs(cfg, tensors, feats, torch.float64)
+    eng, res, aux = _run_engine(path, feats, E.PRECISION_FP16)
+    worst = _compare(res, aux, o, FP16_TOL["logits"], FP16_TOL["probs"], FP16_TOL["value"], FP16_TOL["score_mean"])
+    print(config, "fp16 worst errors:", {k: f"{v[0]:.2e}" for k, v in worst.items()})
+    eng.close()
+
+
 def test_bf16_unsupported_for_tiny(weight_dir):
     from p3achygo_b200 import engine as E
     path, _, _ = weight_dir("tiny")
@@ -123,13 +143,13 @@ def test_bf16_unsupported_for_tiny(weight_dir):
     assert ei.value.code == E._lib.P3_ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16", "fp16"])
 def test_engine_contract(precision_name, weight_dir, golden_positions):
     """Slot semantics of nn::Engine (SURVEY 8b): full batch every run, stale slots tolerated, outputs of a slot stay
     intact until the next RunInference, results independent of slot index and of other slots' contents, CUDA-graph
     replay == plain launches, deterministic across runs."""
     from p3achygo_b200 import engine as E
-    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    prec = {"fp32": E.PRECISION_FP32, "bf16": E.PRECISION_BF16, "fp16": E.PRECISION_FP16}[precision_name]
     path, cfg, tensors = weight_dir("b10c128btl3")
     feats = golden_positions["feats"][:8]
     B = 8
@@ -210,22 +230,23 @@ _GOLDEN_MAP = [("move_logits", "res", "pi_logits"), ("move_probs", "res", "pi"),
                ("mcts_dist_logits", "aux", "mcts_dist_logits")]
 
 
-@pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision_name", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("config", ["tiny", "small", "b10c128btl3", "b12c256btl3", "b14c384btl3", "b15c192_classic", "b8c128nbt"])
 def test_engine_matches_reference_model_golden(config, precision_name, weight_dir, golden_positions):
     """The CUDA engine on the positions / weights of the fixture produced by the reference's unmodified python/model.py
     (float64, on oracle/tf_shim).  fp32 engine: max-abs 1e-3 (north star); bf16 engine: the documented bound."""
     import os
     from p3achygo_b200 import engine as E
-    if config == "tiny" and precision_name == "bf16":
-        pytest.skip("tiny (C=16) is below the tensor-core tile sizes; bf16 engine reports UNSUPPORTED (tested above)")
+    if config == "tiny" and precision_name != "fp32":
+        pytest.skip("tiny (C=16) is below the tensor-core tile sizes; the tensor engines report UNSUPPORTED (tested above)")
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_golden.npz"))
     first, n = (int(v) for v in z[f"{config}/first"])
     path, cfg, tensors = weight_dir(config)
     feats = golden_positions["feats"][first:first + n]
-    prec = E.PRECISION_FP32 if precision_name == "fp32" else E.PRECISION_BF16
+    prec = {"fp32": E.PRECISION_FP32, "bf16": E.PRECISION_BF16, "fp16": E.PRECISION_FP16}[precision_name]
     eng, res, aux = _run_engine(path, feats, prec)
-    tl, tp, tv = (FP32_TOL, FP32_TOL, FP32_TOL) if precision_name == "fp32" else (BF16_TOL["logits"], BF16_TOL["probs"], BF16_TOL["value"])
+    tl, tp, tv = {"fp32": (FP32_TOL, FP32_TOL, FP32_TOL), "bf16": (BF16_TOL["logits"], BF16_TOL["probs"], BF16_TOL["value"]),
+                  "fp16": (FP16_TOL["logits"], FP16_TOL["probs"], FP16_TOL["value"])}[precision_name]
     tol_of = {"move_logits": tl, "pi_logits_aux": tl, "pi_logits_soft": tl, "pi_logits_optimistic": tl, "outcome_logits": tl,
               "score_logits": 4 * tl, "gamma": tl, "move_probs": tp, "score_probs": tp, "mcts_dist_probs": tp, "value_probs": tv,
               "ownership": tv, "mcts_dist_logits": 4 * tl}
