@@ -101,7 +101,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int m_tiles = (rows + 255) / 256;
+  const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
   const int n_it = pair < m_tiles ? (m_tiles - pair + n_pairs - 1) / n_pairs : 0;  // tiles of this pair
   const int defer = acc2_stages >= 2 ? 1 : 0;  // epi2 runs one tile behind epi1 (needs the second acc2 stage)
 
@@ -165,7 +165,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair; mt < m_tiles; mt += n_pairs) {
-      const int m0 = mt * 256 + static_cast<int>(rank) * 128;
+      const int m0 = pair_tile_row0(mt, static_cast<int>(rank));
       for (int ks = 0; ks < k1_slabs; ++ks) {
         ptx::mbar_wait(&a1_empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -254,7 +254,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     uint64_t* my_written = box_written + kChMaxBoxes * q;
     const uint32_t a2_full_l = ptx::mapa_shared(ptx::smem_u32(a2_full), 0);
     uint8_t* my_box = smem_box + q * n_boxes * kChBoxBytes;
-    const int q_row = static_cast<int>(rank) * 128 + q * 32;
+    const int q_row = q * 32;  // within this CTA's 128 rows of a tile
     // The quarter's step sequence (the epilogue warps walk the same one): per iteration `it`, the n1_slabs epi1 steps of
     // tile it, then the n2_slabs epi2 steps of tile it - defer.  `ahead` runs n_boxes - 1 steps in front of `cur`
     // (the box of step cur - 1, just read by its store, serves step cur + n_boxes - 1).
@@ -284,7 +284,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       const bool is_epi1 = c.it < n_it && c.idx < n1_slabs;
       if (is_epi1) {
         ptx::mbar_arrive_expect_tx(&my_ready[b], kChBoxBytes);
-        ptx::tma_load_2d(my_box + b * kChBoxBytes, &map_res, &my_ready[b], c.idx * 64, (pair + c.it * n_pairs) * 256 + q_row);
+        ptx::tma_load_2d(my_box + b * kChBoxBytes, &map_res, &my_ready[b], c.idx * 64, pair_tile_row0(pair + c.it * n_pairs, static_cast<int>(rank)) + q_row);
       } else {
         ptx::mbar_arrive(&my_ready[b]);
       }
@@ -306,10 +306,10 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         if (is_epi1) {
           ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
           ptx::tma_store_2d(&map_raw, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
-                            (pair + cur.it * n_pairs) * 256 + q_row);
+                            pair_tile_row0(pair + cur.it * n_pairs, static_cast<int>(rank)) + q_row);
         } else {
           ptx::tma_store_2d(&map_out2, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, (cur.idx - (cur.it < n_it ? n1_slabs : 0)) * 64,
-                            (pair + (cur.it - defer) * n_pairs) * 256 + q_row);
+                            pair_tile_row0(pair + (cur.it - defer) * n_pairs, static_cast<int>(rank)) + q_row);
         }
         ptx::bulk_commit();
         ptx::bulk_wait_read<1>();  // the previous step's store has read its box: that box serves the step n_boxes - 1 ahead
@@ -425,7 +425,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       // commit latency are never waited for)
       const int it2 = it - defer;
       if (it2 >= 0 && it2 < n_it) {
-        const int m = (pair + it2 * n_pairs) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+        const int m = pair_tile_row0(pair + it2 * n_pairs, static_cast<int>(rank)) + q * 32 + lane;
         const bool live = m < rows && row_is_live(m % kRowsPerPos);
         const int as = it2 % acc2_stages;
         const long long tc0 = tr ? clock64() : 0;
@@ -571,7 +571,7 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
     else
       cudaGetLastError();
   }
-  const int m_tiles = (rows + 255) / 256;
+  const int m_tiles = pair_tile_count(rows);
   p->grid = 2 * std::max(1, std::min(max_pairs, m_tiles));
   if (std::getenv("P3_TC_TRACE")) {
     cudaMalloc(&p->trace, 16 * sizeof(unsigned long long));

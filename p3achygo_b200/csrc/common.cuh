@@ -47,6 +47,18 @@ __host__ __device__ inline int row_point(int q) {  // live padded row -> point i
   return ((q - kRowBase) / kRowPitch) * 19 + ((q - kRowBase) % kRowPitch);
 }
 
+// Position-aligned pair tiles (CTA-pair kernels: 3x3, fused boundary, stand-alone 1x1).  A pair's 256-row tile is tile k (of 3)
+// of two consecutive positions, one per CTA: CTA `rank` of tile `mt` covers rows
+//     [(2 * (mt / 3) + rank) * 400 + 20 + (mt % 3) * 128, + 128),
+// i.e. a position is 3 x 128 = 384 rows starting at its first board row.  Its 20 leading padding rows are never loaded,
+// multiplied or stored (they stay the zeros the buffers were allocated with; every other writer writes zeros there), which
+// removes 4 % of the rows of a flat 256-row tiling.  The last tile of a position spills 4 rows into the next position's leading
+// padding (written as zeros: not live); rows beyond the batch are zero-filled / clipped by TMA.  `rows` is a multiple of 400.
+__host__ __device__ inline int pair_tile_count(int rows) { return ((rows / kRowsPerPos + 1) / 2) * 3; }
+__host__ __device__ inline int pair_tile_row0(int mt, int rank) {
+  return ((mt / 3) * 2 + rank) * kRowsPerPos + kRowBase + (mt % 3) * 128;
+}
+
 // What a conv epilogue writes besides the raw sum.
 enum ActMode : int {
   kActNone = 0,      // no activated copy

@@ -710,7 +710,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int slice = pair % n_slices;
   const int n0 = slice * N;
   const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
-  const int m_tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+  const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
 
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
     s_scale[c] = act_mode == kActMishBN ? scale[n0 + c] : 1.0f;
@@ -756,7 +756,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice) {
-      const int m0 = mt * 2 * kTileM + static_cast<int>(rank) * kTileM;
+      const int m0 = pair_tile_row0(mt, static_cast<int>(rank));
       for (int ks = 0; ks < k_slabs; ++ks) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -844,7 +844,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
       if (tr && iter == 0 && ew == 0 && lane == 0) atomicAdd(&trace[4], global_timer() - t_start);
-      const int m = mt * 2 * kTileM + static_cast<int>(rank) * kTileM + quarter * 32 + lane;
+      const int m = pair_tile_row0(mt, static_cast<int>(rank)) + quarter * 32 + lane;
       const bool in_range = m < rows;
       const bool live = in_range && row_is_live(m % kRowsPerPos);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * N + c0);
@@ -936,7 +936,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !(debug & 8)) {
-          ptx::tma_store_2d(&map_o64, nullptr, 0, 0, my_stage, n0 + c0, mt * 2 * kTileM + static_cast<int>(rank) * kTileM + quarter * 32);
+          ptx::tma_store_2d(&map_o64, nullptr, 0, 0, my_stage, n0 + c0, pair_tile_row0(mt, static_cast<int>(rank)) + quarter * 32);
           ptx::bulk_commit();
         }
       }
@@ -1089,7 +1089,7 @@ int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int row
     p->resident = false;
     p->tmem_cols = 512;  // one CTA per SM: take all columns -> 4 accumulator stages at N <= 128
     const int n_slices = cout / p->n_tile;
-    const int m_tiles = (rows + 2 * kTileM - 1) / (2 * kTileM);
+    const int m_tiles = pair_tile_count(rows);
     rc = make_map_bf16_k64(&p->map_a, in, cin, rows, kResRows);
     if (rc == P3_OK) rc = make_map_bf16_k64(&p->map_w, w, cin, static_cast<uint64_t>(taps) * cout, p->n_half);
     p->map_raw = p->map_a;  // placeholders unless staged

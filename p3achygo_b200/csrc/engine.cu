@@ -1654,7 +1654,13 @@ int p3_block_boundary_test(int device, int fused, const float* t, const float* x
       (rc = upload_f32(ds2, std::vector<float>(scale2, scale2 + n2))) || (rc = upload_f32(dh2, std::vector<float>(shift2, shift2 + n2))) ||
       (rc = du.alloc(R * n1 * 2)) || (rc = dout.alloc(R * n2 * 2)))
     return rc;
-  P3_CUDA(cudaMemset(dout.p, 0xff, dout.bytes));  // padding rows must come back as zeros
+  {  // padding rows inside a position's tiles must come back as zeros; its 20 leading padding rows are never written by the
+     // position-aligned pair tiles (common.cuh) and keep the zeros every engine buffer starts with
+    std::vector<uint16_t> init(R * n2, 0xffffu);
+    for (size_t row = 0; row < R; ++row)
+      if (row % kRowsPerPos < static_cast<size_t>(kRowBase)) std::fill(init.begin() + row * n2, init.begin() + (row + 1) * n2, uint16_t(0));
+    P3_CUDA(cudaMemcpy(dout.p, init.data(), dout.bytes, cudaMemcpyHostToDevice));
+  }
   if (fused) {
     TcChainPlan* plan = nullptr;
     if ((rc = tc_chain_plan_create(dt.as<__nv_bfloat16>(), dw1.as<__nv_bfloat16>(), dw2.as<__nv_bfloat16>(), static_cast<int>(R), k1, n1,

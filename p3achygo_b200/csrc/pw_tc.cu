@@ -79,7 +79,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const int slice = pair % n_slices;
   const int n0 = slice * n_tile;
   const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
-  const int m_tiles = (rows + 255) / 256;
+  const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
   const int n_it = pair_in_slice < m_tiles ? (m_tiles - pair_in_slice + pairs_per_slice - 1) / pairs_per_slice : 0;
   const int boxes_per_slab = (has_raw && has_act) ? 2 : 1;
 
@@ -132,7 +132,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int m0 = (pair_in_slice + it * pairs_per_slice) * 256 + static_cast<int>(rank) * 128;
+      const int m0 = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank));
       for (int ks = 0; ks < k1_slabs; ++ks) {
         ptx::mbar_wait(&a1_empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -191,10 +191,12 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     uint64_t* my_ready = box_ready + kPwMaxBoxes * q;
     uint64_t* my_written = box_written + kPwMaxBoxes * q;
     uint8_t* my_box = smem_box + q * n_boxes * kPwBoxBytes;
-    const int q_row = static_cast<int>(rank) * 128 + q * 32;
+    const int q_row = q * 32;  // within this CTA's 128 rows of a tile
     const int steps_per_tile = n_slabs * boxes_per_slab;
     const uint32_t total_steps = static_cast<uint32_t>(n_it) * steps_per_tile;
-    auto row_of = [&](uint32_t s) { return (pair_in_slice + static_cast<int>(s / steps_per_tile) * pairs_per_slice) * 256 + q_row; };
+    auto row_of = [&](uint32_t s) {
+      return pair_tile_row0(pair_in_slice + static_cast<int>(s / steps_per_tile) * pairs_per_slice, static_cast<int>(rank)) + q_row;
+    };
     auto col_of = [&](uint32_t s) { return n0 + static_cast<int>((s % steps_per_tile) / boxes_per_slab) * 64; };
     auto prepare = [&](uint32_t s) {
       if (s >= total_steps) return;
@@ -244,7 +246,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     };
     for (int it = 0; it < n_it; ++it) {
       const int as = it & 1;
-      const int m = (pair_in_slice + it * pairs_per_slice) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const int m = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank)) + q * 32 + lane;
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
       ptx::mbar_wait(&acc_full[as], (static_cast<uint32_t>(it) >> 1) & 1u);
       ptx::tc_fence_after_sync();
@@ -405,7 +407,7 @@ int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows,
       cudaGetLastError();
   }
   const int n_slices = n1 / p->n_tile;
-  const int m_tiles = (rows + 255) / 256;
+  const int m_tiles = pair_tile_count(rows);
   const int pairs = std::max(n_slices, std::min(max_pairs, m_tiles * n_slices) / n_slices * n_slices);
   p->grid = 2 * pairs;
   *out = p;
