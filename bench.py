@@ -56,7 +56,7 @@ def kernel_source_hash() -> str:
     """Identifies the kernels a committed ncu capture was taken from: sha256 over the tensor-path sources."""
     import hashlib
     h = hashlib.sha256()
-    for name in ("conv_tc.cu", "chain_tc.cu", "pw_tc.cu", "broadcast_tc.cu", "init_tc.cu", "heads.cu", "tc_util.cuh", "ptx.cuh"):
+    for name in ("conv_tc.cu", "chain_tc.cu", "pw_tc.cu", "broadcast_tc.cu", "init_tc.cu", "init_tc2.cu", "heads.cu", "tc_util.cuh", "ptx.cuh", "common.cuh"):
         with open(os.path.join(ROOT, "p3achygo_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]

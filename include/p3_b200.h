@@ -245,6 +245,12 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
  * every p3_engine_run_inference runs this check and fails with P3_ERR_UNSUPPORTED when n_saturated > 0 (validation mode for a
  * new checkpoint: slower, one extra pass per run).  The fp32 engine has an fp32 stream: it reports max_abs and non-finite values. */
 int p3_engine_range_check(p3_engine* e, float* max_abs, long long* n_saturated);
+/* Test hook for the first layer alone (python/model.py:1230-1237: 5x5 conv of the planes + dense of the game state): runs encode +
+ * first layer on the inputs resident in HBM and copies its two outputs to the host, both in the padded board-row layout
+ * [batch * 400, C] (point (r, c) of slot b = row b * 400 + 20 + r * 20 + c): stream_out = the residual stream x (IEEE fp16),
+ * act_out = mish(BN_0(x)) in the engine's operand format (bf16 or fp16).  bytes = size of each buffer (>= batch * 400 * C * 2).
+ * 16-bit engines only. */
+int p3_engine_first_layer(p3_engine* e, void* stream_out, void* act_out, size_t bytes);
 /* Per-stage device times of one eager pass (ms): [0] encode, [1] tower, [2] heads. */
 int p3_engine_stage_ms(p3_engine* e, float ms[3]);
 /* Number of kernel launches one p3_engine_run_inference issues (for bench.py's gpu_launches). */

@@ -35,7 +35,7 @@ EXPORTS = [
     "p3_engine_set_cuda_graph", "p3_encode_features", "p3_board_liberties", "p3_legal_mask", "p3_game_derive", "p3_gumbel_topk",
     "p3_conv_test", "p3_broadcast_test", "p3_block_boundary_test", "p3_last_error", "p3_version",
     "p3_engine_set_result_mode", "p3_engine_get_leaf", "p3_engine_get_leaf_bank", "p3_engine_get_aux_bank",
-    "p3_engine_get_ownership_bank", "p3_engine_gumbel_topk_bank", "p3_engine_range_check",
+    "p3_engine_get_ownership_bank", "p3_engine_gumbel_topk_bank", "p3_engine_range_check", "p3_engine_first_layer",
 ]
 
 
@@ -88,6 +88,7 @@ def _load() -> ctypes.CDLL:
     lib.p3_engine_get_aux_bank.argtypes = [vp, ci, ci, vp]
     lib.p3_engine_get_ownership_bank.argtypes = [vp, ci, ci, vp]
     lib.p3_engine_range_check.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ctypes.c_longlong)]
+    lib.p3_engine_first_layer.argtypes = [vp, vp, vp, ctypes.c_size_t]
     lib.p3_engine_gumbel_topk_bank.argtypes = [vp, ci, vp, ci, vp, vp, cf, ci, vp, vp, vp]
     return lib
 

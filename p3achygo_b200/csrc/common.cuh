@@ -172,6 +172,15 @@ int init_tc_plan_create(const uint16_t* masks_padded, const float* gs, int n, in
 void init_tc_plan_destroy(InitTcPlan* p);
 int init_tc_launch(const InitTcPlan* p, cudaStream_t stream);
 
+// second form (init_tc2.cu): the planes expanded once per position, the 25 taps as row-shifted views, 4-D TMA output map
+bool init_tc2_supported(int nplanes, int nscalars, int C);
+struct InitTc2Plan;
+int init_tc2_plan_create(const uint16_t* masks_padded, const float* gs, int n, int C, const __nv_bfloat16* w_packed,
+                         __half* raw_out, __nv_bfloat16* act_out, const float* scale, const float* shift, InitTc2Plan** out,
+                         bool op_f16 = false);
+void init_tc2_plan_destroy(InitTc2Plan* p);
+int init_tc2_launch(const InitTc2Plan* p, cudaStream_t stream);
+
 // ---- broadcast mix (broadcast.cu) -------------------------------------------------------------------
 // y[b,q,c] = sum_p W[p,q] * x[b,p,c] + bias[q], then act = mish(BN(y)); x, act in the operand type.
 int broadcast_launch(const void* x, const float* w, const float* bias, int n, int C, void* act_out,

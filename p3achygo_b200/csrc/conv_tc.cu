@@ -881,9 +881,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               v[g * 8 + 2 * i + 1] = __float_as_uint(x1);
               o[i] = pack_f16(x0, x1);
             }
-            // padding rows need no masking: their A rows and residual rows are zeros (layout invariant)
+            // padding rows / columns of the residual stream stay zero too (a 3x3 output there is not zero; the first layer
+            // does not rewrite them every step: init_tc2.cu)
             if (raw != nullptr && in_range)
-              *reinterpret_cast<uint4*>(raw + static_cast<size_t>(m) * cout + n0 + c0 + col + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(raw + static_cast<size_t>(m) * cout + n0 + c0 + col + g * 8) =
+                  live ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0, 0, 0, 0);
           }
         }
         if (last) {

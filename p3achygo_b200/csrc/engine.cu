@@ -26,6 +26,7 @@
 
 namespace p3 {
 int init_tc_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out, bool op_f16);  // init_tc.cu
+int init_tc2_pack_weights(const float* wt, int nplanes, int C, std::vector<__nv_bfloat16>& out, bool op_f16);  // init_tc2.cu
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -162,9 +163,11 @@ struct p3_engine {
   // weights
   DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
   bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
-  bool init_tc = false;    // init conv as a tcgen05 implicit GEMM over the plane masks (init_tc.cu)
+  bool init_tc = false;    // init conv as a tcgen05 implicit GEMM over the plane masks (init_tc.cu / init_tc2.cu)
+  bool init_form2 = false; // ... in its shifted-view form (init_tc2.cu)
   DevBuf init_wt_tc, d_masks_pad, d_gs, d_sym;
   InitTcPlan* init_plan = nullptr;
+  InitTc2Plan* init_plan2 = nullptr;  // the shifted-view form of the first layer (init_tc2.cu); P3_INIT_TC=1 keeps the first form
   EncodeExtra enc_extra;
   std::vector<std::unique_ptr<ConvLayer>> layers;
   std::vector<DevBuf*> owned;
@@ -228,6 +231,7 @@ struct p3_engine {
       if (s.pplan) tc_pw_plan_destroy(s.pplan);
     }
     if (init_plan) init_tc_plan_destroy(init_plan);
+    if (init_plan2) init_tc2_plan_destroy(init_plan2);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (graph_exec_host) cudaGraphExecDestroy(graph_exec_host);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -273,6 +277,7 @@ struct p3_engine {
   }
 
   int run_init() {
+    if (init_plan2) return init_tc2_launch(init_plan2, stream);
     if (init_tc) return init_tc_launch(init_plan, stream);
     if (init_smem)
       return init_conv_smem_launch(d_masks.as<uint16_t>(), d_scalars.as<float>(), batch, nplanes, nscalars, C,
@@ -626,7 +631,10 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     e.init_tc = e.bf16 && init_tc_supported(P, e.nscalars, C) && !(env_it && std::atoi(env_it) == 0);
     if (e.init_tc) {
       std::vector<__nv_bfloat16> packed;
-      init_tc_pack_weights(wt.data(), P, C, packed, e.f16);
+      const bool form2 = init_tc2_supported(P, e.nscalars, C) && !(env_it && std::atoi(env_it) == 1);
+      if (form2) init_tc2_pack_weights(wt.data(), P, C, packed, e.f16);
+      else init_tc_pack_weights(wt.data(), P, C, packed, e.f16);
+      e.init_form2 = form2;
       if ((rc = upload(e.init_wt_tc, packed.data(), packed.size() * sizeof(__nv_bfloat16)))) return rc;
       if ((rc = e.d_masks_pad.alloc(sizeof(uint16_t) * B * kMaskPadElems)) || (rc = e.d_gs.alloc(sizeof(float) * B * C))) return rc;
       P3_CUDA(cudaMemset(e.d_masks_pad.p, 0, e.d_masks_pad.bytes));  // the grid borders stay zero for the engine's lifetime
@@ -702,9 +710,13 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   void* other = e.actB.p;
   e.first_scale = blocks[0].convs[0]->in_scale.as<float>();
   e.first_shift = blocks[0].convs[0]->in_shift.as<float>();
-  if (e.init_tc && (rc = init_tc_plan_create(e.d_masks_pad.as<uint16_t>(), e.d_gs.as<float>(), B, C,
-                                             e.init_wt_tc.as<__nv_bfloat16>(), e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(),
-                                             e.first_scale, e.first_shift, &e.init_plan, e.f16)))
+  if (e.init_tc && e.init_form2) {
+    if ((rc = init_tc2_plan_create(e.d_masks_pad.as<uint16_t>(), e.d_gs.as<float>(), B, C, e.init_wt_tc.as<__nv_bfloat16>(),
+                                   e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(), e.first_scale, e.first_shift, &e.init_plan2, e.f16)))
+      return rc;
+  } else if (e.init_tc && (rc = init_tc_plan_create(e.d_masks_pad.as<uint16_t>(), e.d_gs.as<float>(), B, C,
+                                                    e.init_wt_tc.as<__nv_bfloat16>(), e.xraw.as<__half>(), e.actA.as<__nv_bfloat16>(),
+                                                    e.first_scale, e.first_shift, &e.init_plan, e.f16)))
     return rc;
   const char* env_pw = std::getenv("P3_TC_PW");
   const bool pw_enabled = !(env_pw && std::atoi(env_pw) == 0);
@@ -1465,6 +1477,22 @@ int p3_engine_range_check(p3_engine* e, float* max_abs, long long* n_saturated) 
   std::memcpy(&ns, h + 8, 8);
   std::memcpy(max_abs, &mb, 4);
   *n_saturated = static_cast<long long>(ns);
+  return P3_OK;
+}
+
+int p3_engine_first_layer(p3_engine* e, void* stream_out, void* act_out, size_t bytes) {
+  if (!e || !stream_out || !act_out) return fail(P3_ERR_INVALID_ARG, "first_layer: bad argument");
+  if (!e->bf16) return fail(P3_ERR_UNSUPPORTED, "first_layer: 16-bit engines only");
+  const size_t need = static_cast<size_t>(e->batch) * kRowsPerPos * e->C * 2;
+  if (bytes < need) return fail(P3_ERR_INVALID_ARG, "first_layer: buffers smaller than batch * 400 * C * 2 bytes");
+  P3_CUDA(cudaSetDevice(e->device));
+  int rc = encode_launch(e->d_feats.as<p3_go_features>(), e->batch, e->version, e->d_planes.as<float>(), e->d_scalars.as<float>(),
+                         e->d_masks.as<uint16_t>(), e->stream, &e->enc_extra);
+  if (!rc) rc = e->run_init();
+  if (rc) return rc;
+  P3_CUDA(cudaMemcpyAsync(stream_out, e->xraw.p, need, cudaMemcpyDeviceToHost, e->stream));
+  P3_CUDA(cudaMemcpyAsync(act_out, e->actA.p, need, cudaMemcpyDeviceToHost, e->stream));
+  P3_CUDA(cudaStreamSynchronize(e->stream));
   return P3_OK;
 }
 

@@ -221,6 +221,13 @@ class B200Engine:
         check(lib.p3_engine_range_check(self._h, ctypes.byref(mx), ctypes.byref(sat)))
         return mx.value, sat.value
 
+    def FirstLayer(self, C: int):
+        """Test hook: (residual stream as float16, activated copy as raw uint16) of the first layer, each [batch, 400, C] (C = the net's trunk width)."""
+        x = np.zeros((self.batch_size, 400, C), dtype=np.float16)
+        a = np.zeros((self.batch_size, 400, C), dtype=np.uint16)
+        check(lib.p3_engine_first_layer(self._h, ptr(x), ptr(a), x.nbytes))
+        return x, a
+
     def StageMs(self):
         arr = (ctypes.c_float * 3)()
         check(lib.p3_engine_stage_ms(self._h, ctypes.byref(arr)))

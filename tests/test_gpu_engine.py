@@ -412,6 +412,13 @@ def test_full_size_batch_independence_other_configs(config, B, weight_dir, golde
     big.RunInference()
     sample = sorted({0, 1, 2, 3, B // 2 - 1, B // 2, B - 3, B - 2, B - 1, B // 3, (2 * B) // 3, B // 5})
     big_res = {b: big.GetBatch(b).copy() for b in sample}
+    # the golden positions repeat with period len(feats): EVERY slot must equal the slot one period earlier, bit for bit
+    # (a race between a CTA's consecutive positions shows up here, not in a 12-slot sample)
+    P = len(feats)
+    logits = np.stack([np.asarray(big.GetBatch(b)["move_logits"]) for b in range(B)])
+    value = np.stack([np.asarray(big.GetBatch(b)["value_probs"]) for b in range(B)])
+    for b in range(P, B):
+        assert np.array_equal(logits[b], logits[b - P]) and np.array_equal(value[b], value[b - P]), (config, b)
     big.close()
     small = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=E.PRECISION_BF16)
     ref32 = E.CreateEngine(E.Kind.kB200, path, 4, 1, precision=E.PRECISION_FP32)
@@ -429,6 +436,48 @@ def test_full_size_batch_independence_other_configs(config, B, weight_dir, golde
             assert np.abs(np.asarray(r32["value_probs"]) - np.asarray(big_res[b]["value_probs"])).max() < BF16_TOL["value"]
     small.close()
     ref32.close()
+
+
+# ---- the first layer alone (init_tc2.cu): against the fp32 restatement, and bit-identical to the explicit-im2col kernel ------------
+@pytest.mark.parametrize("config,B", [("b12c256btl3", 600), ("b15c192_classic", 450), ("b14c384btl3", 330), ("b10c128btl3", 700)])
+def test_first_layer_against_oracle_and_explicit_im2col_kernel(config, B, weight_dir, golden_positions, monkeypatch):
+    """python/model.py:1230-1237 (conv5x5 of the planes + dense of the game state) through p3_engine_first_layer, several
+    positions per persistent CTA: the fp16 residual stream is within operand rounding of the fp32 oracle, the activated copy's
+    padding rows / columns are zero (the 3x3 kernels read them as the conv's zero padding), and the shifted-view kernel
+    (init_tc2.cu) equals the explicit-im2col one (init_tc.cu, P3_INIT_TC=1) bit for bit on every board point."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir(config)
+    feats = golden_positions["feats"]
+    reps = (B + len(feats) - 1) // len(feats)
+    raw = np.ascontiguousarray(feats).view(np.uint8).reshape(len(feats), feats.dtype.itemsize)
+    allf = np.ascontiguousarray(np.tile(raw, (reps, 1))[:B]).reshape(-1).view(feats.dtype)
+    C = cfg.channels
+    live = np.array([20 + r * 20 + c for r in range(19) for c in range(19)])
+    pad = np.setdiff1d(np.arange(400), live)
+    out = {}
+    for form in ("2", "1"):
+        monkeypatch.setenv("P3_INIT_TC", form)
+        eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+        eng.LoadBatchAll(allf)
+        eng.RunInference()  # leaves the tower's own traffic in both buffers first
+        out[form] = eng.FirstLayer(C)
+        eng.close()
+    x2, a2 = out["2"]
+    x1, a1 = out["1"]
+    assert np.array_equal(x2[:, live], x1[:, live]) and np.array_equal(a2[:, live], a1[:, live])
+    assert not a2[:, pad].any() and not a1[:, pad].any()
+    assert not x2[:, pad].any()
+    # fp32 restatement on the first len(feats) positions (the rest repeat them)
+    planes, scalars = oracle_lib.load_go_features(feats, 1)
+    m = RefModel(cfg, tensors)
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(planes)).float().permute(0, 3, 1, 2)
+        ref = m.conv("model/init_conv", x) + m.dense("model/init_game_state", torch.from_numpy(np.ascontiguousarray(scalars)).float())[:, :, None, None]
+        ref = ref.permute(0, 2, 3, 1).reshape(len(feats), 361, C).numpy()
+    got = x2[:, live].astype(np.float32)
+    for b in range(B):
+        r = ref[b % len(feats)]
+        assert np.abs(got[b] - r).max() <= 2e-2 * max(1.0, np.abs(r).max()), (config, b)
 
 
 # ---- compact leaf records, per-bank auxiliary outputs, ownership symmetry, root sampling on resident logits ---------------------
