@@ -46,6 +46,10 @@ struct TcChainPlan {
   const float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
   int act2_mode = kActMishBN;
   int f16 = 0;                          // operands are IEEE fp16 instead of bf16 (P3_PRECISION_FP16)
+  // tail form (the tower's last expand + the heads' 1x1 conv): u = x' (the heads take the raw trunk output), x' is not stored,
+  // and `out` is written as fp32, channel-major [n2_valid, out_ld] (what heads.cu reads), straight from the registers
+  int tail = 0, out_ld = 0, n2_valid = 0;
+  float* out_t = nullptr;
   unsigned long long* trace = nullptr;  // P3_TC_TRACE
 };
 
@@ -70,7 +74,8 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                      const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_out2, int rows, int k1,
                      int n1, int n2, int acc2_stages, int a1_stages, int n_boxes, int tmem_cols, const float* __restrict__ scale1,
                      const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
-                     int act2_mode, unsigned long long* trace, int f16) {
+                     int act2_mode, unsigned long long* trace, int f16, int tail, float* __restrict__ out_t, int out_ld,
+                     int n2_valid) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n1_slabs = n1 / 64, n2_slabs = n2 / 64;
@@ -305,9 +310,10 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       if (lane == 0) {
         if (is_epi1) {
           ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
-          ptx::tma_store_2d(&map_raw, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
-                            pair_tile_row0(pair + cur.it * n_pairs, static_cast<int>(rank)) + q_row);
-        } else {
+          if (!tail)
+            ptx::tma_store_2d(&map_raw, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
+                              pair_tile_row0(pair + cur.it * n_pairs, static_cast<int>(rank)) + q_row);
+        } else if (!tail) {  // (tail form: the epilogue warps have stored their fp32 columns themselves)
           ptx::tma_store_2d(&map_out2, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, (cur.idx - (cur.it < n_it ? n1_slabs : 0)) * 64,
                             pair_tile_row0(pair + (cur.it - defer) * n_pairs, static_cast<int>(rank)) + q_row);
         }
@@ -390,7 +396,12 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           const uint4 r0 = make_uint4(tc_pack_f16(x[0], x[1]), tc_pack_f16(x[2], x[3]), tc_pack_f16(x[4], x[5]), tc_pack_f16(x[6], x[7]));
           const uint4 r1 = make_uint4(tc_pack_f16(x[8], x[9]), tc_pack_f16(x[10], x[11]), tc_pack_f16(x[12], x[13]), tc_pack_f16(x[14], x[15]));
           float a[16];
-          bn_mish16(x, a, sc1, sh1, col);
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = x[i];
+          } else {
+            bn_mish16(x, a, sc1, sh1, col);
+          }
           const uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
           const uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
           // A2 slot free: the MMAs that read its previous slab have completed.  x' replaces the residual in place.
@@ -398,8 +409,10 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           if (tr) t[3] = clock64() + (p0.x & 0);
           ptx::mbar_wait(&a2_empty[slot], ((g >> 1) & 1u) ^ 1u);
           if (tr) t[4] = t[5] = clock64();
-          ptx::sts_u4(obuf + ch0, r0);
-          ptx::sts_u4(obuf + ch1, r1);
+          if (!tail) {
+            ptx::sts_u4(obuf + ch0, r0);
+            ptx::sts_u4(obuf + ch1, r1);
+          }
           const uint32_t ap = a2_base + slot * kChSlabBytes + slab_row;
           ptx::sts_u4(ap + ch0, p0);
           ptx::sts_u4(ap + ch1, p1);
@@ -452,13 +465,23 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
           } else {  // kActMishBN (scale, shift) / kActMish (1, 0)
             bn_mish16(x, a, sc2, sh2, col);
           }
-          uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
-          uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
-          if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
           ptx::mbar_wait(&my_ready[ob], ob_phase);
-          const uint32_t obuf = box_base + ob * kChBoxBytes;
-          ptx::sts_u4(obuf + ch0, p0);
-          ptx::sts_u4(obuf + ch1, p1);
+          if (tail) {
+            // fp32, channel-major: a warp's 32 rows of one column are 128 contiguous bytes
+            if (m < rows) {
+              float* op = out_t + static_cast<size_t>(col) * out_ld + m;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col + i < n2_valid) op[static_cast<size_t>(i) * out_ld] = live ? a[i] : 0.0f;
+            }
+          } else {
+            uint4 p0 = make_uint4(tc_pack_act(a[0], a[1], f16), tc_pack_act(a[2], a[3], f16), tc_pack_act(a[4], a[5], f16), tc_pack_act(a[6], a[7], f16));
+            uint4 p1 = make_uint4(tc_pack_act(a[8], a[9], f16), tc_pack_act(a[10], a[11], f16), tc_pack_act(a[12], a[13], f16), tc_pack_act(a[14], a[15], f16));
+            if (!live) p0 = p1 = make_uint4(0, 0, 0, 0);  // padding rows of the layout stay zero
+            const uint32_t obuf = box_base + ob * kChBoxBytes;
+            ptx::sts_u4(obuf + ch0, p0);
+            ptx::sts_u4(obuf + ch1, p1);
+          }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&my_written[ob]);
@@ -502,8 +525,11 @@ bool tc_chain_supported(int k1, int n1, int n2) {
 
 int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
                          int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
-                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16) {
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16, float* tail_out_t,
+                         int tail_out_ld, int tail_n2_valid) {
   if (!tc_chain_supported(k1, n1, n2)) return fail(P3_ERR_UNSUPPORTED, "tc_chain: shape not supported");
+  if (tail_out_t && (act2_mode != kActIdentity || tail_n2_valid <= 0 || tail_n2_valid > n2 || tail_out_ld < rows))
+    return fail(P3_ERR_INVALID_ARG, "tc_chain: tail form needs an identity output and n2_valid <= n2");
   if (!in || !w1 || !w2 || !residual_f16 || !raw_f16 || !scale1 || !shift1 || !out2)
     return fail(P3_ERR_INVALID_ARG, "tc_chain: null argument");
   TcChainPlan* p = new TcChainPlan();
@@ -517,6 +543,10 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
   p->shift2 = shift2;
   p->act2_mode = act2_mode;
   p->f16 = op_f16 ? 1 : 0;
+  p->tail = tail_out_t ? 1 : 0;
+  p->out_t = tail_out_t;
+  p->out_ld = tail_out_ld;
+  p->n2_valid = tail_n2_valid;
   p->acc2_stages = (512 - n1) / n2 >= 2 ? 2 : 1;
   p->tmem_cols = 512;
   {  // split what is left of shared memory between the A1 ring (up to one tile) and the box pool (up to 5 per quarter)
@@ -600,7 +630,7 @@ int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
   P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
                         p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->a1_stages, p->n_boxes, p->tmem_cols, p->scale1, p->shift1, p->scale2,
-                        p->shift2, p->act2_mode, p->trace, p->f16));
+                        p->shift2, p->act2_mode, p->trace, p->f16, p->tail, p->out_t, p->out_ld, p->n2_valid));
   return P3_OK;
 }
 

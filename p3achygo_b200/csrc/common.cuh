@@ -98,7 +98,10 @@ struct TcChainPlan;
 bool tc_chain_supported(int k1, int n1, int n2);
 int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const __nv_bfloat16* w2, int rows, int k1, int n1,
                          int n2, const void* residual_f16, void* raw_f16, const float* scale1, const float* shift1, void* out2,
-                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16 = false);
+                         const float* scale2, const float* shift2, int act2_mode, TcChainPlan** out, bool op_f16 = false,
+                         float* tail_out_t = nullptr, int tail_out_ld = 0, int tail_n2_valid = 0);
+// tail form (tail_out_t != nullptr): u = x' (identity), x' is not stored, out2 is ignored and act2(W2*u) (identity) is written
+// as fp32, channel-major [tail_n2_valid, tail_out_ld] - the tower's last expand fused with the heads' 1x1 conv
 void tc_chain_plan_destroy(TcChainPlan* p);
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
 

@@ -131,6 +131,7 @@ struct Step {
   // fused block boundary (bf16 mode): `layer` = the block's expand conv, `layer2` = the next block's reduce conv
   ConvLayer* layer2 = nullptr;
   TcChainPlan* cplan = nullptr;
+  bool tail = false;  // cplan is the tail form: last expand + the heads' 1x1 conv
   TcPwPlan* pplan = nullptr;  // stand-alone 1x1 layer on the CTA-pair kernel (pw_tc.cu) instead of layer->plan
 };
 
@@ -159,7 +160,8 @@ struct p3_engine {
   p3_leaf_result* h_leaf = nullptr;  // pinned: the serial path's compact results (P3_RESULT_LEAF)
   int result_mode = P3_RESULT_FULL;
   // activations
-  DevBuf xraw, actA, actB, actS0, actS1, rawB, pgv;
+  DevBuf xraw, actA, actB, actS0, actS1, rawB, pgv, head_w_pad;
+  bool head_fused = false;  // the tower's last expand and the heads' 1x1 conv run as one launch (chain_tc.cu, tail form)
   // weights
   DevBuf init_wt, init_wt_bf16, gs_w, gs_b, ident_scale, ident_shift;
   bool init_smem = false;  // init conv with the bf16 weight table resident in shared memory
@@ -311,8 +313,7 @@ struct p3_engine {
       if (rc) return rc;
     }
     if (with_events) P3_CUDA(cudaEventRecord(ev[2], stream));
-    rc = run_conv(head_step);
-    if (rc) return rc;
+    if (!head_fused && (rc = run_conv(head_step))) return rc;
     rc = heads_launch(pgv.as<float>(), batch, hw, to_host ? h_results : d_results.as<p3_infer_result>(), d_aux.as<p3_aux_result>(),
                       stream, !bf16, d_sym.as<int8_t>(), d_leaf.as<p3_leaf_result>());
     if (rc) return rc;
@@ -754,6 +755,8 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
   const bool chain_enabled = !(env_chain && std::atoi(env_chain) == 0);
   const char* env_cb = std::getenv("P3_TC_CHAIN_BCAST");
   const bool chain_bcast = !(env_cb && std::atoi(env_cb) == 0);
+  const char* env_tail = std::getenv("P3_TC_TAIL");
+  const bool tail_enabled = !(env_tail && std::atoi(env_tail) == 0);
   for (int i = 0; i < e.blocks; ++i) {
     BlockDesc& bk = blocks[i];
     const bool last_block = i == e.blocks - 1;
@@ -863,6 +866,27 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
           return rc;
         e.program.push_back(cs);
         bcast_conv0_done = true;  // its output is in `other`, which becomes `cur` below
+      } else if (e.bf16 && chain_enabled && tail_enabled && last_block && ex->taps == 1 && 3 * Ch <= 128 && ex->cout == C &&
+                 tc_chain_supported(ex->cin, ex->cout, 128)) {
+        // end of the tower: expand + residual + the heads' 1x1 conv (policy / global-pool / value channels) as ONE launch.  The
+        // heads take the raw trunk output (no BN, no mish: model.py:783-786, 887-889), so u = x'; nothing reads x' afterwards.
+        // The head conv's 3 * Ch output channels are padded to a 128-wide N tile with zero weight rows.
+        if ((rc = e.head_w_pad.alloc(static_cast<size_t>(128) * C * 2))) return rc;
+        P3_CUDA(cudaMemset(e.head_w_pad.p, 0, e.head_w_pad.bytes));
+        P3_CUDA(cudaMemcpy(e.head_w_pad.p, e.head_conv->w_bf16.p, static_cast<size_t>(3 * Ch) * C * 2, cudaMemcpyDeviceToDevice));
+        Step cs;
+        cs.kind = kStepChain;
+        cs.layer = ex;
+        cs.layer2 = e.head_conv;
+        cs.in = s0;
+        cs.tail = true;
+        if ((rc = tc_chain_plan_create(reinterpret_cast<const __nv_bfloat16*>(s0), ex->w_bf16.as<__nv_bfloat16>(),
+                                       e.head_w_pad.as<__nv_bfloat16>(), e.rows, ex->cin, ex->cout, 128, e.xraw.p, e.xraw.p, e.first_scale,
+                                       e.first_shift, s1, nullptr, nullptr, kActIdentity, &cs.cplan, e.f16, e.pgv.as<float>(), e.rows,
+                                       3 * Ch)))
+          return rc;
+        e.program.push_back(cs);
+        e.head_fused = true;
       } else if ((rc = add_conv(ex, s0, e.xraw.p, raw_dst, end_act, end_mode, next_first))) {
         return rc;
       }
@@ -895,7 +919,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     s.ep.raw_out = e.pgv.as<float>();
     s.ep.op_f16 = e.f16;
     s.ep.raw_transposed = true;  // channel-major [3Ch, rows]: what the heads kernel reads coalesced
-    if (e.bf16) {
+    if (e.bf16 && !e.head_fused) {
       int r = tc_conv_plan_create(reinterpret_cast<const __nv_bfloat16*>(head_in), e.head_conv->w_bf16.as<__nv_bfloat16>(),
                                   e.rows, C, 3 * Ch, 1, e.head_conv->tap_off.data(), s.ep, &e.head_conv->plan);
       if (r) return r;
@@ -985,7 +1009,7 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     mac += C * Ch * Pn + Ch * Pn + 2.0 * 2 * Ch * Cv + Cv * 66.0 + 2.0 * Ch * Cv + 2.0 * 800 * Cv;
     e.flops_per_pos = 2.0 * mac;
   }
-  e.launches = 2 + static_cast<int>(e.program.size()) + 2;
+  e.launches = 2 + static_cast<int>(e.program.size()) + (e.head_fused ? 1 : 2);
   return P3_OK;
 }
 
@@ -1394,9 +1418,10 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
                         (s.ep.raw_out ? s.layer->cout * rsz : 0.0)));
     } else if (s.kind == kStepChain) {
       rc = tc_chain_launch(s.cplan, e->stream);
-      cls.push_back(7);
+      cls.push_back(s.tail ? 5 : 7);  // the tail form is the head conv's launch
       fl.push_back(2.0 * (double(s.layer->cin) * s.layer->cout + double(s.layer2->cin) * s.layer2->cout) * Pn * B);
-      by.push_back(R * (s.layer->cin * esz + 2.0 * s.layer->cout * rsz + s.layer2->cout * esz));  // t, x in, x' out, next reduce out
+      if (s.tail) by.push_back(R * (s.layer->cin * esz + s.layer->cout * rsz + s.layer2->cout * 4.0));  // t, x in, fp32 head channels out
+      else by.push_back(R * (s.layer->cin * esz + 2.0 * s.layer->cout * rsz + s.layer2->cout * esz));  // t, x in, x' out, next reduce out
     } else {
       rc = e->run_broadcast(s);
       cls.push_back(4); fl.push_back(2.0 * e->C * Pn * Pn * B);
@@ -1404,10 +1429,12 @@ int p3_engine_profile(p3_engine* e, float ms[P3_NUM_KERNEL_CLASSES], int launche
     }
     P3_CUDA(rec());
   }
-  if (!rc) rc = e->run_conv(e->head_step);
-  cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
-  by.push_back(R * (e->C * (e->bf16 ? esz : 4.0) + 3.0 * e->Ch * 4.0));
-  P3_CUDA(rec());
+  if (!e->head_fused) {
+    if (!rc) rc = e->run_conv(e->head_step);
+    cls.push_back(5); fl.push_back(2.0 * e->C * 3.0 * e->Ch * Pn * B);
+    by.push_back(R * (e->C * (e->bf16 ? esz : 4.0) + 3.0 * e->Ch * 4.0));
+    P3_CUDA(rec());
+  }
   if (!rc) rc = heads_launch(e->pgv.as<float>(), e->batch, e->hw, e->d_results.as<p3_infer_result>(), e->d_aux.as<p3_aux_result>(), e->stream, !e->bf16, e->d_sym.as<int8_t>(), e->d_leaf.as<p3_leaf_result>());
   cls.push_back(6); fl.push_back(0.0);
   by.push_back(R * 3.0 * e->Ch * 4.0 + B * (sizeof(p3_infer_result) + sizeof(p3_aux_result) + sizeof(p3_leaf_result)));

@@ -480,6 +480,29 @@ def test_first_layer_against_oracle_and_explicit_im2col_kernel(config, B, weight
         assert np.abs(got[b] - r).max() <= 2e-2 * max(1.0, np.abs(r).max()), (config, b)
 
 
+def test_stream_padding_rows_stay_zero_over_repeated_runs(weight_dir, golden_positions):
+    """The first layer writes board points only (init_tc2.cu): nothing may leave values in the residual stream's padding rows /
+    columns, or they would pile up run after run (the 3x3 residual kernel's outputs there are not zero by themselves) and trip
+    the range check of a healthy net.  Classic blocks = the 3x3 kernel with a residual."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir("b15c192_classic")
+    feats = golden_positions["feats"]
+    B = 160
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    eng.LoadBatchAll(feats[np.arange(B) % len(feats)])
+    eng.RunInference()
+    mx0, sat0 = eng.RangeCheck()
+    for _ in range(6):
+        eng.RunInference()
+    mx1, sat1 = eng.RangeCheck()
+    x, a = eng.FirstLayer(cfg.channels)
+    eng.close()
+    live = np.array([20 + r * 20 + c for r in range(19) for c in range(19)])
+    pad = np.setdiff1d(np.arange(400), live)
+    assert sat0 == 0 and sat1 == 0 and mx1 == mx0
+    assert not x[:, pad].any() and not a[:, pad].any()
+
+
 # ---- compact leaf records, per-bank auxiliary outputs, ownership symmetry, root sampling on resident logits ---------------------
 @pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
 def test_leaf_results_equal_initfields_of_full_results(precision_name, weight_dir, golden_positions):
