@@ -62,14 +62,9 @@ def kernel_source_hash() -> str:
     return h.hexdigest()[:16]
 
 
-def selfplay_leg(wpath: str, device: int, seconds: float):
-    """Self-play moves/s through the reference's OWN, unmodified search: oracle/_ref/libp3refnn.so = cc/nn/nn_interface.cc +
-    cc/mcts/* + cc/game/* compiled from /root/reference (oracle/Makefile) and linked with the product's nn::B200Engine adapter;
-    game threads call GumbelEvaluator::SearchRoot per move (cc/mcts/gumbel.cc:260).  The engine under test is libp3b200; the
-    callers are the reference's (that is the point: they drop onto it unchanged).  None when the harness was not built."""
+def selfplay_child(wpath: str, device: int, seconds: float):
+    """Body of the self-play leg; runs in a child process (see selfplay_leg) and prints its result as one SELFPLAY_JSON line."""
     path = os.path.join(ROOT, "oracle", "_ref", "libp3refnn.so")
-    if not os.path.exists(path):
-        return None
     L = ctypes.CDLL(path)
     ci = ctypes.c_int
     L.ref_selfplay_gumbel.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, ctypes.POINTER(ctypes.c_longlong),
@@ -80,10 +75,32 @@ def selfplay_leg(wpath: str, device: int, seconds: float):
         secs = ctypes.c_double(0)
         rc = L.ref_selfplay_gumbel(wpath.encode(), device, 8, 128, n, k, seconds, 1 << 20, 300, out, ctypes.byref(secs))
         if rc != 0 or secs.value <= 0:
-            return None
+            runs = None
+            break
         runs.append({"n": n, "k": k, "moves": int(out[0]), "seconds": secs.value, "moves_per_s": out[0] / secs.value,
                      "leaf_evals_per_s": out[1] / secs.value, "avg_engine_batch": out[1] / max(out[2], 1), "games_finished": int(out[3])})
-    return runs
+    print("SELFPLAY_JSON " + json.dumps(runs), flush=True)
+
+
+def selfplay_leg(wpath: str, device: int, seconds: float):
+    """Self-play moves/s through the reference's OWN, unmodified search: oracle/_ref/libp3refnn.so = cc/nn/nn_interface.cc +
+    cc/mcts/* + cc/game/* compiled from /root/reference (oracle/Makefile) and linked with the product's nn::B200Engine adapter;
+    game threads call GumbelEvaluator::SearchRoot per move (cc/mcts/gumbel.cc:260).  The engine under test is libp3b200; the
+    callers are the reference's (that is the point: they drop onto it unchanged).  None when the harness was not built.
+    Runs in a child process: 1024 game threads of reference code are test infrastructure, and whatever happens to them must not
+    take the bench line with it ({"error": ...} instead)."""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libp3refnn.so")):
+        return None
+    cmd = [sys.executable, os.path.abspath(__file__), "--selfplay-child", wpath, str(device), str(seconds)]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=4 * seconds + 240)
+    except subprocess.TimeoutExpired:
+        return {"error": "self-play child timed out"}
+    for ln in p.stdout.splitlines():
+        if ln.startswith("SELFPLAY_JSON "):
+            return json.loads(ln[len("SELFPLAY_JSON "):])
+    return {"error": f"self-play child exited {p.returncode}: {(p.stderr or '').strip().splitlines()[-1:]}"}
 
 
 def load_positions():
@@ -300,6 +317,8 @@ def run_reference_arm(args):
 
 # --------------------------------------------------------------------------------------------------
 def main():
+    if len(sys.argv) == 5 and sys.argv[1] == "--selfplay-child":
+        return selfplay_child(sys.argv[2], int(sys.argv[3]), float(sys.argv[4]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -509,15 +528,24 @@ def main():
         barrier()
         sp = selfplay_leg(wpath, local, float(os.environ.get("P3_SELFPLAY_SECONDS", "8")))
         barrier()
-        if sp is not None:
-            for r in sp:
-                r["moves_per_s_all_gpus"] = reduce_max(r["moves_per_s"], op="sum")
+        # every rank takes part in the same three reductions whatever happened to its child
+        ok = isinstance(sp, list) and len(sp) == 2
+        any_failed = reduce_max(0.0 if ok else 1.0) > 0
+        totals = [reduce_max(sp[i]["moves_per_s"] if ok else 0.0, op="sum") for i in range(2)]
+        if ok and not any_failed:
+            for r, t in zip(sp, totals):
+                r["moves_per_s_all_gpus"] = t
             selfplay = {"unit": "moves/s", "host_cores": os.cpu_count(), "interfaces_per_gpu": 8, "slots_per_interface": 128,
                         "runs": sp,
                         "what": "reference cc/nn/nn_interface.cc + cc/mcts (unmodified, compiled from /root/reference into "
                                 "oracle/_ref/libp3refnn.so) over nn::B200Engine: one game thread per slot, GumbelEvaluator::SearchRoot per "
                                 "move from the empty board, NN cache 2^20 keyed on the last move (cc/selfplay/main.cc:177), timeout 400 us; "
-                                "Game -> GoFeatures (ladders, liberties) on the host cores as the reference does it"}
+                                "Game -> GoFeatures (ladders, liberties) on the host cores as the reference does it; run in a child "
+                                "process"}
+        elif isinstance(sp, dict):
+            selfplay = sp  # {"error": ...}: the child failed on this rank
+        elif sp is not None:
+            selfplay = {"error": "the self-play child failed on another rank"}
 
     line = {
         "metric": "leaf evals/sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,

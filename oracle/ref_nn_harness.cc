@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <random>
@@ -60,6 +61,9 @@ class CheckedEngine final : public nn::Engine {
     const int gen = generation_.fetch_add(1, std::memory_order_acq_rel) + 1;
     in_run_.store(true, std::memory_order_release);
     inner_->RunInference();
+    // P3_CHECKED_SLEEP_US: stretch the run (the host-side timing a profiler or a much slower device produces)
+    static const int us = std::getenv("P3_CHECKED_SLEEP_US") ? std::atoi(std::getenv("P3_CHECKED_SLEEP_US")) : 0;
+    if (us > 0) std::this_thread::sleep_for(std::chrono::microseconds(us));
     for (auto& g : result_gen_) g.store(gen, std::memory_order_relaxed);
     in_run_.store(false, std::memory_order_release);
     runs.fetch_add(1, std::memory_order_relaxed);
@@ -90,7 +94,10 @@ class NullEngine final : public nn::Engine {
   Kind kind() override { return Kind::kUnknown; }
   std::string path() override { return "null"; }
   void LoadBatch(int, const nn::GoFeatures&) override {}
-  void RunInference() override {}
+  void RunInference() override {  // P3_NULL_ENGINE_SLEEP_US: a slow device (what a profiler makes of the real one)
+    static const int us = std::getenv("P3_NULL_ENGINE_SLEEP_US") ? std::atoi(std::getenv("P3_NULL_ENGINE_SLEEP_US")) : 0;
+    if (us > 0) std::this_thread::sleep_for(std::chrono::microseconds(us));
+  }
   void GetBatch(int t, nn::NNInferResult& r) override {
     for (int i = 0; i < constants::kMaxMovesPerPosition; ++i) {
       r.move_logits[i] = 0.001f * static_cast<float>((i * 7 + t) % 13);

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """Turns the ncu artefacts of one gpurun call into the tracked summaries under profiles/.
 
-    python profiles/summarize_ncu.py <tag> <launch_list.csv> <full_capture.ncu-rep> [more .ncu-rep ...]
+    [ROUND=r2] python profiles/summarize_ncu.py <tag> <launch_list.csv> <full_capture.ncu-rep | raw_page.csv> [more ...]
 
-Writes profiles/r1_launches_<tag>.csv (copy), profiles/r1_ncu_full_<tag>_summary.csv (one row per captured launch) and
-profiles/r1_ncu_traffic_<tag>.json (per-kernel means + share of the step in the launch list; bench.py reads
-roofline.traffic from the newest of these).  Needs the `ncu` CLI (no GPU) to read the .ncu-rep files.
+Writes profiles/<round>_launches_<tag>.csv (copy), profiles/<round>_ncu_full_<tag>_summary.csv (one row per captured launch)
+and the per-kernel means + share of the step in the launch list: profiles/r1_ncu_traffic_<tag>.json for round 1, and from
+round 2 on profiles/<round>_ncu_traffic.json, which carries `kernel_source_hash` (bench.kernel_source_hash() of the sources the
+capture was taken from); bench.py reads roofline.traffic from it and drops it when the sources have changed since.  Needs the
+`ncu` CLI (no GPU) to read .ncu-rep files.
 """
 import collections
 import csv
@@ -18,6 +20,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROUND = os.environ.get("ROUND", "r2")
 KERNELS = r"(tc_conv3x3_pair_kernel|tc_chain_pair_kernel|tc_pw_pair_kernel|tc_broadcast_kernel|init_tc_kernel|tc_conv3x3_res_kernel|tc_conv_kernel|heads_kernel|encode_kernel|[a-z_0-9]+_kernel)"
 KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -79,10 +82,10 @@ def raw_rows(rep):
 
 def main():
     tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
-    shutil.copy(launches, os.path.join(HERE, f"r1_launches_{tag}.csv"))
+    shutil.copy(launches, os.path.join(HERE, f"{ROUND}_launches_{tag}.csv"))
     shares, tot, n = launch_shares(launches)
     rows = [d for rep in reps for d in raw_rows(rep)]
-    with open(os.path.join(HERE, f"r1_ncu_full_{tag}_summary.csv"), "w", newline="") as f:
+    with open(os.path.join(HERE, f"{ROUND}_ncu_full_{tag}_summary.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["# ncu --set full --clock-control none --import-source on; bench.py --steps 2 --warmup 3 --no-cpu-baseline "
                     "(b12c256btl3 @ 1024); one captured launch per row; time in us, dram bytes in MB"])
@@ -92,8 +95,13 @@ def main():
     acc = collections.defaultdict(list)
     for d in rows:
         acc[kname(d["Kernel Name"])].append(d)
-    out = {"source": f"profiles/r1_ncu_full_{tag}_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; "
-                     f"b12c256btl3 batch 1024); shares from profiles/r1_launches_{tag}.csv ({n} launches, {tot:.0f} us)", "kernels": {}}
+    out = {"source": f"profiles/{ROUND}_ncu_full_{tag}_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+                     f"b12c256btl3 batch 1024); shares from profiles/{ROUND}_launches_{tag}.csv ({n} launches, {tot:.0f} us)", "kernels": {}}
+    if ROUND != "r1":
+        sys.path.insert(0, os.path.dirname(HERE))
+        import bench
+        out["kernel_source_hash"] = bench.kernel_source_hash()
+        out["tag"] = tag
     for k, v in acc.items():
         f = lambda key: sum(float(d.get(key) or 0) for d in v) / len(v)  # noqa: E731
         out["kernels"][k] = {"captured_launches": len(v), "dram_read_bytes": f("dram__bytes_read.sum") * 1e6,
@@ -102,7 +110,7 @@ def main():
                              "time_us_under_ncu": f("gpu__time_duration.sum"),
                              "tensor_pipe_active_pct": f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                              "share_of_step_in_launch_list": shares.get(k, {}).get("share")}
-    json.dump(out, open(os.path.join(HERE, f"r1_ncu_traffic_{tag}.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(HERE, f"r1_ncu_traffic_{tag}.json" if ROUND == "r1" else f"{ROUND}_ncu_traffic.json"), "w"), indent=1)
     for k, s in shares.items():
         print(f"{k:28s} n={s['launches']:3d} avg={s['sum_us'] / s['launches']:7.1f} us share={s['share']:.3f}")
     for k, v in out["kernels"].items():
