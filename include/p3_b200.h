@@ -285,7 +285,10 @@ int p3_legal_mask(int device, const int8_t* boards, const int8_t* colors, const 
  *   legal    [n,362]  Game::IsValidMove for colors[b] over all encodings, cc/game/game.cc:45-51 -> Board::PlayMoveDry,
  *                     cc/game/board.cc:595-644: occupied, pass-alive, self-capture AND positional superko,
  *   status   [n]      0 = ok, bit 0 = the move list is not a legal game, bit 1 = candidate list overflow in the reader,
- *                     bit 3 (on position 0) = the reader's watchdog fired: the batch's laddered grids are incomplete.
+ *                     bit 3 (on position 0) = the reader's watchdog fired (a warp polled ~10 s for another warp's part of a
+ *                     split search): p3_game_derive, p3_engine_run_inference and p3_engine_wait then run the batch ONCE more
+ *                     with splitting off (every search on the warp that claimed it; cannot stall, ~10 ms for a hard batch)
+ *                     and only report the bit / P3_ERR_CUDA if that run raises it too.
  * moves [n,max_moves] int16: board point 0..360 or 361 = pass, + P3_MOVE_WHITE for a white move; entries beyond
  * num_moves[b] are ignored.  The reference's pass-alive regions (GroupTracker::BensonSolver, board.cc:246-462, computed at
  * every pass from the game's third on, board.cc:582-593, and prohibited for both colours, :607) are derived from the record

@@ -231,6 +231,7 @@ int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves
 struct LadderWorkspace;   // preallocated buffers of the game-record kernels for batches up to n, move lists up to max_moves
 int ladder_workspace_create(int n, int max_moves, LadderWorkspace** out);
 void ladder_workspace_destroy(LadderWorkspace* w);
+void ladder_workspace_set_unsplit(LadderWorkspace* w, bool on);  // watchdog retry: searches stay on the warp that claimed them
 // asynchronous form of ladder_run on a workspace; ev (optional) = 4 events recorded around the three kernels
 int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_num_moves, const int8_t* d_forbidden,
                    const int8_t* d_colors, int n, int8_t* d_boards, int8_t* d_laddered, uint8_t* d_legal, int32_t* d_status,

@@ -362,9 +362,14 @@ struct p3_engine {
 
   // after the run has completed: a slot whose move list was not a legal game record is an error (the reference CHECK-fails on
   // impossible states); the other slots' results are valid
-  int check_game_records(Bank& bk) {
+  // `retry` (optional): set instead of failing when the reader's watchdog fired, so that the caller can run the batch again unsplit
+  int check_game_records(Bank& bk, bool* retry = nullptr) {
     if (!bk.derived) return P3_OK;
     const bool watchdog = (bk.h_gstatus[0] & 8) != 0;  // the reader gave up (ladder.cu): the batch's laddered grids are incomplete
+    if (watchdog && retry) {
+      *retry = true;
+      return P3_OK;
+    }
     for (int b = 0; b < batch; ++b) {
       const int st = bk.h_gstatus[b] & ~8;
       if (bk.sub_nmoves[b] < 0 || st == 0) continue;
@@ -1107,9 +1112,7 @@ int p3_engine_load_batch_sym(p3_engine* e, int batch_id, const p3_go_features* f
   return P3_OK;
 }
 
-int p3_engine_run_inference(p3_engine* e) {
-  if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
-  P3_CUDA(cudaSetDevice(e->device));
+static int run_inference_once(p3_engine* e) {
   static const bool trace = std::getenv("P3_TIME_RUN") != nullptr;  // perf experiments: where RunInference's wall time goes
   if (trace) P3_CUDA(cudaEventRecord(e->ev[0], e->stream));
   P3_CUDA(cudaMemcpyAsync(e->d_feats.p, e->h_feats, sizeof(p3_go_features) * e->batch, cudaMemcpyHostToDevice, e->stream));
@@ -1137,7 +1140,23 @@ int p3_engine_run_inference(p3_engine* e) {
     cudaEventElapsedTime(&d2h, e->ev[2], e->ev[3]);
     std::fprintf(stderr, "[p3 run] h2d %.1f us  device %.1f us  d2h %.1f us\n", h2d * 1e3f, dev * 1e3f, d2h * 1e3f);
   }
-  rc = e->check_game_records(e->banks[0]);
+  return P3_OK;
+}
+
+int p3_engine_run_inference(p3_engine* e) {
+  if (!e) return fail(P3_ERR_INVALID_ARG, "run_inference: null engine");
+  P3_CUDA(cudaSetDevice(e->device));
+  int rc = run_inference_once(e);
+  if (rc) return rc;
+  bool retry = false;
+  rc = e->check_game_records(e->banks[0], &retry);
+  if (!rc && retry) {  // the ladder reader's watchdog fired: the same batch again with the searches unsplit (cannot stall)
+    std::fprintf(stderr, "[p3] ladder reader watchdog fired; re-running the batch unsplit\n");
+    p3::ladder_workspace_set_unsplit(e->ladder_ws, true);
+    rc = run_inference_once(e);
+    p3::ladder_workspace_set_unsplit(e->ladder_ws, false);
+    if (!rc) rc = e->check_game_records(e->banks[0]);
+  }
   if (rc) return rc;
   const char* rc_env = std::getenv("P3_RANGE_CHECK");
   if (rc_env && std::atoi(rc_env) != 0) {  // validation mode: fail loudly instead of evaluating a net whose fp16 residual stream saturates
@@ -1192,13 +1211,8 @@ int p3_engine_load_game_bank(p3_engine* e, int bank, int batch_id, const int16_t
   return P3_OK;
 }
 
-int p3_engine_submit(p3_engine* e, int bank) {
-  if (!e || bank < 0 || bank >= P3_NUM_BANKS) return fail(P3_ERR_INVALID_ARG, "submit: bad argument");
-  p3_engine::Bank& bk = e->banks[bank];
-  if (bk.in_flight.exchange(1, std::memory_order_acq_rel))
-    return fail(P3_ERR_INVALID_ARG, "submit: bank already in flight (p3_engine_wait it first)");
-  std::lock_guard<std::mutex> lock(e->submit_mu);
-  P3_CUDA(cudaSetDevice(e->device));
+// everything p3_engine_submit enqueues for one bank (caller holds submit_mu)
+static int submit_enqueue(p3_engine* e, p3_engine::Bank& bk) {
   const size_t fbytes = sizeof(p3_go_features) * e->batch, rbytes = sizeof(p3_infer_result) * e->batch;
   // game state of this bank -> its device staging copy, on the H2D stream (overlaps the other bank's kernels)
   P3_CUDA(cudaMemcpyAsync(bk.d_feats.p, bk.h_feats, fbytes, cudaMemcpyHostToDevice, e->h2d_stream));
@@ -1227,14 +1241,39 @@ int p3_engine_submit(p3_engine* e, int bank) {
   return P3_OK;
 }
 
+int p3_engine_submit(p3_engine* e, int bank) {
+  if (!e || bank < 0 || bank >= P3_NUM_BANKS) return fail(P3_ERR_INVALID_ARG, "submit: bad argument");
+  p3_engine::Bank& bk = e->banks[bank];
+  if (bk.in_flight.exchange(1, std::memory_order_acq_rel))
+    return fail(P3_ERR_INVALID_ARG, "submit: bank already in flight (p3_engine_wait it first)");
+  std::lock_guard<std::mutex> lock(e->submit_mu);
+  P3_CUDA(cudaSetDevice(e->device));
+  return submit_enqueue(e, bk);
+}
+
 int p3_engine_wait(p3_engine* e, int bank) {
   if (!e || bank < 0 || bank >= P3_NUM_BANKS) return fail(P3_ERR_INVALID_ARG, "wait: bad argument");
   p3_engine::Bank& bk = e->banks[bank];
   if (!bk.in_flight.load(std::memory_order_acquire)) return fail(P3_ERR_INVALID_ARG, "wait: bank was not submitted");
   P3_CUDA(cudaSetDevice(e->device));
   P3_CUDA(cudaEventSynchronize(bk.ev_d2h));
+  bool retry = false;
+  int rc = e->check_game_records(bk, &retry);
+  if (!rc && retry) {
+    // the ladder reader's watchdog fired: this bank again, unsplit, behind whatever the other bank has queued (the bank's host
+    // slots are untouched until p3_engine_wait returns; the other bank waits at submit_mu for the duration of the enqueue only,
+    // but a submit of it that slips in between would run split again - the flag is per workspace - so hold the lock to the end)
+    std::fprintf(stderr, "[p3] ladder reader watchdog fired; re-running bank %d unsplit\n", bank);
+    std::lock_guard<std::mutex> lock(e->submit_mu);
+    p3::ladder_workspace_set_unsplit(e->ladder_ws, true);
+    rc = submit_enqueue(e, bk);
+    cudaError_t se = cudaEventSynchronize(bk.ev_d2h);
+    p3::ladder_workspace_set_unsplit(e->ladder_ws, false);
+    if (!rc && se != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("wait (unsplit retry): ") + cudaGetErrorString(se));
+    if (!rc) rc = e->check_game_records(bk);
+  }
   bk.in_flight.store(0, std::memory_order_release);
-  return e->check_game_records(bk);
+  return rc;
 }
 
 int p3_engine_get_batch_bank(p3_engine* e, int bank, int batch_id, p3_infer_result* result) {

@@ -822,6 +822,7 @@ __global__ void __launch_bounds__(256) legal_exact_kernel(const uint32_t* __rest
 // Host entry: all buffers are device pointers except where noted; scratch is allocated per call.
 struct LadderWorkspace {
   int n = 0, max_moves = 0, blocks = 0, item_cap = 0, node_cap = 0, pool_cap = 0, split_nodes = kSplitNodesDefault, sms = 148;
+  int split_saved = -1;  // >= 0 while the reader runs unsplit (ladder_workspace_set_unsplit)
   uint32_t* rows = nullptr;
   uint64_t* hist = nullptr;
   int32_t* n_hist = nullptr;
@@ -833,6 +834,23 @@ struct LadderWorkspace {
   int* ready = nullptr;
   DeepFrames* scratch = nullptr;
 };
+
+// The retry path of the reader's watchdog (status bit 3): with splitting off every search runs on the warp that claimed it, no
+// warp ever waits for another one's item, and the reader cannot stall - at the round-1 price (one 4 598-node search = 10 ms).
+void ladder_workspace_set_unsplit(LadderWorkspace* w, bool on) {
+  if (!w) return;
+  if (on && w->split_saved < 0) {
+    w->split_saved = w->split_nodes;
+    w->split_nodes = 0x7fffffff;
+  } else if (!on && w->split_saved >= 0) {
+    w->split_nodes = w->split_saved;
+    w->split_saved = -1;
+  }
+}
+
+namespace {
+__global__ void force_watchdog_kernel(int32_t* status) { atomicOr(&status[0], 8); }
+}  // namespace
 
 void ladder_workspace_destroy(LadderWorkspace* w) {
   if (!w) return;
@@ -899,6 +917,9 @@ int ladder_enqueue(LadderWorkspace* w, const int16_t* d_moves, const int32_t* d_
         w->tasks, w->queue, w->nodes, w->node_cap, w->items, w->pool, w->pool_cap, w->ready, w->item_cap, w->rows, w->hist, w->n_hist,
         w->max_moves, w->scratch, d_laddered, d_status, w->split_nodes);
     P3_CUDA(cudaGetLastError());
+    // test hook: pretend the watchdog fired on every split run, so that the unsplit retry is what produces the results
+    const bool force = std::getenv("P3_LADDER_FORCE_WATCHDOG") != nullptr;
+    if (force && w->split_saved < 0) force_watchdog_kernel<<<1, 1, 0, stream>>>(d_status);
   }
   if (ev) cudaEventRecord(ev[2], stream);
   if (d_legal && d_colors) {
@@ -934,6 +955,17 @@ int ladder_run(const int16_t* d_moves, const int32_t* d_num_moves, int max_moves
                       trace ? ev : nullptr);
   cudaError_t se = cudaStreamSynchronize(stream);
   if (!rc && se != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("ladder_run: ") + cudaGetErrorString(se));
+  if (!rc && d_laddered && d_status) {  // the reader's watchdog fired: run the batch again without splitting (cannot stall)
+    int32_t st0 = 0;
+    if (cudaMemcpy(&st0, d_status, sizeof(st0), cudaMemcpyDeviceToHost) == cudaSuccess && (st0 & 8)) {
+      std::fprintf(stderr, "[p3 ladder] reader watchdog fired; re-running %d records unsplit\n", n);
+      ladder_workspace_set_unsplit(w, true);
+      rc = ladder_enqueue(w, d_moves, d_num_moves, d_forbidden, d_colors, n, d_boards, d_laddered, d_legal, d_status, stream, nullptr);
+      se = cudaStreamSynchronize(stream);
+      ladder_workspace_set_unsplit(w, false);
+      if (!rc && se != cudaSuccess) rc = fail(P3_ERR_CUDA, std::string("ladder_run (unsplit retry): ") + cudaGetErrorString(se));
+    }
+  }
   if (trace && !rc) {
     float a = 0, b = 0, c = 0;
     Queue h{};

@@ -210,6 +210,49 @@ def test_engine_game_record_slots_equal_feature_slots(pipelined, games, weight_d
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path_kind", ["derive", "run_inference", "banks"])
+def test_reader_watchdog_retries_unsplit(path_kind, games, weight_dir, monkeypatch, capfd):
+    """The ladder reader's watchdog (status bit 3: a warp polled ~10 s for a split search's item) is not the end of the batch: the
+    entry points run it again with splitting off - every search stays on the warp that claimed it, nothing waits for another
+    warp - and the results are the reference's.  P3_LADDER_FORCE_WATCHDOG raises the bit after every SPLIT run, so whatever
+    comes back here came from the retry."""
+    from p3achygo_b200 import engine as E
+    monkeypatch.setenv("P3_LADDER_FORCE_WATCHDOG", "1")
+    if path_kind == "derive":
+        sel = slice(0, 400)
+        boards, lad, legal, status = E.game_derive(games["moves"][sel], games["num_moves"][sel], colors=games["colors"][sel],
+                                                   forbidden=games["forbidden"][sel])
+        assert not status.any()
+        assert np.array_equal(lad, games["ladder"][sel]) and np.array_equal(legal, games["legal"][sel])
+        assert "unsplit" in capfd.readouterr().err
+        return
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    B = 48
+    idx = np.concatenate([np.arange(0, 17), np.arange(100, 100 + B - 17)])
+    feats = _features_from_fixture(games, idx)
+    eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+    for b in range(B):
+        eng.LoadBatchSym(b, feats[b], 0)
+    eng.RunInference()
+    want = [eng.GetBatch(b).copy() for b in range(B)]
+    bank = 1 if path_kind == "banks" else 0
+    for b in range(B):
+        g = idx[b]
+        eng.LoadGameBank(bank, b, games["moves"][g][: games["num_moves"][g]], int(games["colors"][g]), 7.5, games["forbidden"][g], 0)
+    if path_kind == "banks":
+        eng.Submit(1)
+        eng.Wait(1)
+    else:
+        eng.RunInference()
+    for b in range(B):
+        got = eng.GetBatchBank(1, b) if path_kind == "banks" else eng.GetBatch(b)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[b][f]), (b, f)
+    eng.close()
+    assert "unsplit" in capfd.readouterr().err
+
+
+@pytest.mark.gpu
 def test_game_derive_matches_oracle_on_fresh_games():
     """GPU against the CPU restatement (oracle/features_oracle.c::orc_game_derive) on fresh seeded games that neither the fixture
     nor the reference has seen: the games are played with the oracle's own exact legality (no /root/reference needed)."""
