@@ -44,7 +44,7 @@ constexpr int kBFixedSmem = (4 * kBBoxes + 1) * kBBoxBytes + 1024 /*align*/ + 51
 
 struct TcBcastPlan {
   CUtensorMap map_wt, map_x, map_act, map_halo;
-  int B, C, n_tile, stages, tmem_cols, grid, f16 = 0;
+  int B, C, n_tile, stages, tmem_cols, grid, f16 = 0, reverse = 0;
   size_t smem_bytes;
   const float *bias_pad, *scale, *shift;
   void* wt_dev = nullptr;
@@ -82,7 +82,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
                     const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_halo, int B, int C,
                     int n_tile, int stages, int tmem_cols,
                     const float* __restrict__ bias_pad, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int f16) {
+                    const float* __restrict__ shift, int f16, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_box = smem;                                  // [4 quarters][kBBoxes] output boxes, then one zero box
@@ -146,6 +146,7 @@ tc_broadcast_kernel(const __grid_constant__ CUtensorMap map_wt, const __grid_con
     const int rest = tile / kBMTiles;
     nt = rest % n_tiles;
     b = rest / n_tiles;
+    if (reverse) b = B - 1 - b;  // from the last position to the first (tile order of a launch: common.cuh, pair_tile_row0)
   };
 
   if (warp == 0) {
@@ -409,6 +410,10 @@ int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const 
   return P3_OK;
 }
 
+void tc_broadcast_plan_set_reverse(TcBcastPlan* p, bool reverse) {
+  if (p) p->reverse = reverse ? 1 : 0;
+}
+
 void tc_broadcast_plan_destroy(TcBcastPlan* p) {
   if (!p) return;
   cudaFree(p->wt_dev);
@@ -418,7 +423,7 @@ void tc_broadcast_plan_destroy(TcBcastPlan* p) {
 
 int tc_broadcast_launch(const TcBcastPlan* p, cudaStream_t stream) {
   tc_broadcast_kernel<<<p->grid, kBThreads, p->smem_bytes, stream>>>(p->map_wt, p->map_x, p->map_act, p->map_halo, p->B, p->C, p->n_tile,
-                                                                     p->stages, p->tmem_cols, p->bias_pad, p->scale, p->shift, p->f16);
+                                                                     p->stages, p->tmem_cols, p->bias_pad, p->scale, p->shift, p->f16, p->reverse);
   P3_CUDA(cudaGetLastError());
   return P3_OK;
 }

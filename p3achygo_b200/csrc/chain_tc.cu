@@ -49,6 +49,7 @@ struct TcChainPlan {
   // tail form (the tower's last expand + the heads' 1x1 conv): u = x' (the heads take the raw trunk output), x' is not stored,
   // and `out` is written as fp32, channel-major [n2_valid, out_ld] (what heads.cu reads), straight from the registers
   int tail = 0, out_ld = 0, n2_valid = 0;
+  int reverse = 0;                      // tile order (common.cuh, pair_tile_row0)
   float* out_t = nullptr;
   unsigned long long* trace = nullptr;  // P3_TC_TRACE
 };
@@ -75,7 +76,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                      int n1, int n2, int acc2_stages, int a1_stages, int n_boxes, int tmem_cols, const float* __restrict__ scale1,
                      const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
                      int act2_mode, unsigned long long* trace, int f16, int tail, float* __restrict__ out_t, int out_ld,
-                     int n2_valid) {
+                     int n2_valid, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n1_slabs = n1 / 64, n2_slabs = n2 / 64;
@@ -107,6 +108,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
   const uint32_t rank = ptx::cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
+  const int rev_last = reverse ? m_tiles - 1 : -1;
   const int n_it = pair < m_tiles ? (m_tiles - pair + n_pairs - 1) / n_pairs : 0;  // tiles of this pair
   const int defer = acc2_stages >= 2 ? 1 : 0;  // epi2 runs one tile behind epi1 (needs the second acc2 stage)
 
@@ -170,12 +172,12 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair; mt < m_tiles; mt += n_pairs) {
-      const int m0 = pair_tile_row0(mt, static_cast<int>(rank));
+      const int m0 = pair_tile_row0(mt, static_cast<int>(rank), rev_last);
       for (int ks = 0; ks < k1_slabs; ++ks) {
         ptx::mbar_wait(&a1_empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
           if (rank == 0) ptx::mbar_arrive_expect_tx(&a1_full[stage], 2 * kChSlabBytes);
-          ptx::tma_load_2d_pair(smem_a1 + stage * kChSlabBytes, &map_a1, ptx::mapa_shared(ptx::smem_u32(&a1_full[stage]), 0),
+          ptx::tma_load_2d_pair_h<P3_HINT_ACT_LOAD>(smem_a1 + stage * kChSlabBytes, &map_a1, ptx::mapa_shared(ptx::smem_u32(&a1_full[stage]), 0),
                                 ks * 64, m0);
         }
         __syncwarp();
@@ -289,7 +291,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       const bool is_epi1 = c.it < n_it && c.idx < n1_slabs;
       if (is_epi1) {
         ptx::mbar_arrive_expect_tx(&my_ready[b], kChBoxBytes);
-        ptx::tma_load_2d(my_box + b * kChBoxBytes, &map_res, &my_ready[b], c.idx * 64, pair_tile_row0(pair + c.it * n_pairs, static_cast<int>(rank)) + q_row);
+        ptx::tma_load_2d_h<P3_HINT_RES_LOAD>(my_box + b * kChBoxBytes, &map_res, &my_ready[b], c.idx * 64, pair_tile_row0(pair + c.it * n_pairs, static_cast<int>(rank), rev_last) + q_row);
       } else {
         ptx::mbar_arrive(&my_ready[b]);
       }
@@ -311,11 +313,11 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         if (is_epi1) {
           ptx::mbar_arrive_remote(a2_full_l + 8u * (g & 1u));  // this quarter's rows of the A2 slab are in place
           if (!tail)
-            ptx::tma_store_2d(&map_raw, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
-                              pair_tile_row0(pair + cur.it * n_pairs, static_cast<int>(rank)) + q_row);
+            ptx::tma_store_2d_h<P3_HINT_RES_STORE>(&map_raw, ptx::smem_u32(my_box) + b * kChBoxBytes, cur.idx * 64,
+                              pair_tile_row0(pair + cur.it * n_pairs, static_cast<int>(rank), rev_last) + q_row);
         } else if (!tail) {  // (tail form: the epilogue warps have stored their fp32 columns themselves)
-          ptx::tma_store_2d(&map_out2, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kChBoxBytes, (cur.idx - (cur.it < n_it ? n1_slabs : 0)) * 64,
-                            pair_tile_row0(pair + (cur.it - defer) * n_pairs, static_cast<int>(rank)) + q_row);
+          ptx::tma_store_2d_h<P3_HINT_ACT_STORE>(&map_out2, ptx::smem_u32(my_box) + b * kChBoxBytes, (cur.idx - (cur.it < n_it ? n1_slabs : 0)) * 64,
+                            pair_tile_row0(pair + (cur.it - defer) * n_pairs, static_cast<int>(rank), rev_last) + q_row);
         }
         ptx::bulk_commit();
         ptx::bulk_wait_read<1>();  // the previous step's store has read its box: that box serves the step n_boxes - 1 ahead
@@ -438,7 +440,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
       // commit latency are never waited for)
       const int it2 = it - defer;
       if (it2 >= 0 && it2 < n_it) {
-        const int m = pair_tile_row0(pair + it2 * n_pairs, static_cast<int>(rank)) + q * 32 + lane;
+        const int m = pair_tile_row0(pair + it2 * n_pairs, static_cast<int>(rank), rev_last) + q * 32 + lane;
         const bool live = m < rows && row_is_live(m % kRowsPerPos);
         const int as = it2 % acc2_stages;
         const long long tc0 = tr ? clock64() : 0;
@@ -611,6 +613,10 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
   return P3_OK;
 }
 
+void tc_chain_plan_set_reverse(TcChainPlan* p, bool reverse) {
+  if (p) p->reverse = reverse ? 1 : 0;
+}
+
 void tc_chain_plan_destroy(TcChainPlan* p) {
   if (p && p->trace) {
     unsigned long long h[16];
@@ -630,7 +636,7 @@ int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
   P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
                         p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->a1_stages, p->n_boxes, p->tmem_cols, p->scale1, p->shift1, p->scale2,
-                        p->shift2, p->act2_mode, p->trace, p->f16, p->tail, p->out_t, p->out_ld, p->n2_valid));
+                        p->shift2, p->act2_mode, p->trace, p->f16, p->tail, p->out_t, p->out_ld, p->n2_valid, p->reverse));
   return P3_OK;
 }
 

@@ -58,6 +58,12 @@ __host__ __device__ inline int pair_tile_count(int rows) { return ((rows / kRows
 __host__ __device__ inline int pair_tile_row0(int mt, int rank) {
   return ((mt / 3) * 2 + rank) * kRowsPerPos + kRowBase + (mt % 3) * 128;
 }
+// Tile order of a launch: consecutive launches walk the batch in opposite directions (rev_last = m_tiles - 1, else -1), so that a
+// kernel starts on the rows its predecessor wrote last - the part of that output the 126 MB L2 still holds - instead of on the
+// rows it wrote first, which are long evicted (every tensor of the b12c256btl3 step at batch 1024 is 105 - 210 MB).
+__host__ __device__ inline int pair_tile_row0(int mt, int rank, int rev_last) {
+  return pair_tile_row0(rev_last >= 0 ? rev_last - mt : mt, rank);
+}
 
 // What a conv epilogue writes besides the raw sum.
 enum ActMode : int {
@@ -89,6 +95,7 @@ struct TcConvPlan;  // TMA maps + tile config for one layer (opaque; built once 
 int tc_conv_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int cin, int cout,
                         int taps, const int* tap_off_host, const ConvEpilogue& ep, TcConvPlan** out);
 void tc_conv_plan_destroy(TcConvPlan* plan);
+bool tc_conv_plan_set_reverse(TcConvPlan* p, bool reverse);  // pair-kernel plans only (returns false otherwise)
 int tc_conv_launch(const TcConvPlan* plan, cudaStream_t stream);
 bool tc_conv_supported(int cin, int cout);
 
@@ -103,6 +110,7 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
 // tail form (tail_out_t != nullptr): u = x' (identity), x' is not stored, out2 is ignored and act2(W2*u) (identity) is written
 // as fp32, channel-major [tail_n2_valid, tail_out_ld] - the tower's last expand fused with the heads' 1x1 conv
 void tc_chain_plan_destroy(TcChainPlan* p);
+void tc_chain_plan_set_reverse(TcChainPlan* p, bool reverse);  // walk the tiles from the last position to the first
 int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream);
 
 // stand-alone 1x1 trunk layers of the bf16 engine (pw_tc.cu): CTA-pair GEMM with resident weights, in-place residual boxes,
@@ -112,6 +120,7 @@ bool tc_pw_supported(int k1, int n1);
 int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows, int k1, int n1, const ConvEpilogue& ep,
                       TcPwPlan** out);
 void tc_pw_plan_destroy(TcPwPlan* p);
+void tc_pw_plan_set_reverse(TcPwPlan* p, bool reverse);
 int tc_pw_launch(const TcPwPlan* p, cudaStream_t stream);
 
 // ---- encode (encode.cu) --------------------------------------------------------------------------
@@ -195,6 +204,7 @@ bool tc_broadcast_supported(int C);
 int tc_broadcast_plan_create(const float* w_host, const float* bias_host, const void* x, void* act_out, int B, int C,
                              const float* scale, const float* shift, TcBcastPlan** out, bool op_f16 = false);
 void tc_broadcast_plan_destroy(TcBcastPlan* p);
+void tc_broadcast_plan_set_reverse(TcBcastPlan* p, bool reverse);
 int tc_broadcast_launch(const TcBcastPlan* p, cudaStream_t stream);
 
 // ---- heads (heads.cu) ------------------------------------------------------------------------------------

@@ -76,6 +76,7 @@ struct TcConvPlan {
   bool pair = false;      // tc_conv3x3_pair_kernel (CTA pairs, cta_group::2)
   int n_half = 0;         // pair kernel: output channels held per CTA
   bool staged = false;    // pair kernel: output leaves through per-warp smem staging + TMA stores (map_raw = the box map)
+  int reverse = 0;        // pair kernel: tile order (common.cuh, pair_tile_row0)
   int debug = 0;          // P3_TC_DEBUG ablation bits (perf experiments only; results are wrong when set)
   unsigned long long* trace = nullptr;  // P3_TC_TRACE: per-phase clock64 sums of one epilogue leader (perf experiments)
 };
@@ -675,7 +676,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                        int cin, int cout, int n_half, int stages, int staged, int tmem_cols, TcTaps tap,
                        __nv_bfloat16* __restrict__ act_out, const float* __restrict__ scale,
                        const float* __restrict__ shift, int act_mode, int debug, unsigned long long* trace,
-                       const __half* res, __half* raw, int f16) {
+                       const __half* res, __half* raw, int f16, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // P3_TC_TRACE: globaltimer stamps of CTA 0 (ns since its first instruction), summed over launches
@@ -711,6 +712,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int n0 = slice * N;
   const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
   const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
+  const int rev_last = reverse ? m_tiles - 1 : -1;
 
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
     s_scale[c] = act_mode == kActMishBN ? scale[n0 + c] : 1.0f;
@@ -756,7 +758,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = pair_in_slice; mt < m_tiles; mt += pairs_per_slice) {
-      const int m0 = pair_tile_row0(mt, static_cast<int>(rank));
+      const int m0 = pair_tile_row0(mt, static_cast<int>(rank), rev_last);
       for (int ks = 0; ks < k_slabs; ++ks) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -764,7 +766,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);  // ablation: no A traffic
           } else {
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kResABytes);
-            ptx::tma_load_2d_pair(smem_a + stage * kResABytes, &map_a, ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0),
+            ptx::tma_load_2d_pair_h<P3_HINT_ACT_LOAD>(smem_a + stage * kResABytes, &map_a, ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0),
                                   ks * kSlabK, m0 - kResHalo);
           }
         }
@@ -844,7 +846,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
       if (tr && iter == 0 && ew == 0 && lane == 0) atomicAdd(&trace[4], global_timer() - t_start);
-      const int m = pair_tile_row0(mt, static_cast<int>(rank)) + quarter * 32 + lane;
+      const int m = pair_tile_row0(mt, static_cast<int>(rank), rev_last) + quarter * 32 + lane;
       const bool in_range = m < rows;
       const bool live = in_range && row_is_live(m % kRowsPerPos);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * N + c0);
@@ -938,7 +940,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !(debug & 8)) {
-          ptx::tma_store_2d(&map_o64, nullptr, 0, 0, my_stage, n0 + c0, pair_tile_row0(mt, static_cast<int>(rank)) + quarter * 32);
+          ptx::tma_store_2d_h<P3_HINT_ACT_STORE>(&map_o64, my_stage, n0 + c0, pair_tile_row0(mt, static_cast<int>(rank), rev_last) + quarter * 32);
           ptx::bulk_commit();
         }
       }
@@ -1000,7 +1002,7 @@ int make_map_bf16_k64(CUtensorMap* map, const void* base, uint64_t dim0, uint64_
 
 typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int,
                              int, int, int, TcTaps, __nv_bfloat16*,
-                             const float*, const float*, int, int, unsigned long long*, const __half*, __half*, int);
+                             const float*, const float*, int, int, unsigned long long*, const __half*, __half*, int, int);
 PairKernelFn pair_kernel_for(int N, bool res = false) {
   switch (N) {
     case 128: return res ? tc_conv3x3_pair_kernel<32, true> : tc_conv3x3_pair_kernel<32, false>;
@@ -1194,6 +1196,12 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
   delete plan;
 }
 
+bool tc_conv_plan_set_reverse(TcConvPlan* p, bool reverse) {  // false: not a pair-kernel plan (its tile order is fixed)
+  if (!p || !p->pair) return false;
+  p->reverse = reverse ? 1 : 0;
+  return true;
+}
+
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
   const ConvEpilogue& ep = p->ep;
   if (p->pair) {
@@ -1202,7 +1210,7 @@ int tc_conv_launch(const TcConvPlan* p, cudaStream_t stream) {
                           p->map_raw, p->map_act, p->rows, p->cin, p->cout, p->n_half, p->stages, p->staged ? 1 : 0, p->tmem_cols,
                           p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale, ep.shift, ep.act_mode, p->debug & 0xff,
                           p->trace, reinterpret_cast<const __half*>(ep.residual), reinterpret_cast<__half*>(ep.raw_out),
-                          ep.op_f16 ? 1 : 0));
+                          ep.op_f16 ? 1 : 0, p->reverse));
   } else if (p->resident) {
     tc_conv3x3_res_kernel<<<p->grid, kResThreads, p->smem_bytes, stream>>>(
         p->map_a, p->map_w, p->rows, p->cin, p->cout, p->tap, reinterpret_cast<__nv_bfloat16*>(ep.act_out), ep.scale,

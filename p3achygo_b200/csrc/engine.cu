@@ -1014,6 +1014,30 @@ int build_engine(p3_engine& e, const WeightFile& wf) {
     mac += C * Ch * Pn + Ch * Pn + 2.0 * 2 * Ch * Cv + Cv * 66.0 + 2.0 * Ch * Cv + 2.0 * 800 * Cv;
     e.flops_per_pos = 2.0 * mac;
   }
+  // Tile order: consecutive pair-kernel launches walk the batch in opposite directions, so each starts on the rows its
+  // predecessor wrote last (still in L2).  The first layer walks upwards; kernels with a fixed order count as upwards.  P3_TILE_ALTERNATE=0 keeps every launch upwards.
+  {
+    const char* env_alt = std::getenv("P3_TILE_ALTERNATE");
+    const bool alternate = !(env_alt && std::atoi(env_alt) == 0);
+    bool prev_up = true;  // the first layer
+    for (Step& s : e.program) {
+      const bool want_rev = alternate && prev_up;
+      bool is_rev = false;
+      if (s.kind == kStepChain) {
+        tc_chain_plan_set_reverse(s.cplan, want_rev);
+        is_rev = want_rev;
+      } else if (s.kind == kStepConv && s.pplan) {
+        tc_pw_plan_set_reverse(s.pplan, want_rev);
+        is_rev = want_rev;
+      } else if (s.kind == kStepConv && e.bf16 && s.layer->plan) {
+        is_rev = tc_conv_plan_set_reverse(s.layer->plan, want_rev) && want_rev;
+      } else if (s.kind == kStepBroadcast && s.bplan) {
+        tc_broadcast_plan_set_reverse(s.bplan, want_rev);
+        is_rev = want_rev;
+      }
+      prev_up = !is_rev;
+    }
+  }
   e.launches = 2 + static_cast<int>(e.program.size()) + (e.head_fused ? 1 : 2);
   return P3_OK;
 }

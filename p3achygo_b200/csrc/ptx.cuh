@@ -127,6 +127,47 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void*, int,
                ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_src_addr), "r"(c0), "r"(c1)
                : "memory");
 }
+// ---- L2 cache hints on TMA traffic ---------------------------------------------------------------------------------------
+// Every activation tensor of the tower is written once and read once (by the next launch); the only re-read is the residual
+// stream, four launches later.  P3_HINT_ACT_LOAD / P3_HINT_ACT_STORE (0 = none, 1 = evict_first, 2 = evict_last, 3 = evict_normal)
+// choose the createpolicy-equivalent 64-bit descriptors below for those loads / stores (the values CUTLASS hard-codes for
+// createpolicy.fractional.L2::evict_*.b64 with fraction 1.0).
+#ifndef P3_HINT_ACT_LOAD
+#define P3_HINT_ACT_LOAD 0
+#endif
+#ifndef P3_HINT_ACT_STORE
+#define P3_HINT_ACT_STORE 0
+#endif
+#ifndef P3_HINT_RES_LOAD
+#define P3_HINT_RES_LOAD P3_HINT_ACT_LOAD
+#endif
+#ifndef P3_HINT_RES_STORE
+#define P3_HINT_RES_STORE P3_HINT_ACT_STORE
+#endif
+__host__ __device__ constexpr uint64_t l2_policy(int kind) {
+  return kind == 1 ? 0x12F0000000000000ull : kind == 2 ? 0x14F0000000000000ull : 0x1000000000000000ull;
+}
+template <int kHint>
+__device__ __forceinline__ void tma_load_2d_h(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1) {
+  if constexpr (kHint == 0) {
+    tma_load_2d(smem_dst, desc, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(l2_policy(kHint))
+        : "memory");
+  }
+}
+template <int kHint>
+__device__ __forceinline__ void tma_store_2d_h(const void* desc, uint32_t smem_src_addr, int32_t c0, int32_t c1) {
+  if constexpr (kHint == 0) {
+    tma_store_2d(desc, nullptr, 0, 0, smem_src_addr, c0, c1);
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_src_addr), "r"(c0), "r"(c1), "l"(l2_policy(kHint))
+                 : "memory");
+  }
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory SOURCE of all committed bulk stores has been read (staging reusable)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -247,6 +288,17 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* des
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
+}
+template <int kHint>
+__device__ __forceinline__ void tma_load_2d_pair_h(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  if constexpr (kHint == 0) {
+    tma_load_2d_pair(smem_dst, desc, bar_cluster_addr, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(l2_policy(kHint))
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)

@@ -35,7 +35,7 @@ constexpr int kPwMisc = 1024 /*align*/ + kPwBarRegion + 2 * kPwMaxN * 4;
 struct TcPwPlan {
   CUtensorMap map_a1, map_w1, map_res, map_raw, map_act;
   int rows = 0, k1 = 0, n1 = 0, n_tile = 0, a1_stages = 0, n_boxes = 0, grid = 0;
-  int has_res = 0, has_raw = 0, has_act = 0, act_mode = kActNone, f16 = 0;
+  int has_res = 0, has_raw = 0, has_act = 0, act_mode = kActNone, f16 = 0, reverse = 0;
   size_t smem_bytes = 0;
   const float *scale = nullptr, *shift = nullptr;
 };
@@ -53,7 +53,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
                   const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_raw,
                   const __grid_constant__ CUtensorMap map_act, int rows, int k1, int n1, int n_tile, int a1_stages, int n_boxes,
                   int has_res, int has_raw, int has_act, int act_mode, const float* __restrict__ scale,
-                  const float* __restrict__ shift, int f16) {
+                  const float* __restrict__ shift, int f16, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n_slabs = n_tile / 64;
@@ -80,6 +80,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const int n0 = slice * n_tile;
   const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
   const int m_tiles = pair_tile_count(rows);  // position-aligned pair tiles (common.cuh)
+  const int rev_last = reverse ? m_tiles - 1 : -1;
   const int n_it = pair_in_slice < m_tiles ? (m_tiles - pair_in_slice + pairs_per_slice - 1) / pairs_per_slice : 0;
   const int boxes_per_slab = (has_raw && has_act) ? 2 : 1;
 
@@ -132,12 +133,12 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int m0 = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank));
+      const int m0 = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank), rev_last);
       for (int ks = 0; ks < k1_slabs; ++ks) {
         ptx::mbar_wait(&a1_empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
           if (rank == 0) ptx::mbar_arrive_expect_tx(&a1_full[stage], 2 * kPwSlabBytes);
-          ptx::tma_load_2d_pair(smem_a1 + stage * kPwSlabBytes, &map_a1, ptx::mapa_shared(ptx::smem_u32(&a1_full[stage]), 0),
+          ptx::tma_load_2d_pair_h<P3_HINT_ACT_LOAD>(smem_a1 + stage * kPwSlabBytes, &map_a1, ptx::mapa_shared(ptx::smem_u32(&a1_full[stage]), 0),
                                 ks * 64, m0);
         }
         __syncwarp();
@@ -195,7 +196,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     const int steps_per_tile = n_slabs * boxes_per_slab;
     const uint32_t total_steps = static_cast<uint32_t>(n_it) * steps_per_tile;
     auto row_of = [&](uint32_t s) {
-      return pair_tile_row0(pair_in_slice + static_cast<int>(s / steps_per_tile) * pairs_per_slice, static_cast<int>(rank)) + q_row;
+      return pair_tile_row0(pair_in_slice + static_cast<int>(s / steps_per_tile) * pairs_per_slice, static_cast<int>(rank), rev_last) + q_row;
     };
     auto col_of = [&](uint32_t s) { return n0 + static_cast<int>((s % steps_per_tile) / boxes_per_slab) * 64; };
     auto prepare = [&](uint32_t s) {
@@ -203,7 +204,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       const uint32_t b = s % n_boxes;
       if (has_res && (s % boxes_per_slab) == 0) {
         ptx::mbar_arrive_expect_tx(&my_ready[b], kPwBoxBytes);
-        ptx::tma_load_2d(my_box + b * kPwBoxBytes, &map_res, &my_ready[b], col_of(s), row_of(s));
+        ptx::tma_load_2d_h<P3_HINT_RES_LOAD>(my_box + b * kPwBoxBytes, &map_res, &my_ready[b], col_of(s), row_of(s));
       } else {
         ptx::mbar_arrive(&my_ready[b]);
       }
@@ -216,7 +217,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       ptx::mbar_wait(&my_written[b], (s / n_boxes) & 1u);
       if (lane == 0) {
         const bool to_raw = has_raw && (s % boxes_per_slab) == 0;
-        ptx::tma_store_2d(to_raw ? &map_raw : &map_act, nullptr, 0, 0, ptx::smem_u32(my_box) + b * kPwBoxBytes, col_of(s), row_of(s));
+        ptx::tma_store_2d_h<P3_HINT_ACT_STORE>(to_raw ? &map_raw : &map_act, ptx::smem_u32(my_box) + b * kPwBoxBytes, col_of(s), row_of(s));
         ptx::bulk_commit();
         ptx::bulk_wait_read<1>();  // the previous box-step's store has read its box: it serves box-step s - 1 + n_boxes
         if (s > 0) prepare(s - 1 + n_boxes);
@@ -246,7 +247,7 @@ tc_pw_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
     };
     for (int it = 0; it < n_it; ++it) {
       const int as = it & 1;
-      const int m = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank)) + q * 32 + lane;
+      const int m = pair_tile_row0(pair_in_slice + it * pairs_per_slice, static_cast<int>(rank), rev_last) + q * 32 + lane;
       const bool live = m < rows && row_is_live(m % kRowsPerPos);
       ptx::mbar_wait(&acc_full[as], (static_cast<uint32_t>(it) >> 1) & 1u);
       ptx::tc_fence_after_sync();
@@ -415,11 +416,14 @@ int tc_pw_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w, int rows,
 }
 
 void tc_pw_plan_destroy(TcPwPlan* p) { delete p; }
+void tc_pw_plan_set_reverse(TcPwPlan* p, bool reverse) {
+  if (p) p->reverse = reverse ? 1 : 0;
+}
 
 int tc_pw_launch(const TcPwPlan* p, cudaStream_t stream) {
   P3_CUDA(tc_launch_pdl(tc_pw_pair_kernel, p->grid, kPwThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_res, p->map_raw,
                         p->map_act, p->rows, p->k1, p->n1, p->n_tile, p->a1_stages, p->n_boxes, p->has_res, p->has_raw, p->has_act,
-                        p->act_mode, p->scale, p->shift, p->f16));
+                        p->act_mode, p->scale, p->shift, p->f16, p->reverse));
   return P3_OK;
 }
 
