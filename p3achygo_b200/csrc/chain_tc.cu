@@ -50,6 +50,7 @@ struct TcChainPlan {
   // and `out` is written as fp32, channel-major [n2_valid, out_ld] (what heads.cu reads), straight from the registers
   int tail = 0, out_ld = 0, n2_valid = 0;
   int reverse = 0;                      // tile order (common.cuh, pair_tile_row0)
+  int l2pf = 0;                         // residual boxes are prefetched into L2 this many steps beyond the box pool's look-ahead
   float* out_t = nullptr;
   unsigned long long* trace = nullptr;  // P3_TC_TRACE
 };
@@ -76,7 +77,7 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
                      int n1, int n2, int acc2_stages, int a1_stages, int n_boxes, int tmem_cols, const float* __restrict__ scale1,
                      const float* __restrict__ shift1, const float* __restrict__ scale2, const float* __restrict__ shift2,
                      int act2_mode, unsigned long long* trace, int f16, int tail, float* __restrict__ out_t, int out_ld,
-                     int n2_valid, int reverse) {
+                     int n2_valid, int reverse, int l2pf) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int k1_slabs = k1 / 64, n1_slabs = n1 / 64, n2_slabs = n2 / 64;
@@ -296,12 +297,23 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         ptx::mbar_arrive(&my_ready[b]);
       }
     };
-    Cursor cur{0, 0, 0, 0, 0}, ahead{0, 0, 0, 0, 0};
+    Cursor cur{0, 0, 0, 0, 0}, ahead{0, 0, 0, 0, 0}, pf{0, 0, 0, 0, 0};
+    // shapes whose resident weights leave only 3 boxes per quarter (2 loads in flight) cannot cover the HBM latency from shared
+    // memory alone: their residual boxes are also prefetched into L2, l2pf steps further ahead
+    auto prefetch = [&](const Cursor& c) {
+      if (c.it < n_it && c.idx < n1_slabs)
+        ptx::tma_prefetch_2d(&map_res, c.idx * 64, pair_tile_row0(pair + c.it * n_pairs, static_cast<int>(rank), rev_last) + q_row);
+    };
     ptx::griddep_wait();  // residual loads / output stores touch buffers of the previous kernel
     if (n_it > 0) {
       for (int i = 0; i < n_boxes; ++i) {  // all boxes start out free
         if (lane == 0) prepare(ahead);
         advance(ahead);
+      }
+      pf = ahead;
+      for (int i = 0; i < l2pf; ++i) {
+        if (lane == 0) prefetch(pf);
+        advance(pf);
       }
     }
     uint32_t g = 0;
@@ -324,7 +336,13 @@ tc_chain_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_co
         if (cur.s > 0) prepare(ahead);
       }
       if (is_epi1) ++g;
-      if (cur.s > 0) advance(ahead);
+      if (cur.s > 0) {
+        advance(ahead);
+        if (l2pf > 0) {
+          if (lane == 0) prefetch(pf);
+          advance(pf);
+        }
+      }
       advance(cur);
       __syncwarp();
     }
@@ -568,6 +586,9 @@ int tc_chain_plan_create(const __nv_bfloat16* in, const __nv_bfloat16* w1, const
     }
     p->a1_stages = stages;
     p->n_boxes = boxes;
+    p->l2pf = boxes <= 3 ? 3 : 0;
+    if (const char* pf = std::getenv("P3_CHAIN_L2PF")) p->l2pf = boxes <= 3 ? std::max(0, std::atoi(pf)) : 0;
+    if (const char* pf = std::getenv("P3_CHAIN_L2PF_ALL")) p->l2pf = boxes <= 3 ? p->l2pf : std::max(0, std::atoi(pf));
     p->smem_bytes = static_cast<size_t>(chain_fixed_smem(k1, n1, n2)) + static_cast<size_t>(stages) * kChSlabBytes +
                     static_cast<size_t>(4 * boxes) * kChBoxBytes + 1024 + kChBarBytes;
   }
@@ -636,7 +657,7 @@ int tc_chain_launch(const TcChainPlan* p, cudaStream_t stream) {
   auto kern = p->trace ? tc_chain_pair_kernel<true> : tc_chain_pair_kernel<false>;
   P3_CUDA(tc_launch_pdl(kern, p->grid, kChThreads, p->smem_bytes, stream, p->map_a1, p->map_w1, p->map_w2, p->map_res, p->map_raw,
                         p->map_out2, p->rows, p->k1, p->n1, p->n2, p->acc2_stages, p->a1_stages, p->n_boxes, p->tmem_cols, p->scale1, p->shift1, p->scale2,
-                        p->shift2, p->act2_mode, p->trace, p->f16, p->tail, p->out_t, p->out_ld, p->n2_valid, p->reverse));
+                        p->shift2, p->act2_mode, p->trace, p->f16, p->tail, p->out_t, p->out_ld, p->n2_valid, p->reverse, p->l2pf));
   return P3_OK;
 }
 
