@@ -46,10 +46,8 @@ inline int tc_make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataTyp
 // Launch `kern` with programmatic stream serialization (see ptx::griddep_wait); P3_PDL=0 falls back to a plain launch.
 template <typename... KArgs, typename... Args>
 inline cudaError_t tc_launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
-  static const bool enabled = [] {
-    const char* e = std::getenv("P3_PDL");
-    return !(e && std::atoi(e) == 0);
-  }();
+  const char* pdl_env = std::getenv("P3_PDL");  // read per launch (launches are captured into a graph once per engine)
+  const bool enabled = !(pdl_env && std::atoi(pdl_env) == 0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(static_cast<unsigned>(block));

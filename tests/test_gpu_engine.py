@@ -503,6 +503,38 @@ def test_stream_padding_rows_stay_zero_over_repeated_runs(weight_dir, golden_pos
     assert not x[:, pad].any() and not a[:, pad].any()
 
 
+@pytest.mark.parametrize("config,B", [("b12c256btl3", 320), ("b10c128btl3", 200)])
+def test_scheduling_knobs_do_not_change_results(config, B, weight_dir, golden_positions, monkeypatch):
+    """Round-2 changes that only re-schedule the same arithmetic - alternating tile order between launches, the tower's end as
+    one launch, the shifted-view first layer, the L2 prefetch of the boundaries next to a broadcast block, CUDA graph / programmatic
+    dependent launch - must leave every output bit-identical: each is switched off in turn and compared with the default engine."""
+    from p3achygo_b200 import engine as E
+    path, cfg, tensors = weight_dir(config)
+    feats = golden_positions["feats"]
+    allf = feats[np.arange(B) % len(feats)]
+
+    def run():
+        eng = E.CreateEngine(E.Kind.kB200, path, B, 1, precision=E.PRECISION_BF16)
+        eng.LoadBatchAll(allf)
+        eng.RunInference()
+        eng.RunInference()
+        out = [eng.GetBatch(b).copy() for b in range(B)]
+        own = [np.asarray(eng.GetOwnership(b)).copy() for b in range(0, B, 37)]
+        eng.close()
+        return out, own
+
+    want, want_own = run()
+    for knob, val in (("P3_TILE_ALTERNATE", "0"), ("P3_TC_TAIL", "0"), ("P3_INIT_TC", "1"), ("P3_CHAIN_L2PF", "0"), ("P3_CUDA_GRAPH", "0"),
+                      ("P3_PDL", "0")):
+        monkeypatch.setenv(knob, val)
+        got, got_own = run()
+        monkeypatch.delenv(knob)
+        for b in range(B):
+            assert _same(got[b], want[b]), (knob, b)
+        for a, w in zip(got_own, want_own):
+            assert np.array_equal(a, w), knob
+
+
 # ---- compact leaf records, per-bank auxiliary outputs, ownership symmetry, root sampling on resident logits ---------------------
 @pytest.mark.parametrize("precision_name", ["fp32", "bf16"])
 def test_leaf_results_equal_initfields_of_full_results(precision_name, weight_dir, golden_positions):
