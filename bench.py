@@ -431,6 +431,12 @@ def main():
                      "achieved_GBps": prof["boundary"][3] / (prof["boundary"][0] * 1e-3) / 1e9 if prof["boundary"][0] else None,
                      "peak_GBps": peaks["hbm"],
                      "hbm_frac": prof["boundary"][3] / (prof["boundary"][0] * 1e-3) / 1e9 / peaks["hbm"] if prof["boundary"][0] else None,
+                     # avg_launch_ms is an eager pass with an event around every launch (no graph, nothing of a launch hidden under
+                     # its predecessor's tail); the graph-replayed step is shorter than the sum of that pass by this factor, and
+                     # the same factor applied to this class gives the in-step estimate
+                     "graph_over_eager": float(np.mean(ms_steps)) / step_ms if step_ms else None,
+                     "hbm_frac_in_graph_estimate": (prof["boundary"][3] / (prof["boundary"][0] * 1e-3 * float(np.mean(ms_steps)) / step_ms)
+                                                    / 1e9 / peaks["hbm"]) if prof["boundary"][0] and step_ms else None,
                      "traffic": chain_traffic},
         "class_hbm_frac": {k: (v[3] / (v[0] * 1e-3) / 1e9 / peaks["hbm"] if v[0] else None) for k, v in prof.items()},
         "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()},
