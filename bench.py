@@ -64,22 +64,39 @@ def kernel_source_hash() -> str:
 
 def selfplay_child(wpath: str, device: int, seconds: float):
     """Body of the self-play leg; runs in a child process (see selfplay_leg) and prints its result as one SELFPLAY_JSON line."""
-    path = os.path.join(ROOT, "oracle", "_ref", "libp3refnn.so")
-    L = ctypes.CDLL(path)
     ci = ctypes.c_int
-    L.ref_selfplay_gumbel.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, ctypes.POINTER(ctypes.c_longlong),
-                                      ctypes.POINTER(ctypes.c_double)]
-    runs = []
-    for n, k in ((96, 8), (600, 16)):   # default and selected n / k of config/v3-b12c256btl3-2000k-inf.json
+
+    def load(name):
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(path):
+            return None
+        L = ctypes.CDLL(path)
+        L.ref_selfplay_gumbel.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, ctypes.POINTER(ctypes.c_longlong),
+                                          ctypes.POINTER(ctypes.c_double)]
+        L.ref_selfplay_record_loads.restype = ctypes.c_longlong
+        return L
+
+    def run(L, n, k):
         out = (ctypes.c_longlong * 4)()
         secs = ctypes.c_double(0)
         rc = L.ref_selfplay_gumbel(wpath.encode(), device, 8, 128, n, k, seconds, 1 << 20, 300, out, ctypes.byref(secs))
         if rc != 0 or secs.value <= 0:
-            runs = None
-            break
-        runs.append({"n": n, "k": k, "moves": int(out[0]), "seconds": secs.value, "moves_per_s": out[0] / secs.value,
-                     "leaf_evals_per_s": out[1] / secs.value, "avg_engine_batch": out[1] / max(out[2], 1), "games_finished": int(out[3])})
-    print("SELFPLAY_JSON " + json.dumps(runs), flush=True)
+            return None
+        return {"n": n, "k": k, "moves": int(out[0]), "seconds": secs.value, "moves_per_s": out[0] / secs.value,
+                "leaf_evals_per_s": out[1] / secs.value, "avg_engine_batch": out[1] / max(out[2], 1), "games_finished": int(out[3]),
+                "slots_loaded_as_game_records": int(L.ref_selfplay_record_loads())}
+
+    L = load("libp3refnn.so")
+    runs = [run(L, n, k) for n, k in ((96, 8), (600, 16))]   # default and selected n / k of config/v3-b12c256btl3-2000k-inf.json
+    if any(r is None for r in runs):
+        runs = None
+    res = {"runs": runs}
+    # the same search over the reference with INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002): NNInterface::LoadBatch hands
+    # the game record to the engine, which derives board / liberties / laddered stones / last moves on the GPU (p3_engine_load_game_bank)
+    G = load("libp3refnn_gr.so")
+    if G is not None and runs is not None:
+        res["game_record_slots"] = [run(G, 96, 8)]
+    print("SELFPLAY_JSON " + json.dumps(res), flush=True)
 
 
 def selfplay_leg(wpath: str, device: int, seconds: float):
@@ -94,12 +111,16 @@ def selfplay_leg(wpath: str, device: int, seconds: float):
         return None
     cmd = [sys.executable, os.path.abspath(__file__), "--selfplay-child", wpath, str(device), str(seconds)]
     try:
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=4 * seconds + 240)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=6 * seconds + 300)
     except subprocess.TimeoutExpired:
         return {"error": "self-play child timed out"}
     for ln in p.stdout.splitlines():
         if ln.startswith("SELFPLAY_JSON "):
-            return json.loads(ln[len("SELFPLAY_JSON "):])
+            res = json.loads(ln[len("SELFPLAY_JSON "):])
+            if not res.get("runs"):
+                return {"error": "self-play harness returned an error"}
+            selfplay_leg.game_record_slots = res.get("game_record_slots")
+            return res["runs"]
     return {"error": f"self-play child exited {p.returncode}: {(p.stderr or '').strip().splitlines()[-1:]}"}
 
 
@@ -548,6 +569,13 @@ def main():
                                 "move from the empty board, NN cache 2^20 keyed on the last move (cc/selfplay/main.cc:177), timeout 400 us; "
                                 "Game -> GoFeatures (ladders, liberties) on the host cores as the reference does it; run in a child "
                                 "process"}
+            gr = getattr(selfplay_leg, "game_record_slots", None)
+            if gr and gr[0]:
+                selfplay["with_game_record_slots"] = {
+                    "runs": gr,
+                    "what": "the same harness over the reference with INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002-load-game-"
+                            "records.patch, 3 hunks): NNInterface::LoadBatch hands the move list to nn::Engine::LoadGameRecord and the engine "
+                            "derives board, liberty grids, laddered stones and last moves on the GPU; this rank only"}
         elif isinstance(sp, dict):
             selfplay = sp  # {"error": ...}: the child failed on this rank
         elif sp is not None:

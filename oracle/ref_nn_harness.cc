@@ -77,6 +77,15 @@ class CheckedEngine final : public nn::Engine {
     served.fetch_add(1, std::memory_order_relaxed);
   }
   void GetOwnership(int t, std::array<float, constants::kNumBoardLocs>& own) override { inner_->GetOwnership(t, own); }
+#ifdef P3_REF_GAME_RECORDS  // built against the reference with INTEGRATION.md's edit 2 (oracle/ref_patches/0002): slots as game records
+  bool LoadGameRecord(int t, const int16_t* moves, int n, int color, float komi, int sym) override {
+    load_gen_[t].store(generation_.load(std::memory_order_acquire), std::memory_order_release);
+    const bool ok = inner_->LoadGameRecord(t, moves, n, color, komi, sym);
+    if (ok) g_record_loads.fetch_add(1, std::memory_order_relaxed);
+    return ok;
+  }
+#endif
+  static std::atomic<long long> g_record_loads;
 
   std::atomic<long long> race{0}, stale{0}, served{0}, runs{0};
 
@@ -86,6 +95,8 @@ class CheckedEngine final : public nn::Engine {
   std::atomic<bool> in_run_{false};
   std::vector<std::atomic<int>> load_gen_, result_gen_, loaded_in_run_;
 };
+
+std::atomic<long long> CheckedEngine::g_record_loads{0};
 
 // Debug stand-in (weights_path == "null"): lets the harness itself run without a GPU, like the NullEngine of the reference's
 // cc/mcts/__tests__/search_test.cc.  Uniform-ish policy, even value.  Never used for a reported number.
@@ -110,6 +121,23 @@ class NullEngine final : public nn::Engine {
   }
   void GetOwnership(int, std::array<float, constants::kNumBoardLocs>& own) override { own.fill(0.0f); }
 };
+// Decorator that declines game records: with the patched NNInterface (edit 2) the serial reference evaluation of
+// ref_nn_b200_sync then takes the GoFeatures path - host-side features, host-side symmetry - while the workers' slots are loaded as
+// records, so `differ == 0` says the two paths give the same NNInferResult bit for bit THROUGH NNInterface.
+class FeaturesOnlyEngine final : public nn::Engine {
+ public:
+  explicit FeaturesOnlyEngine(std::unique_ptr<nn::Engine> inner) : inner_(std::move(inner)) {}
+  Kind kind() override { return inner_->kind(); }
+  std::string path() override { return inner_->path(); }
+  void LoadBatch(int t, const nn::GoFeatures& f) override { inner_->LoadBatch(t, f); }
+  void RunInference() override { inner_->RunInference(); }
+  void GetBatch(int t, nn::NNInferResult& r) override { inner_->GetBatch(t, r); }
+  void GetOwnership(int t, std::array<float, constants::kNumBoardLocs>& own) override { inner_->GetOwnership(t, own); }
+
+ private:
+  std::unique_ptr<nn::Engine> inner_;
+};
+
 std::unique_ptr<nn::Engine> MakeEngine(const char* weights_path, int batch, int device) {
   if (std::strcmp(weights_path, "null") == 0) return std::make_unique<NullEngine>();
   return nn::B200Engine::Create(weights_path, batch, 1, device);
@@ -188,7 +216,7 @@ int ref_nn_b200_sync(const char* weights_path, int device, int threads, int iter
   // inline when num_threads == 1, nn_interface.h:295-297); the engine's results do not depend on batch size or slot
   long long differ = 0, compared = 0;
   {
-    nn::NNInterface serial(1, timeout_us, 0, nn::B200Engine::Create(weights_path, 4, 1, device));
+    nn::NNInterface serial(1, timeout_us, 0, std::make_unique<FeaturesOnlyEngine>(nn::B200Engine::Create(weights_path, 4, 1, device)));
     const int stride = std::max(1, (threads * iters) / 512);  // compare up to ~512 results
     for (int idx = 0; idx < threads * iters; idx += stride) {
       const int tid = idx / iters, it = idx % iters;
@@ -203,6 +231,12 @@ int ref_nn_b200_sync(const char* weights_path, int device, int threads, int iter
   return 0;
 }
 
+// slots ref_nn_b200_sync / ref_selfplay_gumbel have loaded as game records since the last ref_selfplay_gumbel started
+long long ref_record_loads() { return CheckedEngine::g_record_loads.load(); }
+
+// slots the last ref_selfplay_gumbel loaded as game records (0 unless built with -DP3_REF_GAME_RECORDS on the patched reference)
+long long ref_selfplay_record_loads() { return CheckedEngine::g_record_loads.load(); }
+
 // Self-play throughput through the reference's own search: `interfaces` NNInterfaces (each over its own B200 engine with
 // `threads` slots, timeout 400 us, cache `cache_size` keyed on the last move as cc/selfplay/main.cc:177 does) on one GPU, one game
 // thread per slot playing from the empty board with GumbelEvaluator::SearchRoot(n, k) per move, for `seconds` of wall time.
@@ -211,6 +245,7 @@ int ref_nn_b200_sync(const char* weights_path, int device, int threads, int iter
 int ref_selfplay_gumbel(const char* weights_path, int device, int interfaces, int threads, int n, int k, double seconds,
                         int cache_size, int max_moves_per_game, long long* out, double* secs_out) {
   if (interfaces < 1 || threads < 2 || threads > constants::kMaxNumThreads) return -1;
+  CheckedEngine::g_record_loads.store(0);
   std::vector<CheckedEngine*> checked(interfaces);
   std::vector<std::unique_ptr<nn::NNInterface>> ifaces(interfaces);
   for (int i = 0; i < interfaces; ++i) {

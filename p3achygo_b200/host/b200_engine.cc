@@ -46,6 +46,9 @@ void B200Engine::LoadGameBank(int bank, int batch_id, const int16_t* moves, int 
                               const int8_t* forbidden, int sym) {
   P3_CHECK(p3_engine_load_game_bank(engine_, bank, batch_id, moves, num_moves, color, komi, forbidden, sym));
 }
+bool B200Engine::LoadGameRecord(int batch_id, const int16_t* moves, int num_moves, int color_to_move, float komi, int sym) {
+  return p3_engine_load_game_bank(engine_, 0, batch_id, moves, num_moves, color_to_move, komi, nullptr, sym) == P3_OK;
+}
 void B200Engine::Submit(int bank) { P3_CHECK(p3_engine_submit(engine_, bank)); }
 void B200Engine::Wait(int bank) { P3_CHECK(p3_engine_wait(engine_, bank)); }
 void B200Engine::GetBatchBank(int bank, int batch_id, NNInferResult& result) {

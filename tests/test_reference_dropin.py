@@ -73,6 +73,45 @@ def test_unmodified_nninterface_on_b200_engine(wake, dual, records, weight_dir):
     assert served == 128 * 12 and compared >= 256 and runs >= 12   # cache off: every call reached the engine; partial batches => runs > iters
 
 
+REFNN_GR = os.path.join(ROOT, "oracle", "_ref", "libp3refnn_gr.so")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_patched_nn_interface_loads_slots_as_game_records(weight_dir, records):
+    """INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002-load-game-records.patch): NNInterface::LoadBatch hands the move
+    list to nn::Engine::LoadGameRecord and the engine derives board, liberty grids, laddered stones and last moves on the GPU; the
+    slot's result comes back un-rotated.  The reference's sync scenario over that build, with the serial re-evaluation forced onto
+    the GoFeatures path (FeaturesOnlyEngine): every worker slot was a record, and every NNInferResult equals the host-features one
+    bit for bit - through the reference's own NNInterface, random symmetries included.  Then the Gumbel self-play harness on it."""
+    if not os.path.exists(REFNN_GR):
+        pytest.skip("oracle/_ref/libp3refnn_gr.so not built")
+    L = ctypes.CDLL(REFNN_GR)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.ref_nn_b200_sync.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ctypes.POINTER(ctypes.c_longlong)]
+    L.ref_selfplay_gumbel.argtypes = [ctypes.c_char_p, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, ctypes.POINTER(ctypes.c_longlong),
+                                      ctypes.POINTER(ctypes.c_double)]
+    L.ref_record_loads.restype = ctypes.c_longlong
+    L.ref_selfplay_record_loads.restype = ctypes.c_longlong
+    path, cfg, tensors = weight_dir("b10c128btl3")
+    mv, nm, col = records
+    out = (ctypes.c_longlong * 6)()
+    before = L.ref_record_loads()
+    rc = L.ref_nn_b200_sync(path.encode(), 0, 64, 10, 200, 1, 0, 0, mv.ctypes.data_as(vp), nm.ctypes.data_as(vp),
+                            col.ctypes.data_as(vp), mv.shape[1], len(mv), out)
+    race, stale, differ, runs, served, compared = list(out)
+    loaded = L.ref_record_loads() - before
+    print(f"record slots: runs {runs}, served {served}, compared {compared}, loaded as records {loaded}")
+    assert rc == 0 and (race, stale, differ) == (0, 0, 0)
+    assert served == 64 * 10 and loaded == served and compared >= 256
+    out4 = (ctypes.c_longlong * 4)()
+    secs = ctypes.c_double(0)
+    rc = L.ref_selfplay_gumbel(path.encode(), 0, 2, 32, 16, 4, 4.0, 1 << 16, 40, out4, ctypes.byref(secs))
+    moves, served, runs, games = list(out4)
+    print(f"self-play on record slots: {moves} moves, {served} leaf evals, {L.ref_selfplay_record_loads()} record loads")
+    assert rc == 0 and moves > 64 and L.ref_selfplay_record_loads() >= served > moves
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
 def test_gumbel_search_root_runs_on_b200_engine(weight_dir):
