@@ -91,7 +91,7 @@ def selfplay_child(wpath: str, device: int, seconds: float):
     if any(r is None for r in runs):
         runs = None
     res = {"runs": runs}
-    # the same search over the reference with INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002): NNInterface::LoadBatch hands
+    # the same search over the reference with INTEGRATION.md's optional edit 5 (oracle/ref_patches/0002): NNInterface::LoadBatch hands
     # the game record to the engine, which derives board / liberties / laddered stones / last moves on the GPU (p3_engine_load_game_bank)
     G = load("libp3refnn_gr.so")
     if G is not None and runs is not None:
@@ -573,7 +573,7 @@ def main():
             if gr and gr[0]:
                 selfplay["with_game_record_slots"] = {
                     "runs": gr,
-                    "what": "the same harness over the reference with INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002-load-game-"
+                    "what": "the same harness over the reference with INTEGRATION.md's optional edit 5 (oracle/ref_patches/0002-load-game-"
                             "records.patch, 3 hunks): NNInterface::LoadBatch hands the move list to nn::Engine::LoadGameRecord and the engine "
                             "derives board, liberty grids, laddered stones and last moves on the GPU; this rank only"}
         elif isinstance(sp, dict):

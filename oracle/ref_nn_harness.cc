@@ -77,7 +77,7 @@ class CheckedEngine final : public nn::Engine {
     served.fetch_add(1, std::memory_order_relaxed);
   }
   void GetOwnership(int t, std::array<float, constants::kNumBoardLocs>& own) override { inner_->GetOwnership(t, own); }
-#ifdef P3_REF_GAME_RECORDS  // built against the reference with INTEGRATION.md's edit 2 (oracle/ref_patches/0002): slots as game records
+#ifdef P3_REF_GAME_RECORDS  // built against the reference with INTEGRATION.md's optional edit 5 (oracle/ref_patches/0002): slots as game records
   bool LoadGameRecord(int t, const int16_t* moves, int n, int color, float komi, int sym) override {
     load_gen_[t].store(generation_.load(std::memory_order_acquire), std::memory_order_release);
     const bool ok = inner_->LoadGameRecord(t, moves, n, color, komi, sym);
@@ -121,7 +121,7 @@ class NullEngine final : public nn::Engine {
   }
   void GetOwnership(int, std::array<float, constants::kNumBoardLocs>& own) override { own.fill(0.0f); }
 };
-// Decorator that declines game records: with the patched NNInterface (edit 2) the serial reference evaluation of
+// Decorator that declines game records: with the patched NNInterface (optional edit 5) the serial reference evaluation of
 // ref_nn_b200_sync then takes the GoFeatures path - host-side features, host-side symmetry - while the workers' slots are loaded as
 // records, so `differ == 0` says the two paths give the same NNInferResult bit for bit THROUGH NNInterface.
 class FeaturesOnlyEngine final : public nn::Engine {

@@ -30,7 +30,7 @@ class B200Engine final : public Engine {
   // NNInterface::LoadBatch from the game record (nn_interface.cc:245-277): moves as p3_game_derive encodes them; the board, the
   // liberty grids, the laddered stones and the last moves are derived on the GPU by the next run of that bank.
   void LoadGameBank(int bank, int batch_id, const int16_t* moves, int num_moves, int color, float komi, const int8_t* forbidden, int sym);
-  // The same for the serial RunInference cycle, in the shape of INTEGRATION.md's optional edit 2 (nn::Engine::LoadGameRecord, a
+  // The same for the serial RunInference cycle, in the shape of INTEGRATION.md's optional edit 5 (nn::Engine::LoadGameRecord, a
   // virtual with a `return false` default that NNInterface::LoadBatch tries before it computes GoFeatures on the host): overrides
   // it where the base class has it.  Pass-alive regions are derived from the record; results come back un-rotated.
   // false = not loaded (record too long, ...): the caller falls back to LoadBatch.

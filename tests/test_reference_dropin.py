@@ -79,7 +79,7 @@ REFNN_GR = os.path.join(ROOT, "oracle", "_ref", "libp3refnn_gr.so")
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
 def test_patched_nn_interface_loads_slots_as_game_records(weight_dir, records):
-    """INTEGRATION.md's optional edit 2 (oracle/ref_patches/0002-load-game-records.patch): NNInterface::LoadBatch hands the move
+    """INTEGRATION.md's optional edit 5 (oracle/ref_patches/0002-load-game-records.patch): NNInterface::LoadBatch hands the move
     list to nn::Engine::LoadGameRecord and the engine derives board, liberty grids, laddered stones and last moves on the GPU; the
     slot's result comes back un-rotated.  The reference's sync scenario over that build, with the serial re-evaluation forced onto
     the GoFeatures path (FeaturesOnlyEngine): every worker slot was a record, and every NNInferResult equals the host-features one
