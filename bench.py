@@ -76,13 +76,14 @@ def selfplay_child(wpath: str, device: int, seconds: float):
         L.ref_selfplay_record_loads.restype = ctypes.c_longlong
         return L
 
-    def run(L, n, k):
+    def run(L, n, k, interfaces=8, slots=128):
         out = (ctypes.c_longlong * 4)()
         secs = ctypes.c_double(0)
-        rc = L.ref_selfplay_gumbel(wpath.encode(), device, 8, 128, n, k, seconds, 1 << 20, 300, out, ctypes.byref(secs))
+        rc = L.ref_selfplay_gumbel(wpath.encode(), device, interfaces, slots, n, k, seconds, 1 << 20, 300, out, ctypes.byref(secs))
         if rc != 0 or secs.value <= 0:
             return None
-        return {"n": n, "k": k, "moves": int(out[0]), "seconds": secs.value, "moves_per_s": out[0] / secs.value,
+        return {"n": n, "k": k, "interfaces": interfaces, "slots_per_interface": slots, "moves": int(out[0]), "seconds": secs.value,
+                "moves_per_s": out[0] / secs.value,
                 "leaf_evals_per_s": out[1] / secs.value, "avg_engine_batch": out[1] / max(out[2], 1), "games_finished": int(out[3]),
                 "slots_loaded_as_game_records": int(L.ref_selfplay_record_loads())}
 
@@ -95,7 +96,9 @@ def selfplay_child(wpath: str, device: int, seconds: float):
     # the game record to the engine, which derives board / liberties / laddered stones / last moves on the GPU (p3_engine_load_game_bank)
     G = load("libp3refnn_gr.so")
     if G is not None and runs is not None:
-        res["game_record_slots"] = [run(G, 96, 8)]
+        res["game_record_slots"] = [run(G, 96, 8), run(G, 96, 8, 8, 256)]
+    if runs is not None:  # kMaxNumThreads slots per interface (cc/constants/constants.h:78) instead of 128: fuller engine batches
+        res["runs_256_slots"] = [run(L, 96, 8, 6, 256)]
     print("SELFPLAY_JSON " + json.dumps(res), flush=True)
 
 
@@ -111,7 +114,7 @@ def selfplay_leg(wpath: str, device: int, seconds: float):
         return None
     cmd = [sys.executable, os.path.abspath(__file__), "--selfplay-child", wpath, str(device), str(seconds)]
     try:
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=6 * seconds + 300)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=10 * seconds + 300)
     except subprocess.TimeoutExpired:
         return {"error": "self-play child timed out"}
     for ln in p.stdout.splitlines():
@@ -120,6 +123,7 @@ def selfplay_leg(wpath: str, device: int, seconds: float):
             if not res.get("runs"):
                 return {"error": "self-play harness returned an error"}
             selfplay_leg.game_record_slots = res.get("game_record_slots")
+            selfplay_leg.runs_256 = res.get("runs_256_slots")
             return res["runs"]
     return {"error": f"self-play child exited {p.returncode}: {(p.stderr or '').strip().splitlines()[-1:]}"}
 
@@ -569,6 +573,9 @@ def main():
                                 "move from the empty board, NN cache 2^20 keyed on the last move (cc/selfplay/main.cc:177), timeout 400 us; "
                                 "Game -> GoFeatures (ladders, liberties) on the host cores as the reference does it; run in a child "
                                 "process"}
+            r256 = getattr(selfplay_leg, "runs_256", None)
+            if r256 and r256[0]:
+                selfplay["runs_256_slots_per_interface"] = r256  # unmodified reference, 6 interfaces x 256 slots; this rank only
             gr = getattr(selfplay_leg, "game_record_slots", None)
             if gr and gr[0]:
                 selfplay["with_game_record_slots"] = {
